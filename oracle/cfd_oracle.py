@@ -1,0 +1,312 @@
+"""
+oracle/cfd_oracle.py -- Python face of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module (see oracle/README.md).  The product package never does, and has no CPU path.
+
+Three independent checkers live here:
+
+  port   ctypes binding of oracle/cfd_oracle.c (our plain-C restatement; OpenMP over lines).
+  ref    ctypes binding of oracle/_ref/libnpts_ref.so = the reference's own
+         lanl-implementation/npts.c compiled UNMODIFIED against the one-rank mpi.h stand-in
+         (oracle/Makefile `ref`).  Present only where it was built (this container; it travels to
+         the GPU box as a git-ignored artefact).
+  scipy  the banded-LU form every reference test compares with
+         (code/cuda/compact.py:189-203 `scipy_solve_banded`).
+
+plus a NumPy restatement of the reference's multi-rank partition algebra
+(code/cuda/compact.py:65-154) used to check the z-partitioned path.
+
+Parity of the oracle itself is pinned in tests/test_oracle.py (golden known-answer values of
+lanl-implementation/test_npts.c, port == ref == scipy to 1e-14, committed fixtures).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT_SO = os.path.join(_HERE, "liboracle_port.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libnpts_ref.so")
+REF_TEST_BIN = os.path.join(_HERE, "_ref", "test_npts.run")
+REF_TIME_BIN = os.path.join(_HERE, "_ref", "time_npts.run")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (always) and the reference's npts (when /root/reference exists)."""
+    if force or not os.path.exists(_PORT_SO) or os.path.getmtime(_PORT_SO) < os.path.getmtime(
+            os.path.join(_HERE, "cfd_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+    if os.path.isdir("/root/reference/lanl-implementation") and (force or not os.path.exists(_REF_SO)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+
+
+_port = None
+
+
+def port():
+    global _port
+    if _port is None:
+        build()
+        lib = ctypes.CDLL(_PORT_SO)
+        i, d = ctypes.c_int, ctypes.c_double
+        lib.oracle_rhs.argtypes = [_dp, _dp, i, i, i, i, d, _dp, _dp]
+        lib.oracle_npts_beta_gam.argtypes = [i, _dp, _dp]
+        lib.oracle_npts_solve.argtypes = [_dp, _dp, i, i, i, i, _dp, _dp]
+        lib.oracle_near_toeplitz_solve.argtypes = [_dp, i, i, i, i, _dp]
+        lib.oracle_cr_solve.argtypes = [_dp, ctypes.c_long, i, _dp]
+        lib.oracle_pthomas.argtypes = [_dp, _dp, _dp, _dp, i, ctypes.c_long]
+        lib.oracle_derivative.argtypes = [_dp, _dp, i, i, i, i, d]
+        lib.oracle_num_threads.restype = i
+        lib.oracle_set_num_threads.argtypes = [i]
+        for fn in ("oracle_rhs", "oracle_npts_beta_gam", "oracle_npts_solve", "oracle_near_toeplitz_solve",
+                   "oracle_cr_solve", "oracle_pthomas", "oracle_derivative", "oracle_set_num_threads"):
+            getattr(lib, fn).restype = None
+        _port = lib
+    return _port
+
+
+def have_ref() -> bool:
+    return os.path.exists(_REF_SO)
+
+
+_ref = None
+
+
+def ref():
+    """The reference's own npts.c (lanl-implementation/npts.h:6-9), one rank."""
+    global _ref
+    if _ref is None:
+        lib = ctypes.CDLL(_REF_SO)
+        i = ctypes.c_int
+        lib.precompute_beta_gam.argtypes = [i, i, i, i, _dp, _dp]
+        lib.precompute_beta_gam.restype = None
+        lib.nonperiodic_tridiagonal_solver.argtypes = [i, i, i, i, _dp, _dp, _dp, _dp, _dp, _dp]
+        lib.nonperiodic_tridiagonal_solver.restype = None
+        _ref = lib
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------------
+# port wrappers
+# ------------------------------------------------------------------------------------------------
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def rhs(f, axis, h, halo_lo=None, halo_hi=None):
+    f = _c(f)
+    nz, ny, nx = f.shape
+    out = np.empty_like(f)
+    hl = _c(halo_lo).ravel() if halo_lo is not None else None
+    hh = _c(halo_hi).ravel() if halo_hi is not None else None
+    port().oracle_rhs(_ptr(f), _ptr(out), nz, ny, nx, axis, float(h), _ptr(hl), _ptr(hh))
+    return out
+
+
+def npts_beta_gam(n):
+    beta, gam = np.empty(n), np.empty(n)
+    port().oracle_npts_beta_gam(n, _ptr(beta), _ptr(gam))
+    return beta, gam
+
+
+def npts_solve(r, axis):
+    r = _c(r)
+    nz, ny, nx = r.shape
+    beta, gam = npts_beta_gam(r.shape[2 - axis])
+    u = np.empty_like(r)
+    port().oracle_npts_solve(_ptr(r), _ptr(u), nz, ny, nx, axis, _ptr(beta), _ptr(gam))
+    return u
+
+
+def derivative(f, axis, h):
+    """RHS + npts solve on one rank: the reference CPU path (test_npts.c:86-97,126)."""
+    f = _c(f)
+    nz, ny, nx = f.shape
+    df = np.empty_like(f)
+    port().oracle_derivative(_ptr(f), _ptr(df), nz, ny, nx, axis, float(h))
+    return df
+
+
+def near_toeplitz_solve(d, coeffs, axis=0):
+    d = _c(d).copy()
+    nz, ny, nx = d.shape
+    co = _c(coeffs)
+    port().oracle_near_toeplitz_solve(_ptr(d), nz, ny, nx, axis, _ptr(co))
+    return d
+
+
+def cr_solve(d, coeffs):
+    """The reference GPU solver's own cyclic-reduction algorithm, x lines only."""
+    d = _c(d).copy()
+    n = d.shape[-1]
+    co = _c(coeffs)
+    port().oracle_cr_solve(_ptr(d), d.size // n, n, _ptr(co))
+    return d
+
+
+def pthomas(a, b, c, d):
+    """d is [n, ...]: systems strided by prod(d.shape[1:]) (code/cuda/kernels.cu:115-145)."""
+    d = _c(d).copy()
+    n = d.shape[0]
+    a, b, c = _c(a), _c(b), _c(c)
+    port().oracle_pthomas(_ptr(a), _ptr(b), _ptr(c), _ptr(d), n, d.size // n)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# reference (unmodified npts.c) wrappers
+# ------------------------------------------------------------------------------------------------
+def ref_npts_solve(r):
+    """x-lines of r[nz,ny,nx] through the reference's nonperiodic_tridiagonal_solver, 1 rank."""
+    r = _c(r)
+    nz, ny, nx = r.shape
+    beta, gam = np.zeros(nx), np.zeros(nx)
+    ref().precompute_beta_gam(0, nx, ny, nz, _ptr(beta), _ptr(gam))
+    u, phi, psi = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    # PRINT_TIMINGS (options.h:1) makes the solver print eight timing lines to fd 1; silence them.
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        ref().nonperiodic_tridiagonal_solver(0, nx, ny, nz, _ptr(beta), _ptr(gam), _ptr(r), _ptr(u),
+                                             _ptr(phi), _ptr(psi))
+        ctypes.CDLL(None).fflush(None)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    return u, beta, gam
+
+
+def ref_known_answer(n):
+    """`Average absolute error` printed by the reference's test_npts (test_npts.c:146-157)."""
+    out = subprocess.check_output([REF_TEST_BIN, str(n), str(n), str(n), "1", "1", "1"], text=True)
+    return out.strip().splitlines()[-1]
+
+
+# ------------------------------------------------------------------------------------------------
+# scipy: the ground truth of the reference's own tests
+# ------------------------------------------------------------------------------------------------
+def banded_abc(n, coeffs):
+    b1, c1, ai, bi, ci, an, bn = coeffs
+    a = np.full(n, float(ai)); b = np.full(n, float(bi)); c = np.full(n, float(ci))
+    b[0], c[0], a[-1], b[-1] = b1, c1, an, bn
+    return a, b, c
+
+
+def scipy_solve_banded(a, b, c, rhs_):
+    """Same banded layout as code/cuda/compact.py:189-203; rhs_ may be [n] or [n, m]."""
+    from scipy.linalg import solve_banded
+    ab = np.vstack([np.append(0, c[:-1]), b, np.append(a[1:], 0)])
+    return solve_banded((1, 1), ab, rhs_)
+
+
+PADE = (1., 2., 1. / 4, 1., 1. / 4, 2., 1.)
+
+
+def scipy_solve_axis(d, coeffs, axis):
+    """Solve along `axis` (0=x,1=y,2=z) of d[nz,ny,nx] with LAPACK's banded LU."""
+    d = _c(d)
+    ax = 2 - axis
+    n = d.shape[ax]
+    a, b, c = banded_abc(n, coeffs)
+    m = np.moveaxis(d, ax, 0).reshape(n, -1)
+    x = scipy_solve_banded(a, b, c, m)
+    return np.ascontiguousarray(np.moveaxis(x.reshape(np.moveaxis(d, ax, 0).shape), 0, ax))
+
+
+def scipy_derivative(f, axis, h):
+    return scipy_solve_axis(rhs(f, axis, h), PADE, axis)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-rank partition method of the reference, restated in NumPy (serial emulation of P ranks)
+# ------------------------------------------------------------------------------------------------
+def partition_local_coeffs(rank, size):
+    """code/cuda/compact.py:159-166: interior blocks are pure Toeplitz, ends carry the closures."""
+    co = [1., 1. / 4, 1. / 4, 1., 1. / 4, 1. / 4, 1.]
+    if rank == 0:
+        co[1] = 2.
+    if rank == size - 1:
+        co[5] = 2.
+    return co
+
+
+def partition_secondary(n, rank, size):
+    """Unit responses x_UH, x_LH of the local matrix (code/cuda/compact.py:128-154)."""
+    a = np.full(n, .25); b = np.ones(n); c = np.full(n, .25)
+    if rank == 0:
+        c[0], a[0] = 2.0, 0.0
+    if rank == size - 1:
+        a[-1], c[-1] = 2.0, 0.0
+    r_uh, r_lh = np.zeros(n), np.zeros(n)
+    r_uh[0] = -a[0]
+    r_lh[-1] = -c[-1]
+    return scipy_solve_banded(a, b, c, r_uh), scipy_solve_banded(a, b, c, r_lh)
+
+
+def partition_reduced_matrix(n_local, size):
+    """a, b, c of the 2P x 2P interface system (code/cuda/compact.py:96-111)."""
+    uh = np.zeros(2 * size); lh = np.zeros(2 * size)
+    for r in range(size):
+        x_uh, x_lh = partition_secondary(n_local, r, size)
+        uh[2 * r], uh[2 * r + 1] = x_uh[0], x_uh[-1]
+        lh[2 * r], lh[2 * r + 1] = x_lh[0], x_lh[-1]
+    a = np.zeros(2 * size); b = np.zeros(2 * size); c = np.zeros(2 * size)
+    a[0::2] = -1.; a[1::2] = uh[1::2]
+    b[0::2] = uh[0::2]; b[1::2] = lh[1::2]
+    c[0::2] = lh[0::2]; c[1::2] = -1.
+    a[0] = c[0] = 0.; b[0] = 1.
+    a[-1] = c[-1] = 0.; b[-1] = 1.
+    a[1] = 0.; c[-2] = 0.
+    return a, b, c
+
+
+def partition_derivative(f, axis, h, size):
+    """
+    Emulate the reference's P-rank derivative along `axis` on one process
+    (code/cuda/compact.py:29-44): halo -> local RHS -> local solve -> interface system -> sum.
+    Returns the assembled global derivative; equals scipy_derivative(f) up to round-off.
+    """
+    f = _c(f)
+    ax = 2 - axis
+    fm = np.moveaxis(f, ax, 0)                       # [N, ...]
+    N = fm.shape[0]
+    assert N % size == 0
+    n = N // size
+    rest = fm.shape[1:]
+    x_r, faces = [], np.zeros((2 * size,) + rest)
+    for r in range(size):
+        blk = fm[r * n:(r + 1) * n]
+        # RHS with ghost points (code/cuda/kernels.cu:34-44)
+        rr = np.empty_like(blk)
+        lo = fm[r * n - 1] if r > 0 else None
+        hi = fm[(r + 1) * n] if r < size - 1 else None
+        rr[1:-1] = (3. / (4 * h)) * (blk[2:] - blk[:-2])
+        rr[0] = (3. / (4 * h)) * (blk[1] - lo) if r > 0 else (1. / (2 * h)) * (-5 * blk[0] + 4 * blk[1] + blk[2])
+        rr[-1] = (3. / (4 * h)) * (hi - blk[-2]) if r < size - 1 else \
+            -(1. / (2 * h)) * (-5 * blk[-1] + 4 * blk[-2] + blk[-3])
+        a, b, c = banded_abc(n, partition_local_coeffs(r, size))
+        xr = scipy_solve_banded(a, b, c, rr.reshape(n, -1)).reshape(rr.shape)
+        x_r.append(xr)
+        # negateAndCopyFaces (code/cuda/kernels.cu:76-113)
+        faces[2 * r] = 0. if r == 0 else -xr[0]
+        faces[2 * r + 1] = 0. if r == size - 1 else -xr[-1]
+    ra, rb, rc = partition_reduced_matrix(n, size)
+    sol = scipy_solve_banded(ra, rb, rc, faces.reshape(2 * size, -1)).reshape(faces.shape)
+    out = np.empty_like(fm)
+    for r in range(size):
+        x_uh, x_lh = partition_secondary(n, r, size)
+        sh = (n,) + (1,) * len(rest)
+        out[r * n:(r + 1) * n] = x_r[r] + sol[2 * r] * x_uh.reshape(sh) + sol[2 * r + 1] * x_lh.reshape(sh)
+    return np.ascontiguousarray(np.moveaxis(out, 0, ax))
