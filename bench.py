@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the compact-derivative path (BASELINE.json metric:
+"grid points/sec per derivative (fp64), 1/2/4/8 B200, % of HBM roofline").
+
+    python bench.py --gpus 1 --steps K --warmup W          512^3 fp64, derivative along x, y and z (configs[2])
+    torchrun ... bench.py --gpus N ...                     1024^3 fp64 z-partitioned over N ranks (configs[3])
+    python bench.py --impl reference ...                   the reference's CPU path (npts.c) on the host cores
+
+A "step" = the three derivatives d/dx, d/dy, d/dz of one resident field (three launches of the fused kernel;
+at N > 1 d/dz adds the halo send/recv, the interface all-gather and the correction kernel).
+`value` = (grid points x 3 derivatives x steps) / time: grid points per second PER DERIVATIVE, whole job.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid points/sec per derivative (fp64)"
+UNIT = "points/s"
+BYTES_PER_POINT = 16            # algorithmic: read f (8 B) + write f' (8 B), SURVEY.md section 8(d)
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.samples.append([s.strip() for s in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active")
+                                                         for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own npts.c (oracle/_ref) when it was built, else the C port
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(seconds_budget=12.0, n=512, threads=None):
+    """
+    d/dx (RHS + tridiagonal solve) of a [planes, n, n] sample of the n^3 workload on the host cores.
+    kind "reference": RHS by the C port (the reference computes it inside test_npts.c's main(), :86-97, not as a
+    callable), solve by the UNMODIFIED lanl-implementation/npts.c (oracle/_ref), one independent solver call per
+    thread over a y-z sub-batch (= the reference's npz x npy decomposition with npx = 1, which needs no
+    communication).  kind "port": oracle/cfd_oracle.c for both.
+    Returns (points_per_s, kind, cores, sample_text).
+    """
+    from oracle import cfd_oracle as O
+    O.build()
+    cores = threads or (os.cpu_count() or 1)
+    kind = "reference" if O.have_ref() else "port"
+    planes = max(cores, 16)
+    rng = np.random.default_rng(0)
+    f = rng.random((planes, n, n))
+    h = 2 * np.pi / (n - 1)
+    O.port().oracle_set_num_threads(cores)
+
+    if kind == "reference":
+        lib = O.ref()
+        dp = ctypes.POINTER(ctypes.c_double)
+        beta, gam = np.zeros(n), np.zeros(n)
+        lib.precompute_beta_gam(0, n, n, 1, beta.ctypes.data_as(dp), gam.ctypes.data_as(dp))
+        per = planes // cores
+        slabs = [(t * per, (t + 1) * per if t < cores - 1 else planes) for t in range(cores)]
+        u = np.zeros_like(f)
+        phi, psi = np.zeros_like(f), np.zeros_like(f)
+
+        def one_pass():
+            r = O.rhs(f, 0, h)
+
+            def work(lo, hi):
+                lib.nonperiodic_tridiagonal_solver(0, n, n, hi - lo, beta.ctypes.data_as(dp), gam.ctypes.data_as(dp),
+                                                   r[lo:hi].ctypes.data_as(dp), u[lo:hi].ctypes.data_as(dp),
+                                                   phi[lo:hi].ctypes.data_as(dp), psi[lo:hi].ctypes.data_as(dp))
+            ts = [threading.Thread(target=work, args=s) for s in slabs if s[1] > s[0]]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+    else:
+        def one_pass():
+            O.derivative(f, 0, h)
+
+    # npts.c prints timing lines (options.h PRINT_TIMINGS): silence fd 1 around the timed region
+    sys.stdout.flush()
+    saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        one_pass()                                   # warm-up
+        t0, reps = time.perf_counter(), 0
+        while True:
+            one_pass()
+            reps += 1
+            dt = time.perf_counter() - t0
+            if dt > seconds_budget or reps >= 200:
+                break
+        ctypes.CDLL(None).fflush(None)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    rate = f.size * reps / dt
+    sample = f"d/dx of a [{planes},{n},{n}] fp64 slab of the {n}^3 field, {reps} passes in {dt:.1f} s"
+    return rate, kind, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 512 if args.gpus == 1 else 1024
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    kind = cores = sample = None
+    for i in range(args.warmup + args.steps):
+        r, kind, cores, sample = cpu_reference_rate(seconds_budget=per_step, n=n)
+        if i >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates))
+    pts = n ** 3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * 3 * pts / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    if n_gpus == 1:
+        return {"workload": "512^3 fp64 field, derivative along x, y and z on 1 B200 (BASELINE configs[2])",
+                "grid": [512, 512, 512], "derivatives_per_step": 3, "partition": "none",
+                "l2": "inputs (1 GiB field) larger than the 126 MB L2; no flush needed"}
+    return {"workload": f"1024^3 fp64 field z-partitioned over {n_gpus} B200, derivative along x, y and z "
+                        "(d/dz: halo send/recv + interface all-gather + correction; BASELINE configs[3])",
+            "grid": [1024, 1024, 1024], "derivatives_per_step": 3, "partition": f"z/{n_gpus}",
+            "l2": "inputs (slab >= 1 GiB) larger than the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import compact_finite_differences_b200 as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = 512 if world == 1 else 1024
+    nz_loc = N // world
+    h = 2 * np.pi / (N - 1)
+    t1 = torch.arange(N, dtype=torch.float64, device=dev) * h
+    zz = t1[rank * nz_loc:(rank + 1) * nz_loc]
+    f = (torch.sin(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(zz)[:, None, None]).contiguous()
+    df = [torch.empty_like(f) for _ in range(3)]
+    ops = [C.ZPartitionedDerivative((nz_loc, N, N), h, a) if world > 1 else
+           C.CompactFiniteDifferenceSolver((nz_loc, N, N), h, a) for a in range(3)]
+    pts_local = f.numel()
+
+    def step(events=None):
+        for a in range(3):
+            if events is not None:
+                events[a][0].record()
+            ops[a](f, df[a])
+            if events is not None:
+                events[a][1].record()
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+
+    # sanity: the timed kernels produce the derivative (analytic check, cheap, outside the timed region)
+    ex = torch.cos(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(zz)[:, None, None]
+    err = (df[0] - ex).abs().max().item()
+    del ex
+    assert err < 1e-6, f"d/dx check failed: {err}"
+
+    launches0 = C.lib().cfd_launch_count()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+          for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        fence()
+        t_beg.record()
+        for s in range(args.steps):
+            step(ev[s])
+        t_end.record()
+        fence()
+    launches = C.lib().cfd_launch_count() - launches0
+    ms = t_beg.elapsed_time(t_end)
+    per_axis = [float(np.mean([ev[s][a][0].elapsed_time(ev[s][a][1]) for s in range(args.steps)])) for a in range(3)]
+    if world > 1:
+        t = torch.tensor([ms] + per_axis, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, per_axis = t[0].item(), t[1:].tolist()
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    value = (N ** 3) * 3 * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in pinned memory through the public API, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, 3))
+    f_host = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
+    f_host.copy_(f)
+    out_host = [torch.empty(f.shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+    f_in = torch.empty_like(f)
+
+    def e2e_step():
+        f_in.copy_(f_host, non_blocking=True)
+        for a in range(3):
+            ops[a](f_in, df[a])
+            out_host[a].copy_(df[a], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    fence()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_value = (N ** 3) * 3 * e2e_steps / e2e_s
+    e2e_ok = float((out_host[2] - df[2].cpu()).abs().max()) == 0.0
+
+    # ---- roofline of the dominant kernel (slowest direction), live CUDA-event duration
+    peak, peak_src = measured_peak()
+    dom = int(np.argmax(per_axis))
+    achieved = BYTES_PER_POINT * pts_local / (per_axis[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"stream_kernel d/d{'xyz'[dom]}", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac_of_8TBps_nominal": achieved / 8000.0,
+                "per_axis_ms": {"x": per_axis[0], "y": per_axis[1], "z": per_axis[2]},
+                "per_axis_GBps": {k: BYTES_PER_POINT * pts_local / (v * 1e-3) / 1e9
+                                  for k, v in zip("xyz", per_axis)},
+                "algorithmic_bytes_per_launch": BYTES_PER_POINT * pts_local}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("xyz"[dom])
+        except Exception:
+            pass
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            r, kind, cores, sample = cpu_reference_rate(seconds_budget=12.0, n=N)
+            cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": f.numel() * 8 * world,
+                    "d2h_bytes_per_step": 3 * f.numel() * 8 * world, "steps": e2e_steps, "verified": e2e_ok},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "check": {"ddx_max_abs_err_vs_analytic": err},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+"""
+CompactFiniteDifferenceSolver -- the reference's derivative operator
+(code/cuda/compact.py:16-44 `dfdx(f_d, dx, x_d, f_local_d)`; code/ocl/compact.py:26-61 `dfdx/dfdy/dfdz(f, d)`),
+served by one fused sm_100a kernel per direction (RHS stencil + tridiagonal solve, f read once, f' written once).
+
+    s  = CompactFiniteDifferenceSolver((nz, ny, nx), spacing=dx, direction=0)   # 0 = x, 1 = y, 2 = z
+    df = s(f)                                  # f: CUDA float64 tensor [nz, ny, nx] (contiguous)
+    s.dfdx(f, dx), s.dfdy(f, dy), s.dfdz(f, dz)   # reference spellings; plans are cached per (axis, spacing)
+
+A NumPy array in gives a NumPy array out (the OpenCL flavour's contract) through the library's host-buffer
+entry point: the arithmetic still runs on the GPU -- there is no CPU implementation in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import check, lib
+
+_AXIS_NAMES = {0: "x", 1: "y", 2: "z"}
+
+
+def _stream_ptr(t):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _Plan:
+    """Owns one cfd_plan (cfd_create / cfd_destroy)."""
+
+    def __init__(self, shape, axis, spacing, part_rank=0, part_size=1):
+        nz, ny, nx = (int(s) for s in shape)
+        self.handle = ctypes.c_void_p()
+        check(lib().cfd_create(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
+                               int(part_rank), int(part_size)))
+        self.shape, self.axis, self.spacing = (nz, ny, nx), int(axis), float(spacing)
+        self.part = (int(part_rank), int(part_size))
+        self.plane_elems = lib().cfd_plane_elems(self.handle)
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                lib().cfd_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+class CompactFiniteDifferenceSolver:
+    def __init__(self, shape, spacing=None, direction=None, part=(0, 1)):
+        """
+        :param shape: (nz, ny, nx) of the (local) block, C order, x fastest
+        :param spacing: grid spacing along `direction` (may instead be given per call to dfdx/dfdy/dfdz)
+        :param direction: 0 = x, 1 = y, 2 = z (numbering of code/cuda/gpuDA.py:162)
+        :param part: (rank, size) of this block along the derivative line -- the reference's
+                     (line_da.rank, line_da.size), code/cuda/compact.py:159-166.  (0, 1) = whole line here.
+        """
+        assert len(shape) == 3, "shape is (nz, ny, nx)"
+        self.shape = tuple(int(s) for s in shape)
+        self.part = (int(part[0]), int(part[1]))
+        self.direction = None if direction is None else int(direction)
+        self.spacing = None if spacing is None else float(spacing)
+        self._plans = {}
+        if self.direction is not None:
+            assert self.direction in (0, 1, 2), "direction is 0 (x), 1 (y) or 2 (z)"
+            if self.spacing is not None:
+                self._plan(self.direction, self.spacing)          # fail early, like the reference constructor
+
+    # -- plans ---------------------------------------------------------------------------------------
+    def _plan(self, axis, spacing) -> _Plan:
+        key = (int(axis), float(spacing))
+        p = self._plans.get(key)
+        if p is None:
+            p = _Plan(self.shape, axis, spacing, *self.part)
+            self._plans[key] = p
+        return p
+
+    # -- the hot path --------------------------------------------------------------------------------
+    def _apply(self, axis, spacing, f, out=None, halo_lo=None, halo_hi=None):
+        plan = self._plan(axis, spacing)
+        if isinstance(f, np.ndarray):
+            return self._apply_host(plan, f, out)
+        import torch
+        assert isinstance(f, torch.Tensor), "f is a CUDA float64 tensor (or a NumPy array for the host-buffer path)"
+        assert f.is_cuda and f.dtype == torch.float64, "f must be a CUDA float64 tensor"
+        assert tuple(f.shape) == self.shape, f"f has shape {tuple(f.shape)}, solver was built for {self.shape}"
+        assert f.is_contiguous(), "f must be contiguous (C order, x fastest)"
+        if out is None:
+            out = torch.empty_like(f)
+        else:
+            assert out.is_cuda and out.dtype == torch.float64 and tuple(out.shape) == self.shape and out.is_contiguous()
+            assert out.data_ptr() != f.data_ptr(), "the derivative is out of place"
+        for h in (halo_lo, halo_hi):
+            if h is not None:
+                assert h.is_cuda and h.dtype == torch.float64 and h.is_contiguous() and h.numel() == plan.plane_elems
+        check(lib().cfd_apply(plan.handle, f.data_ptr(), out.data_ptr(),
+                              halo_lo.data_ptr() if halo_lo is not None else None,
+                              halo_hi.data_ptr() if halo_hi is not None else None, _stream_ptr(f)))
+        return out
+
+    @staticmethod
+    def _apply_host(plan, f, out):
+        assert f.dtype == np.float64 and f.shape == plan.shape, "f must be float64 of the solver's shape"
+        f = np.ascontiguousarray(f)
+        if out is None:
+            out = np.empty_like(f)
+        assert out.dtype == np.float64 and out.shape == plan.shape and out.flags.c_contiguous
+        check(lib().cfd_apply_host(plan.handle, f.ctypes.data, out.ctypes.data, 0))
+        return out
+
+    def __call__(self, f, out=None):
+        assert self.direction is not None and self.spacing is not None, \
+            "construct with spacing= and direction= to call the solver directly"
+        return self._apply(self.direction, self.spacing, f, out)
+
+    def apply_local(self, f, out=None, halo_lo=None, halo_hi=None):
+        """Block-local solution x_R of a partitioned line (code/cuda/compact.py:46-64): needs the neighbour
+        planes of f where this block does not own the physical end."""
+        return self._apply(self.direction, self.spacing, f, out, halo_lo, halo_hi)
+
+    # reference spellings (code/ocl/compact.py:26,41,52; code/cuda/compact.py:29)
+    def dfdx(self, f, dx=None, out=None, f_local=None):
+        """f_local (the reference's ghosted scratch array) is accepted and ignored: no ghost copy is made."""
+        return self._apply(0, self._h(dx, 0), f, out)
+
+    def dfdy(self, f, dy=None, out=None):
+        return self._apply(1, self._h(dy, 1), f, out)
+
+    def dfdz(self, f, dz=None, out=None):
+        return self._apply(2, self._h(dz, 2), f, out)
+
+    def _h(self, h, axis):
+        if h is not None:
+            return float(h)
+        assert self.spacing is not None and self.direction == axis, f"spacing along {_AXIS_NAMES[axis]} not given"
+        return self.spacing
+
+    # -- multi-rank pieces (used by partition.ZPartitionedDerivative) -----------------------------------
+    def interface_pack(self, df, faces):
+        plan = self._plan(self.direction, self.spacing)
+        check(lib().cfd_interface_pack(plan.handle, df.data_ptr(), faces.data_ptr(), _stream_ptr(df)))
+        return faces
+
+    def reduced_correct(self, df, faces_all):
+        plan = self._plan(self.direction, self.spacing)
+        check(lib().cfd_reduced_correct(plan.handle, df.data_ptr(), faces_all.data_ptr(), _stream_ptr(df)))
+        return df

@@ -1,0 +1,550 @@
+// api.cu -- C ABI of libcfd_b200.so (see include/cfd_b200.h).  Host logic only: plan construction
+// (coefficient tables, secondary systems, reduced matrix), TMA descriptor encoding, kernel launches.
+// No field arithmetic happens on the host and there is no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cfd_b200.h"
+#include "kernels.cuh"
+
+using namespace cfd;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long> g_launches{0};
+static int g_warps = 0, g_ctas = 0;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(CFD_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char *cfd_last_error(void) { return g_err.c_str(); }
+extern "C" int cfd_version(void) { return CFD_B200_VERSION; }
+extern "C" long cfd_launch_count(void) { return g_launches.load(); }
+extern "C" int cfd_set_launch(int warps_per_cta, int ctas_per_sm)
+{
+    if (warps_per_cta < 0 || warps_per_cta > 9 || ctas_per_sm < 0 || ctas_per_sm > 8)
+        return fail(CFD_EINVAL, "cfd_set_launch(%d, %d): out of range", warps_per_cta, ctas_per_sm);
+    g_warps = warps_per_cta;
+    g_ctas = ctas_per_sm;
+    return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding (driver entry point fetched through the runtime: no link-time libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode()
+{
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry shared by both plan kinds
+// ------------------------------------------------------------------------------------------------
+struct Geometry {
+    int nz, ny, nx, axis;
+    bool contig;
+    int n;        // rows per line
+    long inner;   // elements between consecutive rows of a line (1 for x)
+    long outer;   // number of outer slices
+    long nlines;
+    long nb;      // 32-line bundles
+    int K, jl;
+    int inner_tiles;
+};
+
+static int make_geometry(Geometry &g, int nz, int ny, int nx, int axis)
+{
+    if (nz < 1 || ny < 1 || nx < 1) return fail(CFD_EINVAL, "shape (%d,%d,%d) must be positive", nz, ny, nx);
+    if (axis < 0 || axis > 2) return fail(CFD_EINVAL, "axis %d not in {0,1,2}", axis);
+    if (nx % 2) return fail(CFD_EINVAL, "nx = %d must be even (TMA needs 16-byte row pitch)", nx);
+    g.nz = nz; g.ny = ny; g.nx = nx; g.axis = axis;
+    g.contig = (axis == 0);
+    if (axis == 0)      { g.n = nx; g.inner = 1;             g.outer = (long)nz * ny; }
+    else if (axis == 1) { g.n = ny; g.inner = nx;            g.outer = nz; }
+    else                { g.n = nz; g.inner = (long)ny * nx; g.outer = 1; }
+    if (g.n < 3) return fail(CFD_EINVAL, "extent along axis %d is %d; need >= 3", axis, g.n);
+    g.nlines = (long)nz * ny * nx / g.n;
+    g.K = (g.n + CH - 1) / CH;
+    g.jl = (g.n - 1) - CH * (g.K - 1);
+    if (g.contig) {
+        g.inner_tiles = 1;
+        g.nb = (g.nlines + CH - 1) / CH;
+    } else {
+        if (g.inner > 0x7fffffffL) return fail(CFD_EINVAL, "plane too large");
+        g.inner_tiles = (int)((g.inner + CH - 1) / CH);
+        g.nb = g.outer * g.inner_tiles;
+    }
+    return CFD_OK;
+}
+
+static int encode_maps(const Geometry &g, const void *in, const void *out, CUtensorMap *tm_in, CUtensorMap *tm_out)
+{
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return fail(CFD_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return fail(CFD_EINVAL, "field pointers must be 16-byte aligned");
+    CUresult r;
+    if (g.contig) {
+        cuuint64_t dims[2] = {(cuuint64_t)g.nx, (cuuint64_t)g.nlines};
+        cuuint64_t strides[1] = {(cuuint64_t)g.nx * 8};
+        cuuint32_t box[2] = {16, CH};
+        cuuint32_t es[2] = {1, 1};
+        r = enc(tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = enc(tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[3] = {(cuuint64_t)g.inner, (cuuint64_t)g.n, (cuuint64_t)g.outer};
+        cuuint64_t strides[2] = {(cuuint64_t)g.inner * 8, (cuuint64_t)g.inner * 8 * (cuuint64_t)g.n};
+        cuuint32_t box[3] = {CH, CH, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        r = enc(tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        *tm_out = *tm_in;   // STRIDED results leave through plain coalesced stores
+    }
+    if (r != CUDA_SUCCESS) return fail(CFD_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch of the streaming kernel
+// ------------------------------------------------------------------------------------------------
+struct DeviceInfo { int sms = 0; int max_smem = 0; bool ok = false; };
+
+static int device_info(DeviceInfo &d)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major < 10) return fail(CFD_EUNSUPPORTED, "compute capability %d.x: this library is sm_100a only", major);
+    d.ok = true;
+    return CFD_OK;
+}
+
+template <bool CONTIG, bool DERIV>
+static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                         cudaStream_t stream)
+{
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
+    constexpr int per_warp = (NS + (CONTIG ? 1 : 0)) * SLOT_BYTES;
+    const int max_warps = CONTIG ? 7 : 8;   // register file is 16K per SM sub-partition: <= 2 warps each at ~240 regs
+    int warps = g_warps ? g_warps : max_warps;
+    if (warps > max_warps) warps = max_warps;
+    int ctas = g_ctas ? g_ctas : 1;
+    auto smem_for = [&](int w) { return (size_t)w * per_warp + (size_t)w * NS * 8 + 1024; };
+    while (warps > 1 && (long)ctas * (long)(smem_for(warps) + 1024) > 232448L) warps--;
+    const size_t smem = smem_for(warps);
+    auto kern = stream_kernel<CONTIG, DERIV>;
+    static size_t configured = 0;
+    if (configured < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(max_warps)));
+        configured = smem_for(max_warps);
+    }
+    long blocks = (g.nb + warps - 1) / warps;
+    const long cap = (long)dinfo.sms * ctas;
+    if (blocks > cap) blocks = cap;
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, kp);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------
+struct MapCache { const void *in = nullptr, *out = nullptr; CUtensorMap tm_in, tm_out; };
+
+struct cfd_plan {
+    Geometry g;
+    double h;
+    int rank, size;
+    KParams kp;                       // host template (halo/out pointers filled per call)
+    MapCache cache;
+    // multi-rank
+    std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
+    double *d_x_uh = nullptr, *d_x_lh = nullptr, *d_lu = nullptr;
+    int wc = 0;
+    // host staging
+    double *d_f = nullptr, *d_df = nullptr;
+    cudaStream_t hstream = nullptr;
+};
+
+struct nt_plan {
+    Geometry g;
+    KParams kp;
+    MapCache cache;
+};
+
+static int fill_tables(KParams &kp, const Geometry &g, const LineCoeffs &m, double scale, bool need_fast)
+{
+    Pivots pv = build_pivots(g.n, m);
+    if (!pv.finite) return fail(CFD_EINVAL, "zero pivot: LU without pivoting breaks down for these coefficients");
+    if (g.K > 2 && need_fast) {
+        if (!pv.converged || std::pow(pv.decay, CH) > 1.2e-16)
+            return fail(CFD_EUNSUPPORTED,
+                        "coefficients (ai,bi,ci) = (%g,%g,%g): LU pivots do not converge / coupling %.3f^32 above fp64 "
+                        "round-off; the streaming solver needs a diagonally dominant interior for n > 64",
+                        m.ai, m.bi, m.ci, pv.decay);
+    }
+    memset(&kp, 0, sizeof kp);
+    kp.n = g.n; kp.K = g.K; kp.jl = g.jl;
+    kp.inner = (int)g.inner; kp.inner_tiles = g.inner_tiles;
+    kp.nb = g.nb; kp.rows = g.nlines;
+    kp.head = chunk_table(pv, g.n, 0, scale);
+    kp.tail = chunk_table(pv, g.n, g.K - 1, scale);
+    if (g.K > 2) { kp.sk_mid = pv.beta[CH] * scale; kp.l_mid = pv.l[CH]; kp.g_mid = pv.g[CH]; }
+    kp.s0c = pv.beta[0];        // scaled by the caller for the derivative
+    kp.snc = pv.beta[g.n - 1];
+    return CFD_OK;
+}
+
+static LineCoeffs pade_block(int rank, int size)
+{   // code/cuda/compact.py:159-166
+    LineCoeffs m = {1.0, 0.25, 0.25, 1.0, 0.25, 0.25, 1.0};
+    if (rank == 0) m.c1 = 2.0;
+    if (rank == size - 1) m.an = 2.0;
+    return m;
+}
+
+static void secondary_systems(int n, int rank, int size, std::vector<double> &x_uh, std::vector<double> &x_lh)
+{   // code/cuda/compact.py:128-154
+    std::vector<double> a(n, 0.25), b(n, 1.0), c(n, 0.25);
+    if (rank == 0) { c[0] = 2.0; a[0] = 0.0; }
+    if (rank == size - 1) { a[n - 1] = 2.0; c[n - 1] = 0.0; }
+    x_uh.assign(n, 0.0); x_lh.assign(n, 0.0);
+    x_uh[0] = -a[0];
+    x_lh[n - 1] = -c[n - 1];
+    thomas_host(n, a, b, c, x_uh);
+    thomas_host(n, a, b, c, x_lh);
+}
+
+// Reduced (interface) matrix of the whole line: every rank can build all rows, they depend on the block
+// length and position only (the reference gathers two scalars per rank instead, compact.py:77-82).
+static void reduced_matrix(int n, int P, std::vector<double> &ra, std::vector<double> &rb, std::vector<double> &rc)
+{
+    const int mm = 2 * P;
+    std::vector<double> uh(mm), lh(mm);
+    for (int r = 0; r < P; r++) {
+        std::vector<double> u, l;
+        secondary_systems(n, r, P, u, l);
+        uh[2 * r] = u[0]; uh[2 * r + 1] = u[n - 1];
+        lh[2 * r] = l[0]; lh[2 * r + 1] = l[n - 1];
+    }
+    ra.assign(mm, 0.0); rb.assign(mm, 0.0); rc.assign(mm, 0.0);
+    for (int i = 0; i < mm; i += 2) { ra[i] = -1.0; rb[i] = uh[i]; rc[i] = lh[i]; }     // compact.py:100-105
+    for (int i = 1; i < mm; i += 2) { ra[i] = uh[i]; rb[i] = lh[i]; rc[i] = -1.0; }
+    ra[0] = 0.0; rc[0] = 0.0; rb[0] = 1.0;                                                // :106-107
+    ra[mm - 1] = 0.0; rc[mm - 1] = 0.0; rb[mm - 1] = 1.0;                                 // :108-109
+    ra[1] = 0.0; rc[mm - 2] = 0.0;                                                        // :110-111
+}
+
+// Host-only inspection of the multi-rank tables (no device needed).
+extern "C" int cfd_debug_secondary(int n, int part_rank, int part_size, double *x_uh, double *x_lh, double *ra,
+                                   double *rb, double *rc)
+{
+    if (n < 3 || part_size < 2 || part_rank < 0 || part_rank >= part_size) return fail(CFD_EINVAL, "bad argument");
+    std::vector<double> u, l, a, b, c;
+    secondary_systems(n, part_rank, part_size, u, l);
+    reduced_matrix(n, part_size, a, b, c);
+    if (x_uh) memcpy(x_uh, u.data(), n * sizeof(double));
+    if (x_lh) memcpy(x_lh, l.data(), n * sizeof(double));
+    if (ra) memcpy(ra, a.data(), a.size() * sizeof(double));
+    if (rb) memcpy(rb, b.data(), b.size() * sizeof(double));
+    if (rc) memcpy(rc, c.data(), c.size() * sizeof(double));
+    return CFD_OK;
+}
+
+extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size)
+{
+    if (!out) return fail(CFD_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    if (!(h > 0.0) || !std::isfinite(h)) return fail(CFD_EINVAL, "spacing h = %g must be positive", h);
+    if (part_size < 1 || part_rank < 0 || part_rank >= part_size || part_size > 64)
+        return fail(CFD_EINVAL, "partition position %d of %d is invalid", part_rank, part_size);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CFD_ECUDA, "no CUDA device: libcfd_b200 has no CPU path");
+    }
+    cfd_plan *p = new cfd_plan();
+    int rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (rc) { delete p; return rc; }
+    p->h = h; p->rank = part_rank; p->size = part_size;
+    const LineCoeffs m = pade_block(part_rank, part_size);
+    rc = fill_tables(p->kp, p->g, m, 3.0 / (4.0 * h), true);
+    if (rc) { delete p; return rc; }
+    p->kp.lo_closure = (part_rank == 0);
+    p->kp.hi_closure = (part_rank == part_size - 1);
+    p->kp.s0c *= 1.0 / (2.0 * h);
+    p->kp.snc *= 1.0 / (2.0 * h);
+
+    if (part_size > 1) {
+        const int n = p->g.n, P = part_size, mm = 2 * P;
+        secondary_systems(n, part_rank, P, p->x_uh, p->x_lh);
+        reduced_matrix(n, P, p->ra, p->rb, p->rc);
+        // two-sided elimination tables
+        p->lu.assign(6 * mm, 0.0);
+        double *a = &p->lu[0], *c = &p->lu[mm], *ip = &p->lu[2 * mm], *cp = &p->lu[3 * mm], *iq = &p->lu[4 * mm],
+               *aq = &p->lu[5 * mm];
+        for (int i = 0; i < mm; i++) { a[i] = p->ra[i]; c[i] = p->rc[i]; }
+        double piv = p->rb[0];
+        ip[0] = 1.0 / piv; cp[0] = c[0] / piv;
+        for (int i = 1; i < mm; i++) { piv = p->rb[i] - a[i] * cp[i - 1]; ip[i] = 1.0 / piv; cp[i] = c[i] / piv; }
+        piv = p->rb[mm - 1];
+        iq[mm - 1] = 1.0 / piv; aq[mm - 1] = a[mm - 1] / piv;
+        for (int i = mm - 2; i >= 0; i--) { piv = p->rb[i] - c[i] * aq[i + 1]; iq[i] = 1.0 / piv; aq[i] = a[i] / piv; }
+        // correction band: rows where the secondary solutions are above round-off
+        int wc = 0;
+        while (wc < n && (std::fabs(p->x_uh[wc]) > 1e-19 || std::fabs(p->x_lh[n - 1 - wc]) > 1e-19)) wc++;
+        p->wc = wc;
+        if (cudaMalloc(&p->d_x_uh, n * sizeof(double)) != cudaSuccess || cudaMalloc(&p->d_x_lh, n * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&p->d_lu, p->lu.size() * sizeof(double)) != cudaSuccess) {
+            cfd_destroy(p);
+            return fail(CFD_ECUDA, "cudaMalloc of plan tables failed");
+        }
+        cudaMemcpy(p->d_x_uh, p->x_uh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(p->d_x_lh, p->x_lh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(p->d_lu, p->lu.data(), p->lu.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    *out = p;
+    return CFD_OK;
+}
+
+extern "C" void cfd_destroy(cfd_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu);
+    cudaFree(p->d_f); cudaFree(p->d_df);
+    if (p->hstream) cudaStreamDestroy(p->hstream);
+    delete p;
+}
+
+extern "C" long cfd_plane_elems(const cfd_plan *p) { return p ? p->g.nlines : 0; }
+
+extern "C" int cfd_tables_size(void) { return 3 * CH * 2 + 8; }
+
+extern "C" int cfd_plan_tables(const cfd_plan *p, double *out)
+{
+    if (!p || !out) return fail(CFD_EINVAL, "NULL argument");
+    memcpy(out, &p->kp.head, sizeof(RowTab));
+    memcpy(out + 3 * CH, &p->kp.tail, sizeof(RowTab));
+    double *s = out + 6 * CH;
+    s[0] = p->kp.sk_mid; s[1] = p->kp.l_mid; s[2] = p->kp.g_mid; s[3] = p->kp.s0c; s[4] = p->kp.snc;
+    s[5] = p->kp.K; s[6] = p->kp.jl; s[7] = p->wc;
+    return CFD_OK;
+}
+
+extern "C" int cfd_plan_secondary(const cfd_plan *p, double *x_uh, double *x_lh, double *ra, double *rb, double *rc)
+{
+    if (!p) return fail(CFD_EINVAL, "NULL plan");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no secondary systems");
+    const int n = p->g.n, mm = 2 * p->size;
+    if (x_uh) memcpy(x_uh, p->x_uh.data(), n * sizeof(double));
+    if (x_lh) memcpy(x_lh, p->x_lh.data(), n * sizeof(double));
+    if (ra) memcpy(ra, p->ra.data(), mm * sizeof(double));
+    if (rb) memcpy(rb, p->rb.data(), mm * sizeof(double));
+    if (rc) memcpy(rc, p->rc.data(), mm * sizeof(double));
+    return CFD_OK;
+}
+
+// Host-only inspection (no device needed): the tables cfd_create / nt_create would build for a line of
+// n rows.  out: head[96], tail[96], then sk_mid, l_mid, g_mid, beta_0, beta_{n-1}, K, jl, fast_ok.
+extern "C" int cfd_debug_tables(int n, const double coeffs[7], double scale, double *out)
+{
+    if (n < 3 || !coeffs || !out) return fail(CFD_EINVAL, "bad argument");
+    Geometry g;
+    memset(&g, 0, sizeof g);
+    g.n = n; g.K = (n + CH - 1) / CH; g.jl = (n - 1) - CH * (g.K - 1); g.inner = 1; g.inner_tiles = 1;
+    KParams kp;
+    const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
+    int rc = fill_tables(kp, g, m, scale, false);
+    if (rc) return rc;
+    Pivots pv = build_pivots(n, m);
+    memcpy(out, &kp.head, sizeof(RowTab));
+    memcpy(out + 3 * CH, &kp.tail, sizeof(RowTab));
+    double *s = out + 6 * CH;
+    s[0] = kp.sk_mid; s[1] = kp.l_mid; s[2] = kp.g_mid; s[3] = kp.s0c; s[4] = kp.snc;
+    s[5] = kp.K; s[6] = kp.jl;
+    s[7] = (g.K <= 2 || (pv.converged && std::pow(pv.decay, CH) <= 1.2e-16)) ? 1.0 : 0.0;
+    return CFD_OK;
+}
+
+static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *out)
+{
+    if (c.in == in && c.out == out) return CFD_OK;
+    int rc = encode_maps(g, in, out, &c.tm_in, &c.tm_out);
+    if (rc) { c.in = c.out = nullptr; return rc; }
+    c.in = in; c.out = out;
+    return CFD_OK;
+}
+
+extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+                         void *stream)
+{
+    if (!p || !f || !df) return fail(CFD_EINVAL, "NULL argument");
+    if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
+    if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
+    if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
+    int rc = get_maps(p->cache, p->g, f, df);
+    if (rc) return rc;
+    KParams kp = p->kp;
+    kp.halo_lo = halo_lo; kp.halo_hi = halo_hi; kp.out = df;
+    if (p->g.contig) return launch_stream<true, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+    return launch_stream<false, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+}
+
+extern "C" int cfd_interface_pack(cfd_plan *p, const double *df, double *faces, void *stream)
+{
+    if (!p || !df || !faces) return fail(CFD_EINVAL, "NULL argument");
+    GeomP gp = {p->g.nlines, p->g.n, p->g.inner};
+    const int bs = 256;
+    interface_pack_kernel<<<(unsigned)((gp.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        df, faces, gp, p->kp.lo_closure, p->kp.hi_closure);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+extern "C" int cfd_reduced_correct(cfd_plan *p, double *df, const double *faces_all, void *stream)
+{
+    if (!p || !df || !faces_all) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: nothing to correct");
+    GeomP gp = {p->g.nlines, p->g.n, p->g.inner};
+    const int bs = 128;
+    if (p->g.contig) {
+        const long threads = gp.nlines * 32;
+        reduced_correct_kernel<true><<<(unsigned)((threads + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+            df, faces_all, p->d_lu, p->d_x_uh, p->d_x_lh, gp, p->size, p->rank, p->wc);
+    } else {
+        reduced_correct_kernel<false><<<(unsigned)((gp.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+            df, faces_all, p->d_lu, p->d_x_uh, p->d_x_lh, gp, p->size, p->rank, p->wc);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+extern "C" int cfd_apply_host(cfd_plan *p, const double *f_host, double *df_host, int pinned)
+{
+    (void)pinned;
+    if (!p || !f_host || !df_host) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size != 1) return fail(CFD_EINVAL, "cfd_apply_host serves part_size == 1 only");
+    const size_t bytes = (size_t)p->g.nlines * p->g.n * sizeof(double);
+    if (!p->d_f) {
+        CUDA_TRY(cudaMalloc(&p->d_f, bytes));
+        CUDA_TRY(cudaMalloc(&p->d_df, bytes));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->hstream, cudaStreamNonBlocking));
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_f, f_host, bytes, cudaMemcpyHostToDevice, p->hstream));
+    int rc = cfd_apply(p, p->d_f, p->d_df, nullptr, nullptr, p->hstream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(df_host, p->d_df, bytes, cudaMemcpyDeviceToHost, p->hstream));
+    CUDA_TRY(cudaStreamSynchronize(p->hstream));
+    return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// near-Toeplitz solver
+// ------------------------------------------------------------------------------------------------
+extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const double coeffs[7])
+{
+    if (!out || !coeffs) return fail(CFD_EINVAL, "NULL argument");
+    *out = nullptr;
+    for (int i = 0; i < 7; i++)
+        if (!std::isfinite(coeffs[i])) return fail(CFD_EINVAL, "coefficient %d is not finite", i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CFD_ECUDA, "no CUDA device: libcfd_b200 has no CPU path");
+    }
+    nt_plan *p = new nt_plan();
+    int rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (rc) { delete p; return rc; }
+    const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
+    rc = fill_tables(p->kp, p->g, m, 1.0, true);
+    if (rc) { delete p; return rc; }
+    p->kp.lo_closure = 1; p->kp.hi_closure = 1;
+    *out = p;
+    return CFD_OK;
+}
+
+extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
+{
+    if (!p || !d) return fail(CFD_EINVAL, "NULL argument");
+    int rc = get_maps(p->cache, p->g, d, d);
+    if (rc) return rc;
+    KParams kp = p->kp;
+    kp.out = d;
+    if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+    return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+}
+
+extern "C" void nt_destroy(nt_plan *p) { delete p; }
+
+// ------------------------------------------------------------------------------------------------
+// pThomas
+// ------------------------------------------------------------------------------------------------
+extern "C" int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream)
+{
+    if (!a || !b || !c || !d) return fail(CFD_EINVAL, "NULL argument");
+    if (n < 1 || n > 256 || nsys < 1) return fail(CFD_EINVAL, "n = %d (1..256), nsys = %ld", n, nsys);
+    std::vector<double> lu(3 * n);
+    double piv = b[0];
+    lu[0] = 0.0; lu[n] = 1.0 / piv; lu[2 * n] = c[0] / piv;
+    for (int i = 1; i < n; i++) {
+        piv = b[i] - a[i] * lu[2 * n + i - 1];
+        if (piv == 0.0 || !std::isfinite(piv)) return fail(CFD_EINVAL, "zero pivot at row %d", i);
+        lu[i] = a[i]; lu[n + i] = 1.0 / piv; lu[2 * n + i] = c[i] / piv;
+    }
+    double *d_lu = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_lu, lu.size() * sizeof(double), (cudaStream_t)stream));
+    CUDA_TRY(cudaMemcpyAsync(d_lu, lu.data(), lu.size() * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // lu is a stack-lifetime host buffer
+    const int bs = 128;
+    pthomas_kernel<<<(unsigned)((nsys + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(d, d_lu, n, nsys);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d_lu, (cudaStream_t)stream));
+    return CFD_OK;
+}

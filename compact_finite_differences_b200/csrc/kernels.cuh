@@ -1,0 +1,466 @@
+// kernels.cuh -- sm_100a device code of the compact-derivative path.
+//
+// One fused kernel per direction: Pade right-hand side (reference computeRHS,
+// code/cuda/kernels.cu:4-47) + batched near-Toeplitz tridiagonal solve (reference
+// sharedMemCyclicReduction, code/cuda/solvers/templated/kernels.jinja2:2-123) in ONE pass:
+// every point of f is read from HBM once and every point of f' written once (16 B / point).
+//
+// Design (nothing of the reference's one-block-per-line cyclic reduction survives):
+//
+//  * WARP-AUTONOMOUS STREAMING.  A warp owns a bundle of 32 lines (lane = line) and marches along
+//    them in chunks of CH = 32 rows.  Tiles of 32 rows x 32 lines x 8 B = 8 KiB arrive through
+//    TMA (cp.async.bulk.tensor) into a private 3-slot shared-memory ring guarded by the warp's own
+//    mbarriers; no CTA-wide barrier exists anywhere, so warps drift freely and hide each other's
+//    latencies.  Warps are persistent: the flat tile sequence (bundle, chunk) is prefetched NS
+//    tiles ahead, across bundle boundaries.
+//  * LU WITH CONSTANT PIVOTS + LOOK-AHEAD BACK-SUBSTITUTION.  The forward elimination
+//    e_i = s*r_i - l*e_{i-1} is carried exactly along the whole line in registers.  The backward
+//    sweep x_i = e_i - g*x_{i+1} of chunk k-1 is started one chunk to the right, at the end of
+//    chunk k, from x = e: the neglected term decays by |g| = 2 - sqrt(3) = 0.268 per row, i.e. by
+//    0.268^32 = 5e-19 over the 32 warm-up rows -- below fp64 round-off.  At the true end of the
+//    line the sweep is exact.  Forward-eliminated values of two chunks (64 doubles) live in
+//    registers; nothing is spilled to memory between the two sweeps, which is what makes the
+//    kernel read-once / write-once for any line length (the reference caps nx at 2048).
+//  * LAYOUTS.  CONTIG (derivative along x): lines are rows of the [nz*ny, nx] matrix; the tile is two
+//    TMA boxes of 32 rows x 16 doubles with 128-byte swizzle, so that lane r reading its own row with
+//    16-byte LDS.128 is bank-conflict free (the "tiled transpose" happens inside the TMA unit); the
+//    result tile goes back through swizzled shared memory and a TMA store.  STRIDED (y, z): lanes map
+//    to 32 consecutive x columns, the tile is one [32 rows][32 cols] box, loads are LDS.64 with no
+//    conflicts and results are written straight from registers with 256-byte coalesced stores.
+//
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tables.h"
+
+namespace cfd {
+
+constexpr int NS = 3;             // ring slots per warp (tile k, tile k+1 for the stencil peek, one in flight)
+constexpr int SLOT_BYTES = CH * CH * 8;   // 8 KiB
+
+struct KParams {
+    int n;             // rows per line
+    int K;             // chunks per line = ceil(n / 32)
+    int jl;            // position of row n-1 inside the last chunk
+    int inner;         // STRIDED: extent of the contiguous dimension the lanes map to
+    int inner_tiles;   // STRIDED: ceil(inner / 32)
+    int lo_closure;    // this block owns the physical left end  -> one-sided RHS row 0
+    int hi_closure;    // this block owns the physical right end -> one-sided RHS row n-1
+    long nb;           // number of 32-line bundles
+    long rows;         // CONTIG: number of lines
+    double sk_mid, l_mid, g_mid;
+    double s0c, snc;   // beta_0/(2h), beta_{n-1}/(2h) for the closure rows
+    const double *halo_lo, *halo_hi;   // neighbour planes of f (multi-rank), one value per line
+    double *out;       // STRIDED: destination field
+    RowTab head, tail;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+
+// Bounded wait: a descriptor mistake must fault, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void st_stream(double *p, double v)
+{ asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Tile access.  CONTIG: slot = 2 boxes [32 rows][16 doubles], 128B-swizzled: the 16-byte unit u of row r
+// sits at r*128 + ((u ^ (r & 7)) << 4).  STRIDED: slot = [32 rows][32 cols] dense.
+// ------------------------------------------------------------------------------------------------
+template <bool CONTIG>
+__device__ __forceinline__ void load_chunk(const unsigned char *slot, int lane, double (&F)[CH])
+{
+    if constexpr (CONTIG) {
+        const unsigned char *row = slot + lane * 128;
+        const int sw = (lane & 7) << 4;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const double2 v = *reinterpret_cast<const double2 *>(row + (m >> 3) * 4096 + (((m & 7) << 4) ^ sw));
+            F[2 * m] = v.x;
+            F[2 * m + 1] = v.y;
+        }
+    } else {
+        const double *col = reinterpret_cast<const double *>(slot) + lane;
+#pragma unroll
+        for (int j = 0; j < CH; j++) F[j] = col[j * CH];
+    }
+}
+
+template <bool CONTIG>
+__device__ __forceinline__ double load_first(const unsigned char *slot, int lane)
+{
+    if constexpr (CONTIG) return *reinterpret_cast<const double *>(slot + lane * 128 + ((lane & 7) << 4));
+    else return reinterpret_cast<const double *>(slot)[lane];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward elimination of one chunk.
+//   MODE 0: interior chunk, constant coefficients.  MODE 1: first chunk (HEAD table; also the only
+//   chunk when K == 1).  MODE 2: last chunk (TAIL table).
+//   DERIV: r_i is the Pade stencil of f (code/cuda/kernels.cu:34-44), else r_i = tile value.
+// State carried along the line: eprev = e_{i-1}, fm1 = f_{i-1}, fm2 = f_{i-2}.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool DERIV>
+__device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH], double peek, double hval,
+                                          bool is_last, double (&e)[CH], double &eprev, double &fm1, double &fm2)
+{
+    if constexpr (MODE == 0) {
+        const double sk = p.sk_mid, nl = -p.l_mid;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            double r;
+            if constexpr (DERIV) {
+                const double nxt = (j < CH - 1) ? F[j + 1] : peek;
+                r = sk * (nxt - fm1);
+                fm1 = F[j];
+            } else {
+                r = sk * F[j];
+            }
+            eprev = fma(nl, eprev, r);
+            e[j] = eprev;
+        }
+        if constexpr (DERIV) fm2 = F[CH - 2];
+    } else {
+        const RowTab &T = (MODE == 1) ? p.head : p.tail;
+        const int jl = is_last ? p.jl : -1;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            double r;
+            if constexpr (DERIV) {
+                double nxt = (j < CH - 1) ? F[j + 1] : peek;
+                if (j == jl && !p.hi_closure) nxt = hval;
+                r = T.sk[j] * (nxt - fm1);
+                if (MODE == 1 && j == 0 && p.lo_closure) r = p.s0c * (-5.0 * F[0] + 4.0 * F[1] + F[2]);
+                if (j == jl && p.hi_closure) r = p.snc * (5.0 * F[j] - 4.0 * fm1 - fm2);
+                fm2 = fm1;
+                fm1 = F[j];
+            } else {
+                r = T.sk[j] * F[j];
+            }
+            eprev = fma(-T.l[j], eprev, r);
+            e[j] = eprev;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward substitution over one chunk, x carried in.  OUT = results of this chunk are final.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool OUT, bool CONTIG>
+__device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH], double &x, unsigned char *oslot,
+                                          int lane, double *gout, long gstride, bool lane_ok, int jmax)
+{
+    const RowTab &T = (MODE == 1) ? p.head : p.tail;
+    double hold = 0.0;
+#pragma unroll
+    for (int j = CH - 1; j >= 0; j--) {
+        const double ng = (MODE == 0) ? -p.g_mid : -T.g[j];
+        x = fma(ng, x, e[j]);
+        if constexpr (OUT) {
+            if constexpr (CONTIG) {
+                if (j & 1) hold = x;
+                else {
+                    const int m = j >> 1;
+                    *reinterpret_cast<double2 *>(oslot + lane * 128 + (m >> 3) * 4096 +
+                                                 (((m & 7) << 4) ^ ((lane & 7) << 4))) = make_double2(x, hold);
+                }
+            } else {
+                if (lane_ok && j <= jmax) st_stream(gout + (long)j * gstride, x);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The streaming kernel.
+// ------------------------------------------------------------------------------------------------
+template <bool CONTIG, bool DERIV>
+__global__ void __launch_bounds__(CONTIG ? 224 : 256, 1)
+stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+              const __grid_constant__ KParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int PER_WARP = (NS + (CONTIG ? 1 : 0)) * SLOT_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+    // 1 KiB alignment in the shared window (128B swizzle atom = 8 rows x 128 B)
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *wbase = base + warp * PER_WARP;
+    unsigned char *oslot = wbase + NS * SLOT_BYTES;                      // CONTIG only
+    const uint32_t bar0 = smem_u32(base + nwarps * PER_WARP) + warp * (NS * 8);
+
+    const long G = (long)gridDim.x * nwarps;
+    const long gw = (long)blockIdx.x * nwarps + warp;
+    if (gw >= p.nb) return;
+    const long T = ((p.nb - gw + G - 1) / G) * p.K;
+    const int K = p.K;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+        fence_async_smem();
+    }
+    __syncwarp();
+
+    // ---- producer side (lane 0): flat tile sequence, NS ahead
+    long ib = gw;   // bundle of the next tile to issue
+    int ik = 0;     // chunk of the next tile to issue
+    int islot = 0;
+    auto issue = [&]() {
+        const uint32_t bar = bar0 + 8 * islot;
+        const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
+        mbar_expect_tx(bar, SLOT_BYTES);
+        if constexpr (CONTIG) {
+            tma_load_2d(dst, &tm_in, bar, ik * CH, (int)(ib * CH));
+            tma_load_2d(dst + 4096, &tm_in, bar, ik * CH + 16, (int)(ib * CH));
+        } else {
+            const int o = (int)(ib / p.inner_tiles), it = (int)(ib % p.inner_tiles);
+            tma_load_3d(dst, &tm_in, bar, it * CH, ik * CH, o);
+        }
+        if (++ik == K) { ik = 0; ib += G; }
+        if (++islot == NS) islot = 0;
+    };
+    if (lane == 0) {
+        const int pre = T < NS ? (int)T : NS;
+        for (int s = 0; s < pre; s++) issue();
+    }
+
+    // ---- consumer side (all lanes)
+    double eA[CH], eB[CH], F[CH];
+    double eprev = 0.0, fm1 = 0.0, fm2 = 0.0, hval = 0.0;
+    long b = gw;
+    int k = 0, slot = 0;
+    uint32_t phase = 0;
+    bool lane_ok = true;
+    double *gcol = nullptr;       // STRIDED: &out[(o*n + 0)*inner + col]
+    const long gstride = CONTIG ? 0 : (long)p.inner;
+
+    for (long t = 0; t < T; ++t) {
+        if (k == 0) {
+            long line;
+            if constexpr (CONTIG) {
+                line = b * CH + lane;
+                lane_ok = line < p.rows;
+            } else {
+                const long o = b / p.inner_tiles;
+                const int col = (int)(b % p.inner_tiles) * CH + lane;
+                lane_ok = col < p.inner;
+                line = o * p.inner + col;
+                gcol = p.out + (o * p.n) * (long)p.inner + col;
+            }
+            eprev = 0.0; fm1 = 0.0; fm2 = 0.0; hval = 0.0;
+            if constexpr (DERIV) {
+                if (!p.lo_closure && lane_ok) fm1 = __ldg(p.halo_lo + line);
+                if (!p.hi_closure && lane_ok) hval = __ldg(p.halo_hi + line);
+            }
+        }
+        const bool last = (k == K - 1);
+        const unsigned char *st = wbase + slot * SLOT_BYTES;
+        mbar_wait(bar0 + 8 * slot, phase);
+        load_chunk<CONTIG>(st, lane, F);
+        double peek = 0.0;
+        if constexpr (DERIV) {
+            if (!last) {
+                const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
+                const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;
+                mbar_wait(bar0 + 8 * s1, ph1);
+                peek = load_first<CONTIG>(wbase + s1 * SLOT_BYTES, lane);
+            }
+        }
+        if (k == 0)    fwd_chunk<1, DERIV>(p, F, peek, hval, last, eB, eprev, fm1, fm2);
+        else if (last) fwd_chunk<2, DERIV>(p, F, peek, hval, true, eB, eprev, fm1, fm2);
+        else           fwd_chunk<0, DERIV>(p, F, peek, hval, false, eB, eprev, fm1, fm2);
+
+        // the slot has been consumed into registers: refill it (tile t + NS)
+        __syncwarp();
+        if (lane == 0 && t + NS < T) issue();
+
+        // ---- backward sweeps
+        auto flush = [&](int kc) {       // CONTIG: ship the staged result tile of chunk kc
+            if constexpr (CONTIG) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
+                    tma_store_2d(&tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
+                    tma_commit();
+                }
+            }
+        };
+        auto acquire_out = [&]() {       // CONTIG: previous store must have drained the staging slot
+            if constexpr (CONTIG) {
+                if (lane == 0) tma_wait_read0();
+                __syncwarp();
+            }
+        };
+        double x = 0.0;
+        if (last) {
+            acquire_out();
+            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane, gcol + (long)k * CH * gstride, gstride, lane_ok, p.jl);
+            else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane, gcol + (long)k * CH * gstride, gstride, lane_ok, p.jl);
+            flush(k);
+            if (k > 0) {
+                acquire_out();
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+                flush(k - 1);
+            }
+        } else if (k > 0) {
+            bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane, nullptr, 0, false, CH);   // 32-row warm-up
+            acquire_out();
+            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+            flush(k - 1);
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) eA[j] = eB[j];
+
+        if (++k == K) { k = 0; b += G; }
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    }
+    if constexpr (CONTIG) {
+        if (lane == 0) tma_wait_all0();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-rank helpers (z-partition): interface planes, reduced system, correction.
+// Element (o, i, c) of a block lives at (o*n + i)*inner + c; its line index is o*inner + c.
+// ------------------------------------------------------------------------------------------------
+struct GeomP { long nlines; int n; long inner; };
+
+// faces[0][line] = -x_R[first], faces[1][line] = -x_R[last]; zero at physical ends
+// (reference negateAndCopyFaces, code/cuda/kernels.cu:76-113).
+__global__ void interface_pack_kernel(const double *__restrict__ x, double *__restrict__ faces, GeomP g,
+                                      int lo_phys, int hi_phys)
+{
+    const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= g.nlines) return;
+    const long o = line / g.inner, c = line % g.inner;
+    const long first = (o * g.n) * g.inner + c;
+    const long lastp = (o * g.n + (g.n - 1)) * g.inner + c;
+    faces[line] = lo_phys ? 0.0 : -x[first];
+    faces[g.nlines + line] = hi_phys ? 0.0 : -x[lastp];
+}
+
+// Reduced 2P-unknown system per line, solved redundantly by every rank after the all-gather
+// (rows: code/cuda/compact.py:96-111; same tridiagonal elimination as reducedSolverKernel,
+// code/cuda/kernels.cu:115-145, with the pivots precomputed on the host), then
+// x += alpha*x_UH + beta*x_LH (sumSolutions, kernels.cu:49-74) on the `wc` rows next to each interface
+// where the secondary solutions exceed fp64 round-off.
+// A rank needs only its own two unknowns u[2r] = alpha, u[2r+1] = beta, so the elimination runs from
+// both ends towards rows (2r, 2r+1) and finishes with a 2x2 solve -- registers only, no per-thread array.
+//   lu = [6][2P]: a_i, c_i, 1/p_i, c_i/p_i (top-down pivots p), 1/q_i, a_i/q_i (bottom-up pivots q).
+template <bool CONTIG>
+__global__ void reduced_correct_kernel(double *__restrict__ x, const double *__restrict__ faces_all,
+                                       const double *__restrict__ lu, const double *__restrict__ x_uh,
+                                       const double *__restrict__ x_lh, GeomP g, int P, int rank, int wc)
+{
+    // CONTIG: one warp per line, lanes stride over the band rows (contiguous in memory).
+    // STRIDED: one thread per line, loop over the band rows (coalesced across threads).
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long line = CONTIG ? (tid >> 5) : tid;
+    const int lane = threadIdx.x & 31;
+    if (line >= g.nlines) return;
+    const int m = 2 * P;
+    const double *a = lu, *c = lu + m, *ip = lu + 2 * m, *cp = lu + 3 * m, *iq = lu + 4 * m, *aq = lu + 5 * m;
+    const int r0 = 2 * rank, r1 = 2 * rank + 1;
+    double t = faces_all[line] * ip[0];
+    for (int i = 1; i <= r0; i++) t = (faces_all[(long)i * g.nlines + line] - a[i] * t) * ip[i];
+    double u = faces_all[(long)(m - 1) * g.nlines + line] * iq[m - 1];
+    for (int i = m - 2; i >= r1; i--) u = (faces_all[(long)i * g.nlines + line] - c[i] * u) * iq[i];
+    // x[r0] = t - cp[r0]*x[r1];  x[r1] = u - aq[r1]*x[r0]
+    const double alpha = (t - cp[r0] * u) / (1.0 - cp[r0] * aq[r1]);
+    const double beta = u - aq[r1] * alpha;
+    const long o = line / g.inner, col = line % g.inner;
+    double *xl = x + (o * g.n) * g.inner + col;
+    const int n = g.n;
+    const bool all = 2 * wc >= n;
+    if (CONTIG) {
+        if (all) {
+            for (int i = lane; i < n; i += 32) xl[i] += alpha * x_uh[i] + beta * x_lh[i];
+        } else {
+            for (int i = lane; i < wc; i += 32) xl[i] += alpha * x_uh[i] + beta * x_lh[i];
+            for (int i = n - wc + lane; i < n; i += 32) xl[i] += alpha * x_uh[i] + beta * x_lh[i];
+        }
+    } else {
+        if (all) {
+            for (int i = 0; i < n; i++) xl[(long)i * g.inner] += alpha * x_uh[i] + beta * x_lh[i];
+        } else {
+            for (int i = 0; i < wc; i++) xl[(long)i * g.inner] += alpha * x_uh[i] + beta * x_lh[i];
+            for (int i = n - wc; i < n; i++) xl[(long)i * g.inner] += alpha * x_uh[i] + beta * x_lh[i];
+        }
+    }
+}
+
+// Thread-parallel Thomas over interleaved systems sharing one matrix (reference reducedSolverKernel,
+// code/cuda/kernels.cu:115-145).  lu = [3][n]: a_i, 1/pivot_i, c_i/pivot_i.
+__global__ void pthomas_kernel(double *__restrict__ d, const double *__restrict__ lu, int n, long nsys)
+{
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    const double *a = lu, *ip = lu + n, *cp = lu + 2 * n;
+    double prev = d[s] * ip[0];
+    d[s] = prev;
+    for (int i = 1; i < n; i++) {
+        prev = (d[s + (long)i * nsys] - a[i] * prev) * ip[i];
+        d[s + (long)i * nsys] = prev;
+    }
+    for (int i = n - 2; i >= 0; i--) {
+        prev = d[s + (long)i * nsys] - cp[i] * prev;
+        d[s + (long)i * nsys] = prev;
+    }
+}
+
+}  // namespace cfd

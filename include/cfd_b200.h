@@ -1,0 +1,126 @@
+/*
+ * cfd_b200.h -- C ABI of libcfd_b200.so: the B200-native compact finite-difference derivative path.
+ *
+ * The reference (ashwinsrnth/compact-finite-differences) has no C ABI: its boundary is a set of Python
+ * classes that launch runtime-compiled `extern "C"` kernels through PyCUDA `prepared_call`
+ * (code/cuda/kernels.py:14-23).  This header is the boundary a maintainer of the reference would bind
+ * instead (ctypes stub in INTEGRATION.md).  Each entry point names the reference interface it replaces.
+ *
+ * Conventions (kept from the reference):
+ *   - fields are fp64, C order f[nz][ny][nx] (x fastest); axis numbering 0 = x, 1 = y, 2 = z
+ *     (code/cuda/gpuDA.py:162);
+ *   - every field pointer is a DEVICE pointer owned by the caller (code/cuda/compact.py:29); plans own only
+ *     small coefficient tables (code/cuda/solvers/templated/near_toeplitz.py:62-69);
+ *   - the tridiagonal solve is in place (near_toeplitz.py:78); the derivative is out of place (f -> df);
+ *   - calls are asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL = default
+ *     stream), never allocate, never synchronise -- except the *_host convenience calls, which are
+ *     synchronous and own their staging buffers;
+ *   - every function returns 0 on success or a negative CFD_E* code; cfd_last_error() gives the text.
+ *     Nothing throws, nothing exits.  There is no CPU fallback: without a CUDA device create() fails
+ *     with CFD_ECUDA.
+ *
+ * Constraints (narrower in the reference: nx a power of two <= 2048, extents multiples of 8/16):
+ *   n (extent along the axis) >= 3; nx even (16-byte row pitch for TMA); pointers 16-byte aligned.
+ */
+#ifndef CFD_B200_H
+#define CFD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFD_B200_VERSION 100
+
+#define CFD_OK            0
+#define CFD_EINVAL       (-1)   /* bad shape / axis / pointer / coefficient                    */
+#define CFD_ECUDA        (-2)   /* CUDA runtime or driver error (text in cfd_last_error)        */
+#define CFD_EUNSUPPORTED (-3)   /* valid request this build cannot serve                        */
+
+typedef struct cfd_plan cfd_plan;   /* derivative operator for one (shape, axis, spacing, rank position) */
+typedef struct nt_plan nt_plan;     /* batched near-Toeplitz tridiagonal solver                          */
+
+int cfd_version(void);
+const char *cfd_last_error(void);   /* thread-local text of the last failure */
+
+/* ---------------------------------------------------------------------------------------------------
+ * Derivative operator.
+ * Replaces CompactFiniteDifferenceSolver.__init__ (code/cuda/compact.py:18-27, coefficient choice
+ * :159-173) for one direction.  (part_rank, part_size) is the position of this block along the
+ * derivative line, exactly the reference's (line_da.rank, line_da.size): rank 0 carries the left
+ * closure row [1 2], rank size-1 the right closure row [2 1], other block ends are the cut Toeplitz
+ * rows.  part_size == 1 is the single-GPU operator.
+ * ------------------------------------------------------------------------------------------------- */
+int cfd_create(cfd_plan **plan, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size);
+void cfd_destroy(cfd_plan *plan);
+
+/* df = local solution x_R of the block: Pade RHS (code/cuda/kernels.cu:4-47 computeRHS) fused with the
+ * block's tridiagonal solve (NearToeplitzSolver.solve, templated/near_toeplitz.py:78-107) -- one kernel,
+ * f read once, df written once.  halo_lo / halo_hi: the neighbour's boundary plane of f (what
+ * DA.global_to_local, code/cuda/gpuDA.py:61-132, puts in the ghost layer), one value per line, laid out
+ * like a plane of the field with the axis removed; NULL where the block owns the physical end.
+ * With part_size == 1 this IS the derivative (replaces dfdx, compact.py:29-44; dfdy/dfdz,
+ * code/ocl/compact.py:41-61). */
+int cfd_apply(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+              void *stream);
+
+/* Interface right-hand side of the reduced system: faces[0] = -x_R[first], faces[1] = -x_R[last], zero
+ * at physical ends.  faces is [2][plane].  Replaces negateAndCopyFaces (code/cuda/kernels.cu:76-113). */
+int cfd_interface_pack(cfd_plan *plan, const double *df, double *faces, void *stream);
+
+/* faces_all = the all-gathered [2*part_size][plane] interface planes of every rank along the line.
+ * Solves the 2P-unknown reduced system per line (rows of code/cuda/compact.py:96-111; Thomas as in
+ * reducedSolverKernel, kernels.cu:115-145) redundantly on this rank and adds
+ * alpha * x_UH + beta * x_LH to df (sumSolutions, kernels.cu:49-74; secondary systems
+ * compact.py:128-154 are precomputed at cfd_create).  Only planes whose correction exceeds fp64
+ * round-off are touched. */
+int cfd_reduced_correct(cfd_plan *plan, double *df, const double *faces_all, void *stream);
+
+/* Synchronous host-buffer form of cfd_apply for part_size == 1 (what the reference's OpenCL flavour
+ * offers: ndarray in, ndarray out, code/ocl/compact.py:26-61).  Copies f to the device, runs the kernel,
+ * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory. */
+int cfd_apply_host(cfd_plan *plan, const double *f_host, double *df_host, int pinned);
+
+/* plane = number of lines of the block (elements of one halo / interface plane). */
+long cfd_plane_elems(const cfd_plan *plan);
+
+/* Debug/inspection: copies the plan's host tables (test infrastructure reads them to emulate the
+ * kernel's chunked recurrences on the CPU).  out must hold cfd_tables_size() doubles. */
+int cfd_tables_size(void);
+int cfd_plan_tables(const cfd_plan *plan, double *out);
+/* Host-only (no device): tables for a line of n rows of the matrix coeffs = [b1,c1,ai,bi,ci,an,bn];
+ * same layout as cfd_plan_tables except out[.. + 7] = 1 if the streaming fast path accepts the matrix. */
+int cfd_debug_tables(int n, const double coeffs[7], double scale, double *out);
+int cfd_debug_secondary(int n, int part_rank, int part_size, double *x_uh, double *x_lh, double *ra, double *rb,
+                        double *rc);
+/* secondary solutions x_UH, x_LH (each n doubles) and the reduced matrix a,b,c (each 2*part_size). */
+int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double *ra, double *rb, double *rc);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Batched near-Toeplitz solver.
+ * Replaces NearToeplitzSolver(shape, coeffs) / .solve(x_d)
+ * (code/cuda/solvers/templated/near_toeplitz.py:36-107; globalmem/near_toeplitz.py).
+ * coeffs = [b1, c1, ai, bi, ci, an, bn]; solves, in place, every line of d[nz][ny][nx] along `axis`
+ * (the reference solves along x only).
+ * ------------------------------------------------------------------------------------------------- */
+int nt_create(nt_plan **plan, int nz, int ny, int nx, int axis, const double coeffs[7]);
+int nt_solve(nt_plan *plan, double *d, void *stream);
+void nt_destroy(nt_plan *plan);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Thread-parallel Thomas for `nsys` interleaved systems sharing one general tridiagonal matrix.
+ * Replaces ReducedSolver.solve / reducedSolverKernel (code/cuda/reduced.py:5-18,
+ * code/cuda/kernels.cu:115-145).  a, b, c: HOST arrays of length n (a[0], c[n-1] ignored);
+ * d: DEVICE array [n][nsys], solved in place.  n <= 256.
+ * ------------------------------------------------------------------------------------------------- */
+int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream);
+
+/* Tuning knobs for experiments (0 = built-in default).  Not part of the reference surface. */
+int cfd_set_launch(int warps_per_cta, int ctas_per_sm);
+
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+long cfd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,250 @@
+"""
+Parity of the CUDA path (through the C ABI, via the Python mirror of the reference classes) against the oracle.
+Tolerance: <= 1e-12 relative L-infinity (BASELINE.json north_star), written in TOL below.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cfd_oracle as O
+from tests.conftest import GOLD
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def relinf(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.fixture(scope="module")
+def C():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import compact_finite_differences_b200 as pkg
+    return pkg
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def smooth(shape):
+    nz, ny, nx = shape
+    z, y, x = np.meshgrid(np.linspace(0, 2 * np.pi, nz), np.linspace(0, 2 * np.pi, ny),
+                          np.linspace(0, 2 * np.pi, nx), indexing="ij")
+    return x, y, z
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures generated from the reference itself (oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------------
+def test_golden_derivative_fixture(C):
+    g = np.load(os.path.join(GOLD, "derivative.npz"))
+    f = g["f"]
+    fd = dev(f)
+    for axis in range(3):
+        s = C.CompactFiniteDifferenceSolver(f.shape, float(g[f"h_{axis}"]), axis)
+        got = s(fd).cpu().numpy()
+        assert relinf(got, g[f"df_{axis}"]) <= TOL
+
+
+def test_golden_npts_fixture(C):
+    g = np.load(os.path.join(GOLD, "npts_ref.npz"))
+    for n in (8, 32, 48, 64, 100, 256, 1024):
+        r, u = g[f"r_{n}"], g[f"u_{n}"]
+        d = dev(r)
+        C.NearToeplitzSolver(r.shape, O.PADE).solve(d)
+        assert relinf(d.cpu().numpy(), u) <= TOL
+
+
+@pytest.mark.parametrize("n", [32, 64, 128, 256])
+def test_known_answer(C, n):
+    """BASELINE configs[0]: d/dx sin, 'Average absolute error' of the reference's test_npts."""
+    known = {32: "0.0000293338", 64: "0.0000010363", 128: "0.0000000420", 256: "0.0000000019"}
+    m = min(n, 64)
+    x = np.arange(n) * (2 * np.pi / (n - 1))
+    f = np.broadcast_to(np.sin(x), (m, m, n)).copy()
+    s = C.CompactFiniteDifferenceSolver(f.shape, 2 * np.pi / (n - 1), 0)
+    df = s(dev(f)).cpu().numpy()
+    assert "%.10f" % np.mean(np.abs(np.cos(x) - df)) == known[n]
+
+
+# ---------------------------------------------------------------------------------------------------
+# derivative vs oracle on seeded random fields: ragged shapes, every axis
+# ---------------------------------------------------------------------------------------------------
+SHAPES = [(8, 8, 8), (8, 32, 16), (4, 6, 10), (5, 7, 34), (33, 31, 32), (16, 65, 66), (64, 64, 64), (70, 40, 96),
+          (3, 5, 130), (129, 4, 6), (6, 200, 8), (32, 32, 256), (40, 130, 34)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_derivative_random(C, shape, axis):
+    if shape[2 - axis] < 4:
+        pytest.skip("line shorter than 4")
+    rng = np.random.default_rng(hash((shape, axis)) % 2 ** 32)
+    f = rng.random(shape)
+    h = 0.01 + 0.1 * axis
+    want = O.derivative(f, axis, h)
+    got = C.CompactFiniteDifferenceSolver(shape, h, axis)(dev(f)).cpu().numpy()
+    assert relinf(got, want) <= TOL
+
+
+def test_reference_spellings_and_analytic(C):
+    """code/ocl/test/test_compact.py:15-73 (decimal=2) through dfdx / dfdy / dfdz."""
+    shape = (16, 32, 32)
+    x, y, z = smooth(shape)
+    s = C.CompactFiniteDifferenceSolver(shape)
+    dx, dy, dz = x[0, 0, 1] - x[0, 0, 0], y[0, 1, 0] - y[0, 0, 0], z[1, 0, 0] - z[0, 0, 0]
+    np.testing.assert_almost_equal(s.dfdx(dev(np.sin(x)), dx).cpu().numpy(), np.cos(x), decimal=2)
+    np.testing.assert_almost_equal(s.dfdx(dev(x * y * z), dx).cpu().numpy(), y * z, decimal=2)
+    np.testing.assert_almost_equal(s.dfdy(dev(np.sin(y)), dy).cpu().numpy(), np.cos(y), decimal=2)
+    np.testing.assert_almost_equal(s.dfdy(dev(x * y * z), dy).cpu().numpy(), x * z, decimal=2)
+    np.testing.assert_almost_equal(s.dfdz(dev(x * y * z ** 2), dz).cpu().numpy(), 2 * x * y * z, decimal=1)
+
+
+def test_host_buffer_path(C):
+    rng = np.random.default_rng(11)
+    f = rng.random((12, 20, 64))
+    s = C.CompactFiniteDifferenceSolver(f.shape, 0.05, 1)
+    assert relinf(s(f), O.derivative(f, 1, 0.05)) <= TOL
+
+
+def test_256_cubed_all_axes(C):
+    """BASELINE configs[1]: 256^3, x, y, z, smooth field, full-field parity + analytic derivative."""
+    import torch
+    n = 256
+    x, y, z = smooth((n, n, n))
+    f = np.sin(x) * np.cos(y) * np.sin(z)
+    h = 2 * np.pi / (n - 1)
+    fd = dev(f)
+    exact = [np.cos(x) * np.cos(y) * np.sin(z), -np.sin(x) * np.sin(y) * np.sin(z), np.sin(x) * np.cos(y) * np.cos(z)]
+    O.port().oracle_set_num_threads(os.cpu_count() or 1)
+    for axis in range(3):
+        got = C.CompactFiniteDifferenceSolver((n, n, n), h, axis)(fd).cpu().numpy()
+        assert relinf(got, O.derivative(f, axis, h)) <= TOL
+        assert np.abs(got - exact[axis]).max() < 1e-6
+    torch.cuda.synchronize()
+
+
+def test_512_cubed_properties(C):
+    """BASELINE configs[2] at full size through size-independent properties: sampled-line parity with the
+    oracle (4096 random lines + the boundary lines per axis), linearity, analytic derivative."""
+    import torch
+    n = 512
+    h = 2 * np.pi / (n - 1)
+    t = torch.linspace(0, 2 * np.pi, n, dtype=torch.float64, device="cuda")
+    z, y, x = t[:, None, None], t[None, :, None], t[None, None, :]
+    f = (torch.sin(x) * torch.cos(y) * torch.sin(z)).contiguous()
+    g = (x * torch.cos(x * y) + y * torch.sin(z)).contiguous()          # reference demo field, run.py:29-30
+    rng = np.random.default_rng(512)
+    for axis in range(3):
+        s = C.CompactFiniteDifferenceSolver((n, n, n), h, axis)
+        df, dg = s(f), s(g)
+        comb = s((2.0 * f - 0.5 * g).contiguous())
+        lin = (comb - (2.0 * df - 0.5 * dg)).abs().max().item() / comb.abs().max().item()
+        assert lin < 1e-13                                              # linearity of the operator
+        # sampled lines against the oracle
+        ax = 2 - axis
+        fl = torch.movedim(g, ax, 2).reshape(-1, n)
+        dl = torch.movedim(dg, ax, 2).reshape(-1, n)
+        idx = np.unique(np.concatenate([rng.integers(0, n * n, 4096), [0, n - 1, n * n - n, n * n - 1]]))
+        it = torch.from_numpy(idx).cuda()
+        lines = fl[it].cpu().numpy()
+        want = O.derivative(lines.reshape(1, -1, n), 0, h).reshape(-1, n)
+        assert relinf(dl[it].cpu().numpy(), want) <= TOL
+        exact = [torch.cos(x) * torch.cos(y) * torch.sin(z), -torch.sin(x) * torch.sin(y) * torch.sin(z),
+                 torch.sin(x) * torch.cos(y) * torch.cos(z)][axis]
+        assert (df - exact).abs().max().item() < 1e-7
+        del df, dg, comb
+
+
+# ---------------------------------------------------------------------------------------------------
+# solver-only API
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [32, 64, 128, 512, 1024, 4096])
+def test_near_toeplitz_pade(C, n):
+    rng = np.random.default_rng(n)
+    d = rng.random((4, 37, n))
+    t = dev(d)
+    C.NearToeplitzSolver(d.shape, O.PADE).solve(t)
+    assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, O.PADE)) <= TOL
+
+
+@pytest.mark.parametrize("axis", [1, 2])
+def test_near_toeplitz_other_axes(C, axis):
+    rng = np.random.default_rng(axis)
+    d = rng.random((96, 130, 40))
+    t = dev(d)
+    C.NearToeplitzSolver(d.shape, O.PADE, axis=axis).solve(t)
+    assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, O.PADE, axis)) <= TOL
+
+
+def test_near_toeplitz_general_coefficients(C):
+    """code/ocl/test/test_near_toeplitz.py:31-48: (1,2,3,4,5,6,7), shape (1,1,32), vs LAPACK, rtol 1e-7."""
+    rng = np.random.default_rng(0)
+    co = (1., 2., 3., 4., 5., 6., 7.)
+    d = rng.random((1, 1, 32))
+    t = dev(d)
+    C.NearToeplitzSolver((1, 1, 32), co).solve(t)
+    np.testing.assert_allclose(t.cpu().numpy(), O.scipy_solve_axis(d, co, 0), rtol=1e-7)
+    assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, co)) <= TOL
+
+
+def test_near_toeplitz_round_trip(C):
+    """A x == d for the solved x (matrix applied with torch on the device), large batch."""
+    import torch
+    n, batch = 2048, 4096
+    d = torch.rand((1, batch, n), dtype=torch.float64, device="cuda")
+    x = d.clone()
+    C.NearToeplitzSolver((1, batch, n), O.PADE).solve(x)
+    ax = x.clone()
+    ax[..., 1:-1] = 0.25 * x[..., :-2] + x[..., 1:-1] + 0.25 * x[..., 2:]
+    ax[..., 0] = x[..., 0] + 2 * x[..., 1]
+    ax[..., -1] = 2 * x[..., -2] + x[..., -1]
+    assert (ax - d).abs().max().item() < 1e-13
+
+
+def test_pthomas(C):
+    """code/cuda/test/test_kernels.py:29-53."""
+    rng = np.random.default_rng(4)
+    n = 32
+    a, b, c = rng.random(n), rng.random(n) + 2, rng.random(n)
+    d = rng.random((n, 2, 2))
+    t = dev(d)
+    C.ReducedSolver((n, 2, 2)).solve(a, b, c, None, t)
+    np.testing.assert_allclose(t.cpu().numpy(), O.pthomas(a, b, c, d), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# partitioned line on ONE device: all ranks' blocks processed in turn through the multi-rank entry points
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("axis,P,shape", [(2, 2, (64, 24, 40)), (2, 4, (128, 16, 34)), (2, 8, (256, 8, 32)),
+                                           (0, 4, (6, 10, 128)), (1, 2, (5, 80, 36))])
+def test_partitioned_line_emulated(C, axis, P, shape):
+    import torch
+    rng = np.random.default_rng(P + axis)
+    f = rng.random(shape)
+    h = 0.13
+    want = O.derivative(f, axis, h)
+    ax = 2 - axis
+    n = shape[ax] // P
+    blocks = [np.ascontiguousarray(np.take(f, range(r * n, (r + 1) * n), axis=ax)) for r in range(P)]
+    lshape = blocks[0].shape
+    solvers = [C.CompactFiniteDifferenceSolver(lshape, h, axis, part=(r, P)) for r in range(P)]
+    plane = blocks[0].size // n
+    outs, faces = [], torch.empty((2 * P, plane), dtype=torch.float64, device="cuda")
+    for r in range(P):
+        fb = dev(blocks[r])
+        lo = dev(np.take(blocks[r - 1], n - 1, axis=ax)) if r > 0 else None
+        hi = dev(np.take(blocks[r + 1], 0, axis=ax)) if r < P - 1 else None
+        out = solvers[r].apply_local(fb, None, lo, hi)
+        solvers[r].interface_pack(out, faces[2 * r:2 * r + 2])
+        outs.append(out)
+    for r in range(P):
+        solvers[r].reduced_correct(outs[r], faces)
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=ax)
+    assert relinf(got, want) <= TOL
+    assert relinf(got, O.partition_derivative(f, axis, h, P)) <= TOL

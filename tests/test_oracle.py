@@ -1,0 +1,121 @@
+"""Pin the oracle: golden vectors of the reference, reference npts.c == C port == SciPy banded LU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cfd_oracle as O
+from tests.conftest import GOLD
+
+KNOWN = {32: "0.0000293338", 64: "0.0000010363", 128: "0.0000000420", 256: "0.0000000019"}
+
+
+def relinf(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("n", sorted(KNOWN))
+def test_known_answer_port(n):
+    """d/dx sin on [0, 2pi]: mean |cos - df| printed by the reference's test_npts (test_npts.c:146-157)."""
+    x = np.arange(n) * (2 * np.pi / (n - 1))
+    f = np.broadcast_to(np.sin(x), (2, 3, n)).copy()
+    df = O.derivative(f, 0, 2 * np.pi / (n - 1))
+    assert "%.10f" % np.mean(np.abs(np.cos(x) - df)) == KNOWN[n]
+
+
+def test_known_answer_fixture_matches_reference_output():
+    ka = np.load(os.path.join(GOLD, "known_answer.npz"))
+    for n, v in KNOWN.items():
+        assert str(ka[str(n)]) == "Average absolute error: " + v
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built on this box")
+@pytest.mark.parametrize("n", [32, 64])
+def test_known_answer_reference_binary(n):
+    assert O.ref_known_answer(n) == "Average absolute error: " + KNOWN[n]
+
+
+def test_port_matches_reference_fixture():
+    """Committed output of the reference's own npts.c (one rank) on seeded RHS."""
+    g = np.load(os.path.join(GOLD, "npts_ref.npz"))
+    for n in (8, 32, 48, 64, 100, 256, 1024):
+        r, u = g[f"r_{n}"], g[f"u_{n}"]
+        beta, gam = O.npts_beta_gam(n)
+        assert np.array_equal(beta, g[f"beta_{n}"]) and np.array_equal(gam, g[f"gam_{n}"])
+        assert relinf(O.npts_solve(r, 0), u) < 1e-15
+        assert relinf(O.near_toeplitz_solve(r, O.PADE, 0), u) < 1e-14
+        assert relinf(O.scipy_solve_axis(r, O.PADE, 0), u) < 1e-14
+        if n & (n - 1) == 0:
+            assert relinf(O.cr_solve(r, O.PADE), u) < 1e-14      # the reference GPU algorithm, restated
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built on this box")
+def test_port_matches_live_reference():
+    rng = np.random.default_rng(1)
+    for n in (16, 128, 512):
+        r = rng.random((3, 4, n))
+        u, beta, gam = O.ref_npts_solve(r)
+        assert relinf(O.npts_solve(r, 0), u) < 1e-15
+
+
+def test_derivative_fixture_all_axes():
+    g = np.load(os.path.join(GOLD, "derivative.npz"))
+    f = g["f"]
+    for axis in range(3):
+        h = float(g[f"h_{axis}"])
+        assert relinf(O.derivative(f, axis, h), g[f"df_{axis}"]) < 1e-14
+        assert relinf(O.scipy_derivative(f, axis, h), g[f"df_{axis}"]) < 1e-14
+
+
+def test_rhs_formulas():
+    """code/cuda/kernels.cu:34,38,44 written out by hand for one line."""
+    rng = np.random.default_rng(2)
+    f = rng.random((1, 1, 9))
+    h = 0.3
+    r = O.rhs(f, 0, h)[0, 0]
+    l = f[0, 0]
+    assert r[0] == (1. / (2 * h)) * (-5 * l[0] + 4 * l[1] + l[2])
+    assert r[8] == -(1. / (2 * h)) * (-5 * l[8] + 4 * l[7] + l[6])
+    for i in range(1, 8):
+        assert r[i] == (3. / (4 * h)) * (l[i + 1] - l[i - 1])
+
+
+def test_general_coefficients_vs_lapack():
+    """code/ocl/test/test_near_toeplitz.py:31-48: (1,2,3,4,5,6,7), n = 32, random RHS, rtol 1e-7."""
+    rng = np.random.default_rng(3)
+    co = (1., 2., 3., 4., 5., 6., 7.)
+    d = rng.random((1, 1, 32))
+    want = O.scipy_solve_axis(d, co, 0)
+    np.testing.assert_allclose(O.near_toeplitz_solve(d, co), want, rtol=1e-7)
+    np.testing.assert_allclose(O.cr_solve(d, co), want, rtol=1e-7)
+
+
+def test_pthomas_vs_lapack():
+    """code/cuda/test/test_kernels.py:29-53: strided systems d[32,2,2], random a, b, c."""
+    rng = np.random.default_rng(4)
+    n = 32
+    a, b, c = rng.random(n), rng.random(n) + 2, rng.random(n)
+    d = rng.random((n, 2, 2))
+    want = O.scipy_solve_banded(a, b, c, d.reshape(n, -1)).reshape(d.shape)
+    np.testing.assert_allclose(O.pthomas(a, b, c, d), want, rtol=1e-7)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("P", [2, 4])
+def test_partition_algebra(axis, P):
+    """The reference's multi-rank method (compact.py:65-154) reproduces the one-rank derivative."""
+    rng = np.random.default_rng(5)
+    f = rng.random((16, 24, 32))
+    assert relinf(O.partition_derivative(f, axis, 0.1, P), O.scipy_derivative(f, axis, 0.1)) < 1e-14
+
+
+def test_analytic_fields():
+    """Known-answer fields of the reference tests (code/ocl/test/test_compact.py:15-73), decimal=2."""
+    n = 32
+    z, y, x = np.meshgrid(*(np.linspace(0, 2 * np.pi, n),) * 3, indexing="ij")
+    h = 2 * np.pi / (n - 1)
+    np.testing.assert_almost_equal(O.derivative(np.sin(x), 0, h), np.cos(x), decimal=2)
+    np.testing.assert_almost_equal(O.derivative(x * y * z, 0, h), y * z, decimal=2)
+    np.testing.assert_almost_equal(O.derivative(np.sin(y), 1, h), np.cos(y), decimal=2)
+    np.testing.assert_almost_equal(O.derivative(x * y * z, 1, h), x * z, decimal=2)
+    np.testing.assert_almost_equal(O.derivative(x * y * z ** 2, 2, h), 2 * x * y * z, decimal=2)
