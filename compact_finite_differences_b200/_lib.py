@@ -32,7 +32,7 @@ SIGNATURES = {
     "nt_solve": (_i, [_vp, _vp, _vp]),
     "nt_destroy": (None, [_vp]),
     "cfd_pthomas": (_i, [_dp, _dp, _dp, _vp, _i, _l, _vp]),
-    "cfd_set_launch": (_i, [_i, _i]),
+    "cfd_set_launch": (_i, [_i, _i, _i]),
     "cfd_launch_count": (_l, []),
 }
 

@@ -23,7 +23,7 @@ using namespace cfd;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long> g_launches{0};
-static int g_warps = 0, g_ctas = 0;
+static int g_warps = 0, g_ctas = 0, g_slots = 0;
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -45,12 +45,14 @@ static int fail(int code, const char *fmt, ...)
 extern "C" const char *cfd_last_error(void) { return g_err.c_str(); }
 extern "C" int cfd_version(void) { return CFD_B200_VERSION; }
 extern "C" long cfd_launch_count(void) { return g_launches.load(); }
-extern "C" int cfd_set_launch(int warps_per_cta, int ctas_per_sm)
+extern "C" int cfd_set_launch(int warps_per_cta, int ctas_per_sm, int ring_slots)
 {
-    if (warps_per_cta < 0 || warps_per_cta > 9 || ctas_per_sm < 0 || ctas_per_sm > 8)
-        return fail(CFD_EINVAL, "cfd_set_launch(%d, %d): out of range", warps_per_cta, ctas_per_sm);
+    if (warps_per_cta < 0 || warps_per_cta > 8 || ctas_per_sm < 0 || ctas_per_sm > 8 ||
+        (ring_slots != 0 && (ring_slots < 3 || ring_slots > 5)))
+        return fail(CFD_EINVAL, "cfd_set_launch(%d, %d, %d): out of range", warps_per_cta, ctas_per_sm, ring_slots);
     g_warps = warps_per_cta;
     g_ctas = ctas_per_sm;
+    g_slots = ring_slots;
     return CFD_OK;
 }
 
@@ -161,26 +163,55 @@ static int device_info(DeviceInfo &d)
     return CFD_OK;
 }
 
-template <bool CONTIG, bool DERIV>
-static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                         cudaStream_t stream)
+// Work counters: a ring of {next bundle, finished warps} pairs, one pair per in-flight launch.
+// Each kernel leaves its pair zeroed, so re-use after COUNTER_RING launches needs no memset.
+constexpr int COUNTER_RING = 4096;
+static unsigned long long *g_counters = nullptr;
+static std::atomic<unsigned long> g_launch_seq{0};
+
+static int counter_pair(unsigned long long **out)
+{
+    if (!g_counters) {
+        unsigned long long *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, sizeof(unsigned long long) * 2 * COUNTER_RING));
+        CUDA_TRY(cudaMemset(p, 0, sizeof(unsigned long long) * 2 * COUNTER_RING));
+        g_counters = p;
+    }
+    *out = g_counters + 2 * (g_launch_seq++ % COUNTER_RING);
+    return CFD_OK;
+}
+
+template <bool CONTIG, bool DERIV, int NSLOT>
+static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                            cudaStream_t stream)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
-    constexpr int per_warp = (NS + (CONTIG ? 1 : 0)) * SLOT_BYTES;
-    const int max_warps = CONTIG ? 7 : 8;   // register file is 16K per SM sub-partition: <= 2 warps each at ~240 regs
-    int warps = g_warps ? g_warps : max_warps;
+    constexpr int per_warp = (NSLOT + (CONTIG ? 1 : 0)) * SLOT_BYTES + NSLOT * 16;
+    // Measured on B200 at 512^3 (scripts/sweep_launch.py, profiles/r1_sweep_launch_512.txt):
+    //   CONTIG : 4 warps/SM is fastest (0.3375 ms); 5-7 warps cost 1-2 %.
+    //   STRIDED: its longer per-tile instruction stream needs 6 warps/SM (0.344 ms); 4 -> 0.47 ms, 8 -> 0.353 ms.
+    // The register file (16K per SM sub-partition, ~240 regs/thread) caps a CTA at 8 warps.
+    const int max_warps = CONTIG ? 7 : 8;
+    int warps = g_warps ? g_warps : (CONTIG ? 4 : 6);
     if (warps > max_warps) warps = max_warps;
     int ctas = g_ctas ? g_ctas : 1;
-    auto smem_for = [&](int w) { return (size_t)w * per_warp + (size_t)w * NS * 8 + 1024; };
-    while (warps > 1 && (long)ctas * (long)(smem_for(warps) + 1024) > 232448L) warps--;
+    if (!g_warps) {   // small problems: spread the bundles over all SMs before stacking warps on one
+        const long per_sm = (g.nb + dinfo.sms - 1) / dinfo.sms;
+        if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    }
+    auto smem_for = [&](int w) { return (size_t)w * per_warp + 1024; };
+    while (warps > 1 && ((long)ctas * (long)(smem_for(warps) + 1024) > 233472L || (long)ctas * warps > 8)) warps--;
     const size_t smem = smem_for(warps);
-    auto kern = stream_kernel<CONTIG, DERIV>;
+    if (smem > 232448) return fail(CFD_EUNSUPPORTED, "ring of %d slots does not fit shared memory", NSLOT);
+    auto kern = stream_kernel<CONTIG, DERIV, NSLOT>;
     static size_t configured = 0;
     if (configured < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(max_warps)));
-        configured = smem_for(max_warps);
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
+    int rc = counter_pair(&kp.counter);
+    if (rc) return rc;
     long blocks = (g.nb + warps - 1) / warps;
     const long cap = (long)dinfo.sms * ctas;
     if (blocks > cap) blocks = cap;
@@ -188,6 +219,18 @@ static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
+}
+
+template <bool CONTIG, bool DERIV>
+static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                         cudaStream_t stream)
+{
+    switch (g_slots ? g_slots : 3) {
+        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream);
+        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream);
+        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream);
+        default: return fail(CFD_EINVAL, "ring slots must be 3, 4 or 5");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

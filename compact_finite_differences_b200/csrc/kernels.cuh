@@ -36,7 +36,6 @@
 
 namespace cfd {
 
-constexpr int NS = 3;             // ring slots per warp (tile k, tile k+1 for the stencil peek, one in flight)
 constexpr int SLOT_BYTES = CH * CH * 8;   // 8 KiB
 
 struct KParams {
@@ -53,6 +52,7 @@ struct KParams {
     double s0c, snc;   // beta_0/(2h), beta_{n-1}/(2h) for the closure rows
     const double *halo_lo, *halo_hi;   // neighbour planes of f (multi-rank), one value per line
     double *out;       // STRIDED: destination field
+    unsigned long long *counter;   // {next bundle, finished warps}, zero on entry, zero again on exit
     RowTab head, tail;
 };
 
@@ -223,71 +223,88 @@ __device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH
 
 // ------------------------------------------------------------------------------------------------
 // The streaming kernel.
+//   NS   = ring slots per warp (>= 3: tile k, tile k+1 for the stencil peek, the rest in flight).
+//   Work distribution is DYNAMIC: a warp draws its next 32-line bundle from a global counter when its
+//   producer lane starts prefetching it, so SMs that see less memory bandwidth (fuller GPCs, far L2
+//   slices) simply take fewer bundles and all warps run dry together.  The counter pair
+//   {next bundle, finished warps} is reset by the last warp to finish, so a launch needs no memset.
 // ------------------------------------------------------------------------------------------------
-template <bool CONTIG, bool DERIV>
+template <bool CONTIG, bool DERIV, int NS>
 __global__ void __launch_bounds__(CONTIG ? 224 : 256, 1)
 stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
               const __grid_constant__ KParams p)
 {
     extern __shared__ unsigned char smem_raw[];
     constexpr int PER_WARP = (NS + (CONTIG ? 1 : 0)) * SLOT_BYTES;
+    constexpr int CTRL = NS * 16;       // per warp: NS mbarriers + NS bundle tags
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     // 1 KiB alignment in the shared window (128B swizzle atom = 8 rows x 128 B)
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *wbase = base + warp * PER_WARP;
     unsigned char *oslot = wbase + NS * SLOT_BYTES;                      // CONTIG only
-    const uint32_t bar0 = smem_u32(base + nwarps * PER_WARP) + warp * (NS * 8);
+    unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
+    const uint32_t bar0 = smem_u32(ctrl);
+    volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
 
-    const long G = (long)gridDim.x * nwarps;
-    const long gw = (long)blockIdx.x * nwarps + warp;
-    if (gw >= p.nb) return;
-    const long T = ((p.nb - gw + G - 1) / G) * p.K;
     const int K = p.K;
+    const long nb = p.nb;
 
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
         fence_mbar_init();
-        fence_async_smem();
     }
     __syncwarp();
 
-    // ---- producer side (lane 0): flat tile sequence, NS ahead
-    long ib = gw;   // bundle of the next tile to issue
-    int ik = 0;     // chunk of the next tile to issue
+    // ---- producer side (lane 0): one call per tile position, NS positions ahead of the consumer
+    long ib = 0;          // bundle being prefetched
+    int ik = 0;           // its next chunk
     int islot = 0;
+    bool dry = false;
     auto issue = [&]() {
-        const uint32_t bar = bar0 + 8 * islot;
-        const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
-        mbar_expect_tx(bar, SLOT_BYTES);
-        if constexpr (CONTIG) {
-            tma_load_2d(dst, &tm_in, bar, ik * CH, (int)(ib * CH));
-            tma_load_2d(dst + 4096, &tm_in, bar, ik * CH + 16, (int)(ib * CH));
-        } else {
-            const int o = (int)(ib / p.inner_tiles), it = (int)(ib % p.inner_tiles);
-            tma_load_3d(dst, &tm_in, bar, it * CH, ik * CH, o);
+        if (ik == 0 && !dry) {
+            ib = (long)atomicAdd(p.counter, 1ULL);
+            dry = ib >= nb;
         }
-        if (++ik == K) { ik = 0; ib += G; }
+        if (dry) {
+            tag[islot] = -1;
+        } else {
+            tag[islot] = ib;
+            const uint32_t bar = bar0 + 8 * islot;
+            const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
+            mbar_expect_tx(bar, SLOT_BYTES);
+            if constexpr (CONTIG) {
+                tma_load_2d(dst, &tm_in, bar, ik * CH, (int)(ib * CH));
+                tma_load_2d(dst + 4096, &tm_in, bar, ik * CH + 16, (int)(ib * CH));
+            } else {
+                const int o = (int)(ib / p.inner_tiles), it = (int)(ib % p.inner_tiles);
+                tma_load_3d(dst, &tm_in, bar, it * CH, ik * CH, o);
+            }
+            if (++ik == K) ik = 0;
+        }
         if (++islot == NS) islot = 0;
     };
     if (lane == 0) {
-        const int pre = T < NS ? (int)T : NS;
-        for (int s = 0; s < pre; s++) issue();
+#pragma unroll 1
+        for (int s = 0; s < NS; s++) issue();
     }
+    __syncwarp();
 
     // ---- consumer side (all lanes)
     double eA[CH], eB[CH], F[CH];
     double eprev = 0.0, fm1 = 0.0, fm2 = 0.0, hval = 0.0;
-    long b = gw;
+    long b = 0;
     int k = 0, slot = 0;
     uint32_t phase = 0;
     bool lane_ok = true;
     double *gcol = nullptr;       // STRIDED: &out[(o*n + 0)*inner + col]
     const long gstride = CONTIG ? 0 : (long)p.inner;
 
-    for (long t = 0; t < T; ++t) {
+    for (;;) {
         if (k == 0) {
+            b = tag[slot];
+            if (b < 0) break;
             long line;
             if constexpr (CONTIG) {
                 line = b * CH + lane;
@@ -322,9 +339,10 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         else if (last) fwd_chunk<2, DERIV>(p, F, peek, hval, true, eB, eprev, fm1, fm2);
         else           fwd_chunk<0, DERIV>(p, F, peek, hval, false, eB, eprev, fm1, fm2);
 
-        // the slot has been consumed into registers: refill it (tile t + NS)
+        // the slot has been consumed into registers: refill it (tile position t + NS)
         __syncwarp();
-        if (lane == 0 && t + NS < T) issue();
+        if (lane == 0) issue();
+        __syncwarp();
 
         // ---- backward sweeps
         auto flush = [&](int kc) {       // CONTIG: ship the staged result tile of chunk kc
@@ -366,11 +384,19 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < CH; j++) eA[j] = eB[j];
 
-        if (++k == K) { k = 0; b += G; }
+        if (++k == K) k = 0;
         if (++slot == NS) { slot = 0; phase ^= 1u; }
     }
-    if constexpr (CONTIG) {
-        if (lane == 0) tma_wait_all0();
+    if (lane == 0) {
+        if constexpr (CONTIG) tma_wait_all0();
+        // last warp out re-arms the counters for the next launch that uses this pair
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * nwarps;
+        if (atomicAdd(p.counter + 1, 1ULL) == total - 1) {
+            p.counter[0] = 0ULL;
+            p.counter[1] = 0ULL;
+            __threadfence();
+        }
     }
 }
 

@@ -115,7 +115,7 @@ void nt_destroy(nt_plan *plan);
 int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream);
 
 /* Tuning knobs for experiments (0 = built-in default).  Not part of the reference surface. */
-int cfd_set_launch(int warps_per_cta, int ctas_per_sm);
+int cfd_set_launch(int warps_per_cta, int ctas_per_sm, int ring_slots);
 
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 long cfd_launch_count(void);

@@ -10,7 +10,7 @@ import compact_finite_differences_b200 as C
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 if len(sys.argv) > 4:
-    C.lib().cfd_set_launch(int(sys.argv[3]), int(sys.argv[4]))
+    C.lib().cfd_set_launch(int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 0)
 h = 2 * np.pi / (N - 1)
 t = torch.arange(N, dtype=torch.float64, device="cuda") * h
 f = (torch.sin(t)[None, None, :] * torch.cos(t)[None, :, None] * torch.sin(t)[:, None, None]).contiguous()

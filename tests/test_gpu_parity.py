@@ -248,3 +248,17 @@ def test_partitioned_line_emulated(C, axis, P, shape):
     got = np.concatenate([o.cpu().numpy() for o in outs], axis=ax)
     assert relinf(got, want) <= TOL
     assert relinf(got, O.partition_derivative(f, axis, h, P)) <= TOL
+
+
+def test_partition_nccl_two_gpus():
+    """The real multi-process path (one rank per GPU, NCCL) when the box has >= 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", os.path.join(root, "scripts", "check_partition_nccl.py"), "256"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
