@@ -42,22 +42,64 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 10 ms period; nvidia-smi query
+    of the same fields as a fallback -- B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.reasons, self.sm_max = index, [], set(), None
+        self._stop, self._t, self.n = threading.Event(), None, 0
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML handle through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self._h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hnd = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hnd).bus == bus:
+                        self._h = hnd
+            if self._h is None:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in ((nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                          (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits"], text=True, timeout=5)
+        s = [v.strip() for v in out.strip().split(",")]
+        self.sm.append(float(s[0]))
+        self.sm_max = float(s[1])
+        for v, name in zip(s[2:], ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
-                self.samples.append([s.strip() for s in out.strip().split(",")])
+                (self._sample_nvml if self._nvml else self._sample_smi)()
+                self.n += 1
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01 if self._nvml else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -69,14 +111,12 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active")
-                                                         for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": self.n,
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -95,7 +135,7 @@ def cpu_reference_rate(seconds_budget=12.0, n=512, threads=None):
     O.build()
     cores = threads or (os.cpu_count() or 1)
     kind = "reference" if O.have_ref() else "port"
-    planes = max(cores, 16)
+    planes = 4 * max(cores, 16)
     rng = np.random.default_rng(0)
     f = rng.random((planes, n, n))
     h = 2 * np.pi / (n - 1)
@@ -136,7 +176,7 @@ def cpu_reference_rate(seconds_budget=12.0, n=512, threads=None):
             one_pass()
             reps += 1
             dt = time.perf_counter() - t0
-            if dt > seconds_budget or reps >= 200:
+            if dt > seconds_budget or reps >= 2000:
                 break
         ctypes.CDLL(None).fflush(None)
     finally:
@@ -335,7 +375,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
