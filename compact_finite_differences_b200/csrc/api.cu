@@ -139,7 +139,9 @@ static int encode_maps(const Geometry &g, const void *in, const void *out, CUten
         cuuint32_t es[3] = {1, 1, 1};
         r = enc(tm_in, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        *tm_out = *tm_in;   // STRIDED results leave through plain coalesced stores
+        if (r == CUDA_SUCCESS)
+            r = enc(tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) return fail(CFD_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return CFD_OK;
@@ -187,13 +189,12 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
-    constexpr int per_warp = (NSLOT + (CONTIG ? 1 : 0)) * SLOT_BYTES + NSLOT * 16;
-    // Measured on B200 at 512^3 (scripts/sweep_launch.py, profiles/r1_sweep_launch_512.txt):
-    //   CONTIG : 4 warps/SM is fastest (0.3375 ms); 5-7 warps cost 1-2 %.
-    //   STRIDED: its longer per-tile instruction stream needs 6 warps/SM (0.344 ms); 4 -> 0.47 ms, 8 -> 0.353 ms.
-    // The register file (16K per SM sub-partition, ~240 regs/thread) caps a CTA at 8 warps.
-    const int max_warps = CONTIG ? 7 : 8;
-    int warps = g_warps ? g_warps : (CONTIG ? 4 : 6);
+    constexpr int per_warp = (NSLOT + 1) * SLOT_BYTES + NSLOT * 16;
+    // Measured on B200 at 512^3 (scripts/sweep_launch.py, profiles/r1_sweep_launch_512.txt): 4 warps per SM is
+    // fastest for both layouts (x 0.337, y 0.333, z 0.341 ms); 5-7 warps cost 1-2 %, 3 warps 8-13 %.
+    // Shared memory (32 KiB per warp) caps a CTA at 7 warps.
+    const int max_warps = 7;
+    int warps = g_warps ? g_warps : 4;
     if (warps > max_warps) warps = max_warps;
     int ctas = g_ctas ? g_ctas : 1;
     if (!g_warps) {   // small problems: spread the bundles over all SMs before stacking warps on one
@@ -472,7 +473,7 @@ extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double 
     int rc = get_maps(p->cache, p->g, f, df);
     if (rc) return rc;
     KParams kp = p->kp;
-    kp.halo_lo = halo_lo; kp.halo_hi = halo_hi; kp.out = df;
+    kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
     if (p->g.contig) return launch_stream<true, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
     return launch_stream<false, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
 }
@@ -558,7 +559,6 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
     int rc = get_maps(p->cache, p->g, d, d);
     if (rc) return rc;
     KParams kp = p->kp;
-    kp.out = d;
     if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
     return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
 }

@@ -25,8 +25,9 @@
 //    TMA boxes of 32 rows x 16 doubles with 128-byte swizzle, so that lane r reading its own row with
 //    16-byte LDS.128 is bank-conflict free (the "tiled transpose" happens inside the TMA unit); the
 //    result tile goes back through swizzled shared memory and a TMA store.  STRIDED (y, z): lanes map
-//    to 32 consecutive x columns, the tile is one [32 rows][32 cols] box, loads are LDS.64 with no
-//    conflicts and results are written straight from registers with 256-byte coalesced stores.
+//    to 32 consecutive x columns, the tile is one dense [32 rows][32 cols] box, LDS.64 / STS.64 with no
+//    conflicts, and the result tile leaves through the same staging slot + TMA store (which also clips
+//    ragged rows / columns, so the inner loops carry no predicates and no 64-bit address arithmetic).
 //
 #pragma once
 #include <cuda.h>
@@ -51,7 +52,6 @@ struct KParams {
     double sk_mid, l_mid, g_mid;
     double s0c, snc;   // beta_0/(2h), beta_{n-1}/(2h) for the closure rows
     const double *halo_lo, *halo_hi;   // neighbour planes of f (multi-rank), one value per line
-    double *out;       // STRIDED: destination field
     unsigned long long *counter;   // {next bundle, finished warps}, zero on entry, zero again on exit
     RowTab head, tail;
 };
@@ -102,6 +102,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -197,8 +203,7 @@ __device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH
 // Backward substitution over one chunk, x carried in.  OUT = results of this chunk are final.
 // ------------------------------------------------------------------------------------------------
 template <int MODE, bool OUT, bool CONTIG>
-__device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH], double &x, unsigned char *oslot,
-                                          int lane, double *gout, long gstride, bool lane_ok, int jmax)
+__device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH], double &x, unsigned char *oslot, int lane)
 {
     const RowTab &T = (MODE == 1) ? p.head : p.tail;
     double hold = 0.0;
@@ -215,7 +220,7 @@ __device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH
                                                  (((m & 7) << 4) ^ ((lane & 7) << 4))) = make_double2(x, hold);
                 }
             } else {
-                if (lane_ok && j <= jmax) st_stream(gout + (long)j * gstride, x);
+                reinterpret_cast<double *>(oslot)[j * CH + lane] = x;     // dense [row][col] staging tile
             }
         }
     }
@@ -230,19 +235,19 @@ __device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH
 //   {next bundle, finished warps} is reset by the last warp to finish, so a launch needs no memset.
 // ------------------------------------------------------------------------------------------------
 template <bool CONTIG, bool DERIV, int NS>
-__global__ void __launch_bounds__(CONTIG ? 224 : 256, 1)
+__global__ void __launch_bounds__(224, 1)
 stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
               const __grid_constant__ KParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int PER_WARP = (NS + (CONTIG ? 1 : 0)) * SLOT_BYTES;
+    constexpr int PER_WARP = (NS + 1) * SLOT_BYTES;     // ring + one result staging slot
     constexpr int CTRL = NS * 16;       // per warp: NS mbarriers + NS bundle tags
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     // 1 KiB alignment in the shared window (128B swizzle atom = 8 rows x 128 B)
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *wbase = base + warp * PER_WARP;
-    unsigned char *oslot = wbase + NS * SLOT_BYTES;                      // CONTIG only
+    unsigned char *oslot = wbase + NS * SLOT_BYTES;
     unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
     const uint32_t bar0 = smem_u32(ctrl);
     volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
@@ -297,29 +302,31 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
     long b = 0;
     int k = 0, slot = 0;
     uint32_t phase = 0;
-    bool lane_ok = true;
-    double *gcol = nullptr;       // STRIDED: &out[(o*n + 0)*inner + col]
-    const long gstride = CONTIG ? 0 : (long)p.inner;
+    int oc0 = 0, oc2 = 0;         // STRIDED: first column / outer index of the bundle (TMA store coordinates)
 
     for (;;) {
         if (k == 0) {
             b = tag[slot];
             if (b < 0) break;
-            long line;
-            if constexpr (CONTIG) {
-                line = b * CH + lane;
-                lane_ok = line < p.rows;
-            } else {
-                const long o = b / p.inner_tiles;
-                const int col = (int)(b % p.inner_tiles) * CH + lane;
-                lane_ok = col < p.inner;
-                line = o * p.inner + col;
-                gcol = p.out + (o * p.n) * (long)p.inner + col;
+            if constexpr (!CONTIG) {
+                oc2 = (int)(b / p.inner_tiles);
+                oc0 = (int)(b % p.inner_tiles) * CH;
             }
             eprev = 0.0; fm1 = 0.0; fm2 = 0.0; hval = 0.0;
             if constexpr (DERIV) {
-                if (!p.lo_closure && lane_ok) fm1 = __ldg(p.halo_lo + line);
-                if (!p.hi_closure && lane_ok) hval = __ldg(p.halo_hi + line);
+                if (!p.lo_closure || !p.hi_closure) {          // block of a partitioned line: neighbour planes of f
+                    long line;
+                    bool lane_ok;
+                    if constexpr (CONTIG) {
+                        line = b * CH + lane;
+                        lane_ok = line < p.rows;
+                    } else {
+                        lane_ok = oc0 + lane < p.inner;
+                        line = (long)oc2 * p.inner + oc0 + lane;
+                    }
+                    if (!p.lo_closure && lane_ok) fm1 = __ldg(p.halo_lo + line);
+                    if (!p.hi_closure && lane_ok) hval = __ldg(p.halo_hi + line);
+                }
             }
         }
         const bool last = (k == K - 1);
@@ -345,40 +352,40 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         __syncwarp();
 
         // ---- backward sweeps
-        auto flush = [&](int kc) {       // CONTIG: ship the staged result tile of chunk kc
-            if constexpr (CONTIG) {
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
+        auto flush = [&](int kc) {       // ship the staged result tile of chunk kc (TMA clips rows >= n, cols >= extent)
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CONTIG) {
                     tma_store_2d(&tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
                     tma_store_2d(&tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
-                    tma_commit();
+                } else {
+                    tma_store_3d(&tm_out, smem_u32(oslot), oc0, kc * CH, oc2);
                 }
+                tma_commit();
             }
         };
-        auto acquire_out = [&]() {       // CONTIG: previous store must have drained the staging slot
-            if constexpr (CONTIG) {
-                if (lane == 0) tma_wait_read0();
-                __syncwarp();
-            }
+        auto acquire_out = [&]() {       // the previous store must have drained the staging slot
+            if (lane == 0) tma_wait_read0();
+            __syncwarp();
         };
         double x = 0.0;
         if (last) {
             acquire_out();
-            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane, gcol + (long)k * CH * gstride, gstride, lane_ok, p.jl);
-            else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane, gcol + (long)k * CH * gstride, gstride, lane_ok, p.jl);
+            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane);
+            else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane);
             flush(k);
             if (k > 0) {
                 acquire_out();
-                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
-                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
                 flush(k - 1);
             }
         } else if (k > 0) {
-            bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane, nullptr, 0, false, CH);   // 32-row warm-up
+            bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane);   // 32-row warm-up
             acquire_out();
-            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
-            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane, gcol + (long)(k - 1) * CH * gstride, gstride, lane_ok, CH);
+            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
+            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
             flush(k - 1);
         }
 #pragma unroll
@@ -388,7 +395,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         if (++slot == NS) { slot = 0; phase ^= 1u; }
     }
     if (lane == 0) {
-        if constexpr (CONTIG) tma_wait_all0();
+        tma_wait_all0();
         // last warp out re-arms the counters for the next launch that uses this pair
         __threadfence();
         const unsigned long long total = (unsigned long long)gridDim.x * nwarps;
