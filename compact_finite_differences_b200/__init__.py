@@ -15,7 +15,8 @@ from ._lib import CfdError, lib  # noqa: F401
 from .compact import CompactFiniteDifferenceSolver  # noqa: F401
 from .near_toeplitz import NearToeplitzSolver  # noqa: F401
 from .reduced import ReducedSolver  # noqa: F401
-from .partition import ZPartitionedDerivative, exchange_halo_planes, gather_interface_planes  # noqa: F401
+from .partition import (ZPartitionedDerivative, exchange_halo_planes, exchange_interface_planes,  # noqa: F401
+                        gather_interface_planes)
 
 __all__ = ["CompactFiniteDifferenceSolver", "NearToeplitzSolver", "ReducedSolver", "ZPartitionedDerivative",
-           "exchange_halo_planes", "gather_interface_planes", "CfdError", "lib"]
+           "exchange_halo_planes", "exchange_interface_planes", "gather_interface_planes", "CfdError", "lib"]

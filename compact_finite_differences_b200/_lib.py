@@ -21,6 +21,11 @@ SIGNATURES = {
     "cfd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_interface_pack": (_i, [_vp, _vp, _vp, _vp]),
     "cfd_reduced_correct": (_i, [_vp, _vp, _vp, _vp]),
+    "cfd_edge_faces": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_apply_coupled": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_apply_coupled_nb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_nb_layout": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "cfd_debug_neighbour": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _dp, _dp, _dp]),
     "cfd_apply_host": (_i, [_vp, _vp, _vp, _i]),
     "cfd_plane_elems": (_l, [_vp]),
     "cfd_tables_size": (_i, []),

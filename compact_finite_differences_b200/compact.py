@@ -143,6 +143,46 @@ class CompactFiniteDifferenceSolver:
         check(lib().cfd_interface_pack(plan.handle, df.data_ptr(), faces.data_ptr(), _stream_ptr(df)))
         return faces
 
+    def edge_faces(self, f, faces, halo_lo=None, halo_hi=None):
+        """Interface planes straight from f (no block solve): cfd_edge_faces."""
+        plan = self._plan(self.direction, self.spacing)
+        check(lib().cfd_edge_faces(plan.handle, f.data_ptr(),
+                                   halo_lo.data_ptr() if halo_lo is not None else None,
+                                   halo_hi.data_ptr() if halo_hi is not None else None,
+                                   faces.data_ptr(), _stream_ptr(f)))
+        return faces
+
+    def apply_coupled(self, f, out, halo_lo, halo_hi, faces_all):
+        """Final derivative of the block in one pass, interface unknowns folded in: cfd_apply_coupled."""
+        import torch
+        plan = self._plan(self.direction, self.spacing)
+        if out is None:
+            out = torch.empty_like(f)
+        check(lib().cfd_apply_coupled(plan.handle, f.data_ptr(), out.data_ptr(),
+                                      halo_lo.data_ptr() if halo_lo is not None else None,
+                                      halo_hi.data_ptr() if halo_hi is not None else None,
+                                      faces_all.data_ptr(), _stream_ptr(f)))
+        return out
+
+    def nb_layout(self):
+        """(virtual ranks V, own index) of the neighbour-only interface buffer [2V, plane]: cfd_nb_layout."""
+        plan = self._plan(self.direction, self.spacing)
+        pv, own = ctypes.c_int(), ctypes.c_int()
+        check(lib().cfd_nb_layout(plan.handle, ctypes.byref(pv), ctypes.byref(own)))
+        return pv.value, own.value
+
+    def apply_coupled_nb(self, f, out, halo_lo, halo_hi, faces_nb):
+        """As apply_coupled, with one interface plane from each neighbour only: cfd_apply_coupled_nb."""
+        import torch
+        plan = self._plan(self.direction, self.spacing)
+        if out is None:
+            out = torch.empty_like(f)
+        check(lib().cfd_apply_coupled_nb(plan.handle, f.data_ptr(), out.data_ptr(),
+                                         halo_lo.data_ptr() if halo_lo is not None else None,
+                                         halo_hi.data_ptr() if halo_hi is not None else None,
+                                         faces_nb.data_ptr(), _stream_ptr(f)))
+        return out
+
     def reduced_correct(self, df, faces_all):
         plan = self._plan(self.direction, self.spacing)
         check(lib().cfd_reduced_correct(plan.handle, df.data_ptr(), faces_all.data_ptr(), _stream_ptr(df)))

@@ -247,7 +247,9 @@ struct cfd_plan {
     MapCache cache;
     // multi-rank
     std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
-    double *d_x_uh = nullptr, *d_x_lh = nullptr, *d_lu = nullptr;
+    std::vector<double> lu_nb;        // neighbour-only reduced system (ranks r-1, r, r+1)
+    int nb_pv = 0, nb_own = 0;
+    double *d_x_uh = nullptr, *d_x_lh = nullptr, *d_lu = nullptr, *d_lu_nb = nullptr;
     int wc = 0;
     // host staging
     double *d_f = nullptr, *d_df = nullptr;
@@ -273,7 +275,7 @@ static int fill_tables(KParams &kp, const Geometry &g, const LineCoeffs &m, doub
     }
     memset(&kp, 0, sizeof kp);
     kp.n = g.n; kp.K = g.K; kp.jl = g.jl;
-    kp.inner = (int)g.inner; kp.inner_tiles = g.inner_tiles;
+    kp.inner = (int)g.inner; kp.inner_tiles = g.inner_tiles; kp.outer = (int)g.outer;
     kp.nb = g.nb; kp.rows = g.nlines;
     kp.head = chunk_table(pv, g.n, 0, scale);
     kp.tail = chunk_table(pv, g.n, g.K - 1, scale);
@@ -323,6 +325,45 @@ static void reduced_matrix(int n, int P, std::vector<double> &ra, std::vector<do
     ra[1] = 0.0; rc[mm - 2] = 0.0;                                                        // :110-111
 }
 
+// Two-sided elimination tables of a tridiagonal (a, b, c): [6][m] = a_i, c_i, 1/p_i, c_i/p_i, 1/q_i, a_i/q_i
+// (p: pivots of the top-down sweep, q: pivots of the bottom-up sweep).
+static std::vector<double> elimination_table(const std::vector<double> &ra, const std::vector<double> &rb,
+                                             const std::vector<double> &rc)
+{
+    const int mm = (int)ra.size();
+    std::vector<double> lu(6 * mm, 0.0);
+    double *a = &lu[0], *c = &lu[mm], *ip = &lu[2 * mm], *cp = &lu[3 * mm], *iq = &lu[4 * mm], *aq = &lu[5 * mm];
+    for (int i = 0; i < mm; i++) { a[i] = ra[i]; c[i] = rc[i]; }
+    double piv = rb[0];
+    ip[0] = 1.0 / piv; cp[0] = c[0] / piv;
+    for (int i = 1; i < mm; i++) { piv = rb[i] - a[i] * cp[i - 1]; ip[i] = 1.0 / piv; cp[i] = c[i] / piv; }
+    piv = rb[mm - 1];
+    iq[mm - 1] = 1.0 / piv; aq[mm - 1] = a[mm - 1] / piv;
+    for (int i = mm - 2; i >= 0; i--) { piv = rb[i] - c[i] * aq[i + 1]; iq[i] = 1.0 / piv; aq[i] = a[i] / piv; }
+    return lu;
+}
+
+// Neighbour-only ("pairwise") reduced system of rank r: the unknowns of ranks r-1, r, r+1 only.  For blocks of
+// >= 64 rows the couplings x_UH[-1], x_LH[0] that tie an interface to the next one are ~0.268^64 = 1e-37, so
+// cutting the chain at the neighbours (identity rows, as at a physical end) changes nothing in fp64 and a rank
+// needs ONE interface plane from each neighbour instead of the all-gathered 2P planes.
+//   pv = number of virtual ranks (2 or 3), own = index of this rank among them.
+static void neighbour_matrix(int n, int rank, int P, std::vector<double> &va, std::vector<double> &vb,
+                             std::vector<double> &vc, int &pv, int &own)
+{
+    std::vector<double> ra, rb, rc;
+    reduced_matrix(n, P, ra, rb, rc);
+    const int lo = rank > 0 ? rank - 1 : rank, hi = rank < P - 1 ? rank + 1 : rank;
+    pv = hi - lo + 1;
+    own = rank - lo;
+    const int mm = 2 * pv;
+    va.assign(mm, 0.0); vb.assign(mm, 0.0); vc.assign(mm, 0.0);
+    for (int i = 0; i < mm; i++) { va[i] = ra[2 * lo + i]; vb[i] = rb[2 * lo + i]; vc[i] = rc[2 * lo + i]; }
+    va[0] = 0.0; vc[0] = 0.0; vb[0] = 1.0;                    // outer unknowns of the outermost virtual ranks:
+    va[mm - 1] = 0.0; vc[mm - 1] = 0.0; vb[mm - 1] = 1.0;     // identity rows with zero right-hand side
+    va[1] = 0.0; vc[mm - 2] = 0.0;
+}
+
 // Host-only inspection of the multi-rank tables (no device needed).
 extern "C" int cfd_debug_secondary(int n, int part_rank, int part_size, double *x_uh, double *x_lh, double *ra,
                                    double *rb, double *rc)
@@ -336,6 +377,21 @@ extern "C" int cfd_debug_secondary(int n, int part_rank, int part_size, double *
     if (ra) memcpy(ra, a.data(), a.size() * sizeof(double));
     if (rb) memcpy(rb, b.data(), b.size() * sizeof(double));
     if (rc) memcpy(rc, c.data(), c.size() * sizeof(double));
+    return CFD_OK;
+}
+
+extern "C" int cfd_debug_neighbour(int n, int part_rank, int part_size, int *virtual_ranks, int *own_index,
+                                   double *va, double *vb, double *vc)
+{
+    if (n < 3 || part_size < 2 || part_rank < 0 || part_rank >= part_size) return fail(CFD_EINVAL, "bad argument");
+    std::vector<double> a, b, c;
+    int pv = 0, own = 0;
+    neighbour_matrix(n, part_rank, part_size, a, b, c, pv, own);
+    if (virtual_ranks) *virtual_ranks = pv;
+    if (own_index) *own_index = own;
+    if (va) memcpy(va, a.data(), a.size() * sizeof(double));
+    if (vb) memcpy(vb, b.data(), b.size() * sizeof(double));
+    if (vc) memcpy(vc, c.data(), c.size() * sizeof(double));
     return CFD_OK;
 }
 
@@ -360,6 +416,10 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     if (rc) { delete p; return rc; }
     p->kp.lo_closure = (part_rank == 0);
     p->kp.hi_closure = (part_rank == part_size - 1);
+    // coupled multi-rank solve: known neighbour unknowns enter rows 0 / n-1 as Dirichlet data
+    if (part_rank > 0) p->kp.head.l[0] = m.ai * p->kp.s0c;               // a_i * beta_0 (eprev starts at alpha)
+    p->kp.snb = (part_rank < part_size - 1) ? p->kp.snc * m.ci : 0.0;     // beta_{n-1} * c_i
+    p->kp.P = part_size; p->kp.rank = part_rank;
     p->kp.s0c *= 1.0 / (2.0 * h);
     p->kp.snc *= 1.0 / (2.0 * h);
 
@@ -367,29 +427,26 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
         const int n = p->g.n, P = part_size, mm = 2 * P;
         secondary_systems(n, part_rank, P, p->x_uh, p->x_lh);
         reduced_matrix(n, P, p->ra, p->rb, p->rc);
-        // two-sided elimination tables
-        p->lu.assign(6 * mm, 0.0);
-        double *a = &p->lu[0], *c = &p->lu[mm], *ip = &p->lu[2 * mm], *cp = &p->lu[3 * mm], *iq = &p->lu[4 * mm],
-               *aq = &p->lu[5 * mm];
-        for (int i = 0; i < mm; i++) { a[i] = p->ra[i]; c[i] = p->rc[i]; }
-        double piv = p->rb[0];
-        ip[0] = 1.0 / piv; cp[0] = c[0] / piv;
-        for (int i = 1; i < mm; i++) { piv = p->rb[i] - a[i] * cp[i - 1]; ip[i] = 1.0 / piv; cp[i] = c[i] / piv; }
-        piv = p->rb[mm - 1];
-        iq[mm - 1] = 1.0 / piv; aq[mm - 1] = a[mm - 1] / piv;
-        for (int i = mm - 2; i >= 0; i--) { piv = p->rb[i] - c[i] * aq[i + 1]; iq[i] = 1.0 / piv; aq[i] = a[i] / piv; }
+        p->lu = elimination_table(p->ra, p->rb, p->rc);
+        {
+            std::vector<double> va, vb, vc;
+            neighbour_matrix(n, part_rank, P, va, vb, vc, p->nb_pv, p->nb_own);
+            p->lu_nb = elimination_table(va, vb, vc);
+        }
         // correction band: rows where the secondary solutions are above round-off
         int wc = 0;
         while (wc < n && (std::fabs(p->x_uh[wc]) > 1e-19 || std::fabs(p->x_lh[n - 1 - wc]) > 1e-19)) wc++;
         p->wc = wc;
         if (cudaMalloc(&p->d_x_uh, n * sizeof(double)) != cudaSuccess || cudaMalloc(&p->d_x_lh, n * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&p->d_lu, p->lu.size() * sizeof(double)) != cudaSuccess) {
+            cudaMalloc(&p->d_lu, p->lu.size() * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&p->d_lu_nb, p->lu_nb.size() * sizeof(double)) != cudaSuccess) {
             cfd_destroy(p);
             return fail(CFD_ECUDA, "cudaMalloc of plan tables failed");
         }
         cudaMemcpy(p->d_x_uh, p->x_uh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(p->d_x_lh, p->x_lh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(p->d_lu, p->lu.data(), p->lu.size() * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(p->d_lu_nb, p->lu_nb.data(), p->lu_nb.size() * sizeof(double), cudaMemcpyHostToDevice);
     }
     *out = p;
     return CFD_OK;
@@ -398,7 +455,7 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
 extern "C" void cfd_destroy(cfd_plan *p)
 {
     if (!p) return;
-    cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu);
+    cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu); cudaFree(p->d_lu_nb);
     cudaFree(p->d_f); cudaFree(p->d_df);
     if (p->hstream) cudaStreamDestroy(p->hstream);
     delete p;
@@ -463,8 +520,8 @@ static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *
     return CFD_OK;
 }
 
-extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
-                         void *stream)
+static int apply_impl(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+                      const double *faces_all, void *stream, bool neighbours_only = false)
 {
     if (!p || !f || !df) return fail(CFD_EINVAL, "NULL argument");
     if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
@@ -474,8 +531,66 @@ extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double 
     if (rc) return rc;
     KParams kp = p->kp;
     kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
+    kp.faces_all = faces_all; kp.lu = p->d_lu;
+    if (neighbours_only) { kp.lu = p->d_lu_nb; kp.P = p->nb_pv; kp.rank = p->nb_own; }
     if (p->g.contig) return launch_stream<true, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
     return launch_stream<false, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+}
+
+extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+                         void *stream)
+{
+    return apply_impl(p, f, df, halo_lo, halo_hi, nullptr, stream);
+}
+
+extern "C" int cfd_apply_coupled(cfd_plan *p, const double *f, double *df, const double *halo_lo,
+                                 const double *halo_hi, const double *faces_all, void *stream)
+{
+    if (p && p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: use cfd_apply");
+    if (!faces_all) return fail(CFD_EINVAL, "faces_all is NULL");
+    return apply_impl(p, f, df, halo_lo, halo_hi, faces_all, stream);
+}
+
+extern "C" int cfd_apply_coupled_nb(cfd_plan *p, const double *f, double *df, const double *halo_lo,
+                                    const double *halo_hi, const double *faces_nb, void *stream)
+{
+    if (p && p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: use cfd_apply");
+    if (!faces_nb) return fail(CFD_EINVAL, "faces_nb is NULL");
+    if (p && p->g.n < 2 * CH) return fail(CFD_EUNSUPPORTED, "neighbour-only coupling needs >= %d rows per block", 2 * CH);
+    return apply_impl(p, f, df, halo_lo, halo_hi, faces_nb, stream, true);
+}
+
+extern "C" int cfd_nb_layout(const cfd_plan *p, int *virtual_ranks, int *own_index)
+{
+    if (!p || p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no neighbours");
+    if (virtual_ranks) *virtual_ranks = p->nb_pv;
+    if (own_index) *own_index = p->nb_own;
+    return CFD_OK;
+}
+
+extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,
+                              double *faces, void *stream)
+{
+    if (!p || !f || !faces) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no interfaces");
+    if (p->g.n < 2 * CH + 2)
+        return fail(CFD_EUNSUPPORTED, "cfd_edge_faces needs >= %d rows per block (have %d): use cfd_apply + "
+                    "cfd_interface_pack + cfd_reduced_correct", 2 * CH + 2, p->g.n);
+    if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
+    if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
+    EdgeP ep;
+    memset(&ep, 0, sizeof ep);
+    ep.nlines = p->g.nlines; ep.inner = p->g.inner; ep.n = p->g.n; ep.jl = p->g.jl;
+    ep.lo_closure = p->kp.lo_closure; ep.hi_closure = p->kp.hi_closure;
+    ep.sk_mid = p->kp.sk_mid; ep.l_mid = p->kp.l_mid; ep.s0c = p->kp.s0c; ep.snc = p->kp.snc;
+    ep.sk_last = p->kp.tail.sk[p->g.jl]; ep.l_last = p->kp.tail.l[p->g.jl];
+    ep.halo_lo = halo_lo; ep.halo_hi = halo_hi;
+    ep.head = p->kp.head;
+    const int bs = 128;
+    edge_faces_kernel<<<(unsigned)((ep.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(f, faces, ep);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
 }
 
 extern "C" int cfd_interface_pack(cfd_plan *p, const double *df, double *faces, void *stream)

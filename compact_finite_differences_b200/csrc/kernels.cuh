@@ -45,6 +45,7 @@ struct KParams {
     int jl;            // position of row n-1 inside the last chunk
     int inner;         // STRIDED: extent of the contiguous dimension the lanes map to
     int inner_tiles;   // STRIDED: ceil(inner / 32)
+    int outer;         // STRIDED: number of outer slices
     int lo_closure;    // this block owns the physical left end  -> one-sided RHS row 0
     int hi_closure;    // this block owns the physical right end -> one-sided RHS row n-1
     long nb;           // number of 32-line bundles
@@ -53,6 +54,11 @@ struct KParams {
     double s0c, snc;   // beta_0/(2h), beta_{n-1}/(2h) for the closure rows
     const double *halo_lo, *halo_hi;   // neighbour planes of f (multi-rank), one value per line
     unsigned long long *counter;   // {next bundle, finished warps}, zero on entry, zero again on exit
+    // coupled multi-rank solve: interface unknowns from the all-gathered faces, folded into rows 0 and n-1
+    const double *faces_all;       // [2P][plane] or nullptr (block-local solve)
+    const double *lu;              // [6][2P] two-sided elimination tables of the reduced matrix
+    int P, rank;
+    double snb;                    // beta_{n-1} * c_i: weight of the right neighbour's first unknown in row n-1
     RowTab head, tail;
 };
 
@@ -120,6 +126,29 @@ __device__ __forceinline__ void st_stream(double *p, double v)
 { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// Reduced (interface) system of one line, solved for this rank's two unknowns only:
+//   alpha = the left neighbour's last point, beta = the right neighbour's first point.
+// Rows: code/cuda/compact.py:96-111; same tridiagonal elimination as reducedSolverKernel
+// (code/cuda/kernels.cu:115-145) with host-precomputed pivots, run from both ends towards rows (2r, 2r+1)
+// and closed with a 2x2 solve, so it needs registers only.
+//   lu = [6][2P]: a_i, c_i, 1/p_i, c_i/p_i (top-down pivots p), 1/q_i, a_i/q_i (bottom-up pivots q).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void reduced_unknowns(const double *__restrict__ faces_all, const double *__restrict__ lu,
+                                                 long nlines, long line, int P, int rank, double &alpha, double &beta)
+{
+    const int m = 2 * P;
+    const double *a = lu, *c = lu + m, *ip = lu + 2 * m, *cp = lu + 3 * m, *iq = lu + 4 * m, *aq = lu + 5 * m;
+    const int r0 = 2 * rank, r1 = 2 * rank + 1;
+    double t = __ldg(faces_all + line) * ip[0];
+    for (int i = 1; i <= r0; i++) t = (__ldg(faces_all + (long)i * nlines + line) - a[i] * t) * ip[i];
+    double u = __ldg(faces_all + (long)(m - 1) * nlines + line) * iq[m - 1];
+    for (int i = m - 2; i >= r1; i--) u = (__ldg(faces_all + (long)i * nlines + line) - c[i] * u) * iq[i];
+    // x[r0] = t - cp[r0]*x[r1];  x[r1] = u - aq[r1]*x[r0]
+    alpha = (t - cp[r0] * u) / (1.0 - cp[r0] * aq[r1]);
+    beta = u - aq[r1] * alpha;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tile access.  CONTIG: slot = 2 boxes [32 rows][16 doubles], 128B-swizzled: the 16-byte unit u of row r
 // sits at r*128 + ((u ^ (r & 7)) << 4).  STRIDED: slot = [32 rows][32 cols] dense.
 // ------------------------------------------------------------------------------------------------
@@ -157,7 +186,7 @@ __device__ __forceinline__ double load_first(const unsigned char *slot, int lane
 // State carried along the line: eprev = e_{i-1}, fm1 = f_{i-1}, fm2 = f_{i-2}.
 // ------------------------------------------------------------------------------------------------
 template <int MODE, bool DERIV>
-__device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH], double peek, double hval,
+__device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH], double peek, double hval, double bval,
                                           bool is_last, double (&e)[CH], double &eprev, double &fm1, double &fm2)
 {
     if constexpr (MODE == 0) {
@@ -188,6 +217,7 @@ __device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH
                 r = T.sk[j] * (nxt - fm1);
                 if (MODE == 1 && j == 0 && p.lo_closure) r = p.s0c * (-5.0 * F[0] + 4.0 * F[1] + F[2]);
                 if (j == jl && p.hi_closure) r = p.snc * (5.0 * F[j] - 4.0 * fm1 - fm2);
+                if (j == jl && !p.hi_closure) r = fma(-p.snb, bval, r);      // coupled: - beta_{n-1} c x_n
                 fm2 = fm1;
                 fm1 = F[j];
             } else {
@@ -298,7 +328,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
 
     // ---- consumer side (all lanes)
     double eA[CH], eB[CH], F[CH];
-    double eprev = 0.0, fm1 = 0.0, fm2 = 0.0, hval = 0.0;
+    double eprev = 0.0, fm1 = 0.0, fm2 = 0.0, hval = 0.0, bval = 0.0;
     long b = 0;
     int k = 0, slot = 0;
     uint32_t phase = 0;
@@ -312,7 +342,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                 oc2 = (int)(b / p.inner_tiles);
                 oc0 = (int)(b % p.inner_tiles) * CH;
             }
-            eprev = 0.0; fm1 = 0.0; fm2 = 0.0; hval = 0.0;
+            eprev = 0.0; fm1 = 0.0; fm2 = 0.0; hval = 0.0; bval = 0.0;
             if constexpr (DERIV) {
                 if (!p.lo_closure || !p.hi_closure) {          // block of a partitioned line: neighbour planes of f
                     long line;
@@ -326,6 +356,14 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                     }
                     if (!p.lo_closure && lane_ok) fm1 = __ldg(p.halo_lo + line);
                     if (!p.hi_closure && lane_ok) hval = __ldg(p.halo_hi + line);
+                    if (p.faces_all != nullptr && lane_ok) {
+                        // coupled solve: the interface unknowns become Dirichlet data of the block --
+                        // row 0 sees x_{-1} = alpha through l_0 = a_i*beta_0, row n-1 sees x_n = beta through snb
+                        double alpha;
+                        const long nlines = CONTIG ? p.rows : (long)p.inner * p.outer;
+                        reduced_unknowns(p.faces_all, p.lu, nlines, line, p.P, p.rank, alpha, bval);
+                        eprev = alpha;
+                    }
                 }
             }
         }
@@ -342,9 +380,9 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                 peek = load_first<CONTIG>(wbase + s1 * SLOT_BYTES, lane);
             }
         }
-        if (k == 0)    fwd_chunk<1, DERIV>(p, F, peek, hval, last, eB, eprev, fm1, fm2);
-        else if (last) fwd_chunk<2, DERIV>(p, F, peek, hval, true, eB, eprev, fm1, fm2);
-        else           fwd_chunk<0, DERIV>(p, F, peek, hval, false, eB, eprev, fm1, fm2);
+        if (k == 0)    fwd_chunk<1, DERIV>(p, F, peek, hval, bval, last, eB, eprev, fm1, fm2);
+        else if (last) fwd_chunk<2, DERIV>(p, F, peek, hval, bval, true, eB, eprev, fm1, fm2);
+        else           fwd_chunk<0, DERIV>(p, F, peek, hval, bval, false, eB, eprev, fm1, fm2);
 
         // the slot has been consumed into registers: refill it (tile position t + NS)
         __syncwarp();
@@ -446,16 +484,8 @@ __global__ void reduced_correct_kernel(double *__restrict__ x, const double *__r
     const long line = CONTIG ? (tid >> 5) : tid;
     const int lane = threadIdx.x & 31;
     if (line >= g.nlines) return;
-    const int m = 2 * P;
-    const double *a = lu, *c = lu + m, *ip = lu + 2 * m, *cp = lu + 3 * m, *iq = lu + 4 * m, *aq = lu + 5 * m;
-    const int r0 = 2 * rank, r1 = 2 * rank + 1;
-    double t = faces_all[line] * ip[0];
-    for (int i = 1; i <= r0; i++) t = (faces_all[(long)i * g.nlines + line] - a[i] * t) * ip[i];
-    double u = faces_all[(long)(m - 1) * g.nlines + line] * iq[m - 1];
-    for (int i = m - 2; i >= r1; i--) u = (faces_all[(long)i * g.nlines + line] - c[i] * u) * iq[i];
-    // x[r0] = t - cp[r0]*x[r1];  x[r1] = u - aq[r1]*x[r0]
-    const double alpha = (t - cp[r0] * u) / (1.0 - cp[r0] * aq[r1]);
-    const double beta = u - aq[r1] * alpha;
+    double alpha, beta;
+    reduced_unknowns(faces_all, lu, g.nlines, line, P, rank, alpha, beta);
     const long o = line / g.inner, col = line % g.inner;
     double *xl = x + (o * g.n) * g.inner + col;
     const int n = g.n;
@@ -475,6 +505,66 @@ __global__ void reduced_correct_kernel(double *__restrict__ x, const double *__r
             for (int i = n - wc; i < n; i++) xl[(long)i * g.inner] += alpha * x_uh[i] + beta * x_lh[i];
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interface planes straight from f, WITHOUT the block solve: faces[0] = -x_R[0], faces[1] = -x_R[n-1]
+// (what negateAndCopyFaces, code/cuda/kernels.cu:76-113, extracts after the reference's full local solve).
+// x_R[0] depends on the first rows only and x_R[n-1] on the last rows only, up to 0.268^32 = 5e-19:
+//   head: forward rows 0..31 with the HEAD table, back-substitute from x_31 = e_31 down to x_0;
+//   tail: forward rows n-33..n-1 from a zero state with the MID constants and the last TAIL row; x_{n-1} = e_{n-1}.
+// One thread per line; reads 33 + 34 rows of f (8 B each) instead of the whole block.  Needs n >= 66.
+// ------------------------------------------------------------------------------------------------
+struct EdgeP {
+    long nlines, inner;
+    int n, jl;
+    int lo_closure, hi_closure;
+    double sk_mid, l_mid, s0c, snc, sk_last, l_last;
+    const double *halo_lo, *halo_hi;
+    RowTab head;
+};
+
+__global__ void __launch_bounds__(128)
+edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, const __grid_constant__ EdgeP p)
+{
+    const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= p.nlines) return;
+    const long o = line / p.inner, col = line % p.inner;
+    const double *fl = f + (o * p.n) * p.inner + col;
+    const long st = p.inner;
+    double lo_face = 0.0, hi_face = 0.0;
+    if (!p.lo_closure) {
+        double F[CH + 1], e[CH];
+#pragma unroll
+        for (int j = 0; j <= CH; j++) F[j] = __ldg(fl + (long)j * st);
+        double fm1 = __ldg(p.halo_lo + line), eprev = 0.0;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            eprev = fma(-p.head.l[j], eprev, p.head.sk[j] * (F[j + 1] - fm1));
+            e[j] = eprev;
+            fm1 = F[j];
+        }
+        double x = 0.0;
+#pragma unroll
+        for (int j = CH - 1; j >= 0; j--) x = fma(-p.head.g[j], x, e[j]);
+        lo_face = -x;
+    }
+    if (!p.hi_closure) {
+        const int n = p.n;
+        const double *ft = fl + (long)(n - CH - 2) * st;       // rows n-34 .. n-1
+        double F[CH + 2];
+#pragma unroll
+        for (int j = 0; j < CH + 2; j++) F[j] = __ldg(ft + (long)j * st);
+        const double hval = __ldg(p.halo_hi + line);
+        double eprev = 0.0;
+#pragma unroll
+        for (int j = 1; j <= CH; j++)                           // rows n-33 .. n-2
+            eprev = fma(-p.l_mid, eprev, p.sk_mid * (F[j + 1] - F[j - 1]));
+        eprev = fma(-p.l_last, eprev, p.sk_last * (hval - F[CH]));   // row n-1: neighbour point from the halo
+        hi_face = -eprev;
+    }
+    faces[line] = lo_face;
+    faces[p.nlines + line] = hi_face;
 }
 
 // Thread-parallel Thomas over interleaved systems sharing one matrix (reference reducedSolverKernel,

@@ -8,11 +8,15 @@ The reference's multi-rank dfdx (code/cuda/compact.py:29-44) is
 Here, for a grid split into P slabs along z:
     d/dx, d/dy : no communication at all (lines never leave the slab);
     d/dz       : (1) send/recv ONE boundary plane of f with each z-neighbour;
-                 (2) fused RHS + local solve (one kernel, cfd_apply);
-                 (3) pack the two interface planes (cfd_interface_pack) and ALL-GATHER them -- every rank then
-                     solves the identical 2P-unknown reduced system redundantly (no root, no scatter);
-                 (4) correction x += alpha*x_UH + beta*x_LH on the few planes next to the interfaces where the
-                     secondary solutions are above fp64 round-off (cfd_reduced_correct).
+                 (2) interface planes -x_R[first], -x_R[last] from the 33 + 34 planes next to the slab ends
+                     (cfd_edge_faces: they do not depend on planes further away, to 5e-19);
+                 (3) ALL-GATHER them -- every rank then solves the identical 2P-unknown reduced system
+                     redundantly (no root, no scatter);
+                 (4) ONE fused kernel (cfd_apply_coupled): RHS + solve with the two interface unknowns folded
+                     into rows 0 and n-1 -- the final derivative, no correction pass.
+                 mode="reference" keeps the reference's order instead: local solve (cfd_apply) ->
+                 cfd_interface_pack -> all-gather -> cfd_reduced_correct (correction sweep on the planes next
+                 to the interfaces); it also serves slabs thinner than 66 planes.
 The two collectives below are plain functions over torch tensors so that the host-side logic is testable on
 CPU with the gloo backend (tests/test_partition_gloo.py); compute always goes through libcfd_b200.so.
 """
@@ -64,10 +68,37 @@ def gather_interface_planes(faces, size, group=None, out=None):
     return out
 
 
+def exchange_interface_planes(faces_nb, own, pv, rank, size, group=None):
+    """
+    Neighbour-only replacement of the all-gather: faces_nb is [2*pv, plane] over the virtual ranks
+    (rank-1 if any, rank, rank+1 if any) with this rank's own faces already at planes 2*own, 2*own+1.
+    Sends faces[0] (= -x_R[first]) to rank-1 and faces[1] (= -x_R[last]) to rank+1; receives the left neighbour's
+    faces[1] into plane 2*own-1 and the right neighbour's faces[0] into plane 2*own+2.
+    """
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, faces_nb[2 * own], _peer(group, rank - 1), group))
+        ops.append(dist.P2POp(dist.irecv, faces_nb[2 * own - 1], _peer(group, rank - 1), group))
+    if rank < size - 1:
+        ops.append(dist.P2POp(dist.isend, faces_nb[2 * own + 1], _peer(group, rank + 1), group))
+        ops.append(dist.P2POp(dist.irecv, faces_nb[2 * own + 2], _peer(group, rank + 1), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return faces_nb
+
+
 class ZPartitionedDerivative:
     """Derivative of a z-partitioned field; `local_shape` is this rank's slab [nz/P, ny, nx]."""
 
-    def __init__(self, local_shape, spacing, direction, group=None):
+    def __init__(self, local_shape, spacing, direction, group=None, mode="fused", comm="allgather"):
+        """
+        mode "fused"     : edge faces -> exchange -> ONE coupled kernel (final derivative, no correction pass)
+             "reference" : local solve -> pack -> all-gather -> correction sweep (the reference's order)
+        comm "allgather" : every rank receives all 2P interface planes (the reference's Gather+Scatter, rootless)
+             "pairwise"  : one interface plane from each z-neighbour (exact in fp64 for slabs >= 64 planes;
+                           fused mode only)
+        """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
         self.rank = dist.get_rank(group)
@@ -76,19 +107,64 @@ class ZPartitionedDerivative:
         self.local_shape = tuple(int(s) for s in local_shape)
         part = (self.rank, self.size) if self.direction == 2 else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
+        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise")
+        self.mode = mode if self.local_shape[0] >= 66 else "reference"
+        self.comm = comm if self.mode == "fused" else "allgather"
         self._buf = None
+        self._side = None          # (stream, event) of an exchange started early by begin()
+        self._pending = None
 
     def _buffers(self, f):
         if self._buf is None or self._buf[0].device != f.device:
             nz, ny, nx = self.local_shape
             mk = lambda *s: torch.empty(s, dtype=torch.float64, device=f.device)  # noqa: E731
-            self._buf = (mk(ny, nx), mk(ny, nx), mk(2, ny, nx), mk(2 * self.size, ny, nx))
+            pv, own = self.solver.nb_layout() if self.size > 1 and self.direction == 2 else (1, 0)
+            faces_nb = torch.zeros((2 * pv, ny, nx), dtype=torch.float64, device=f.device)
+            self._buf = (mk(ny, nx), mk(ny, nx), mk(2, ny, nx), mk(2 * self.size, ny, nx), faces_nb, pv, own)
         return self._buf
+
+    def _exchange(self, f):
+        """Steps (1)-(3) of the fused path; returns what the coupled kernel needs."""
+        lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)
+        halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)
+        if self.comm == "pairwise":
+            self.solver.edge_faces(f, faces_nb[2 * own:2 * own + 2], halo_lo, halo_hi)
+            exchange_interface_planes(faces_nb, own, pv, self.rank, self.size, self.group)
+            return halo_lo, halo_hi, faces_nb
+        self.solver.edge_faces(f, faces, halo_lo, halo_hi)
+        gather_interface_planes(faces, self.size, self.group, faces_all)
+        return halo_lo, halo_hi, faces_all
+
+    def begin(self, f):
+        """Start the halo / interface exchange of d/dz on a side stream so that it overlaps whatever the caller
+        launches next on the current stream (typically d/dx and d/dy of the same field).  The next __call__ with
+        the same f picks the result up.  No-op where there is nothing to exchange."""
+        if self.direction != 2 or self.size == 1 or self.mode != "fused":
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=f.device)
+        cur = torch.cuda.current_stream(f.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            res = self._exchange(f)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._pending = (f.data_ptr(), res, ev)
 
     def __call__(self, f, out=None):
         if self.direction != 2 or self.size == 1:
             return self.solver(f, out)
-        lo_buf, hi_buf, faces, faces_all = self._buffers(f)
+        if self.mode == "fused":
+            if self._pending is not None and self._pending[0] == f.data_ptr():
+                _, (halo_lo, halo_hi, planes), ev = self._pending
+                torch.cuda.current_stream(f.device).wait_event(ev)
+            else:
+                halo_lo, halo_hi, planes = self._exchange(f)
+            self._pending = None
+            if self.comm == "pairwise":
+                return self.solver.apply_coupled_nb(f, out, halo_lo, halo_hi, planes)
+            return self.solver.apply_coupled(f, out, halo_lo, halo_hi, planes)
+        lo_buf, hi_buf, faces, faces_all = self._buffers(f)[:4]
         halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)
         out = self.solver.apply_local(f, out, halo_lo, halo_hi)
         self.solver.interface_pack(out, faces)

@@ -75,6 +75,28 @@ int cfd_interface_pack(cfd_plan *plan, const double *df, double *faces, void *st
  * round-off are touched. */
 int cfd_reduced_correct(cfd_plan *plan, double *df, const double *faces_all, void *stream);
 
+/* Fused multi-rank path (no correction pass).  cfd_edge_faces computes the same interface planes as
+ * cfd_apply + cfd_interface_pack, but directly from f and from the 33 + 34 rows next to the block ends only
+ * (x_R[first] / x_R[last] do not depend on rows further away, to 0.268^32 = 5e-19).  After the all-gather,
+ * cfd_apply_coupled solves the reduced system per line inside the fused kernel and folds the two interface
+ * unknowns into rows 0 and n-1 of the block system, so df leaves the kernel as the FINAL derivative:
+ * computeRHS + solve + reducedSolverKernel + sumSolutions (code/cuda/compact.py:40-44) in one pass.
+ * Needs >= 66 rows per block; shorter blocks use the three-call path above. */
+int cfd_edge_faces(cfd_plan *plan, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
+                   void *stream);
+int cfd_apply_coupled(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+                      const double *faces_all, void *stream);
+
+/* Neighbour-only variant of the coupled solve.  For blocks of >= 64 rows the reduced matrix is block diagonal
+ * in fp64 (the couplings x_UH[last], x_LH[first] between successive interfaces are ~0.268^64 = 1e-37), so a
+ * rank needs ONE interface plane from each neighbour instead of the all-gathered 2P planes.
+ * faces_nb is [2*V][plane] over the V = cfd_nb_layout() "virtual ranks" (rank-1 if any, rank, rank+1 if any):
+ * planes 2*own, 2*own+1 = this rank's faces (cfd_edge_faces writes them there), plane 2*own-1 = the left
+ * neighbour's faces[1], plane 2*own+2 = the right neighbour's faces[0]; the two outermost planes are unused. */
+int cfd_apply_coupled_nb(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
+                         const double *faces_nb, void *stream);
+int cfd_nb_layout(const cfd_plan *plan, int *virtual_ranks, int *own_index);
+
 /* Synchronous host-buffer form of cfd_apply for part_size == 1 (what the reference's OpenCL flavour
  * offers: ndarray in, ndarray out, code/ocl/compact.py:26-61).  Copies f to the device, runs the kernel,
  * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory. */
@@ -92,6 +114,8 @@ int cfd_plan_tables(const cfd_plan *plan, double *out);
 int cfd_debug_tables(int n, const double coeffs[7], double scale, double *out);
 int cfd_debug_secondary(int n, int part_rank, int part_size, double *x_uh, double *x_lh, double *ra, double *rb,
                         double *rc);
+int cfd_debug_neighbour(int n, int part_rank, int part_size, int *virtual_ranks, int *own_index, double *va,
+                        double *vb, double *vc);
 /* secondary solutions x_UH, x_LH (each n doubles) and the reduced matrix a,b,c (each 2*part_size). */
 int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double *ra, double *rb, double *rc);
 

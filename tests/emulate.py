@@ -25,7 +25,8 @@ def tables(n, coeffs, scale):
                 K=int(s[5]), jl=int(s[6]), fast_ok=bool(s[7]))
 
 
-def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=None, halo_hi=None):
+def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=None, halo_hi=None,
+                 alpha=None, beta=None):
     """
     F: [nlines, n] (each row one line).  h given -> derivative (Pade RHS fused), else plain solve of F.
     Follows the kernel step by step: per chunk forward elimination with HEAD / MID / TAIL coefficients,
@@ -41,7 +42,13 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
     Fp = np.zeros((nl, K * CH))
     Fp[:, :n] = F                                   # TMA zero-fills out-of-bounds rows
     out = np.full((nl, K * CH), np.nan)
-    eprev = np.zeros(nl)
+    # coupled multi-rank solve (cfd_apply_coupled): interface unknowns as Dirichlet data of the block
+    coupled = alpha is not None
+    if coupled and not lo_closure:
+        T["head"]["l"][0] = coeffs[2] * T["beta0"]                  # a_i * beta_0, as cfd_create does
+    snb = T["betan"] * coeffs[4] if (coupled and not hi_closure) else 0.0
+    bval = np.asarray(beta, dtype=np.float64) if coupled else np.zeros(nl)
+    eprev = np.asarray(alpha, dtype=np.float64).copy() if (coupled and not lo_closure) else np.zeros(nl)
     fm1 = np.zeros(nl) if (lo_closure or not deriv) else np.asarray(halo_lo, dtype=np.float64).copy()
     fm2 = np.zeros(nl)
     hval = np.zeros(nl) if (hi_closure or not deriv) else np.asarray(halo_hi, dtype=np.float64)
@@ -75,6 +82,8 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
                         r = s0c * (-5. * Fc[:, 0] + 4. * Fc[:, 1] + Fc[:, 2])
                     if j == jlast and hi_closure:
                         r = snc * (5. * Fc[:, j] - 4. * fm1 - fm2)
+                    if j == jlast and not hi_closure:
+                        r = r - snb * bval
                     fm2, fm1 = fm1, Fc[:, j]
                 else:
                     r = tab["sk"][j] * Fc[:, j]
@@ -104,3 +113,33 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
             x = bwd(eA, x, 1 if k == 1 else 0, k - 1)
         eA = eB
     return out[:, :n]
+
+
+def edge_faces(F, coeffs, h, lo_closure, hi_closure, halo_lo, halo_hi):
+    """Emulation of edge_faces_kernel: interface values from the 33 + 34 rows next to the block ends."""
+    F = np.asarray(F, dtype=np.float64)
+    nl, n = F.shape
+    assert n >= 2 * CH + 2
+    T = tables(n, coeffs, 3. / (4 * h))
+    lo_face, hi_face = np.zeros(nl), np.zeros(nl)
+    if not lo_closure:
+        fm1 = np.asarray(halo_lo, dtype=np.float64)
+        eprev = np.zeros(nl)
+        e = np.zeros((nl, CH))
+        for j in range(CH):
+            eprev = -T["head"]["l"][j] * eprev + T["head"]["sk"][j] * (F[:, j + 1] - fm1)
+            e[:, j] = eprev
+            fm1 = F[:, j]
+        x = np.zeros(nl)
+        for j in range(CH - 1, -1, -1):
+            x = -T["head"]["g"][j] * x + e[:, j]
+        lo_face = -x
+    if not hi_closure:
+        Ft = F[:, n - CH - 2:]
+        eprev = np.zeros(nl)
+        for j in range(1, CH + 1):
+            eprev = -T["l_mid"] * eprev + T["sk_mid"] * (Ft[:, j + 1] - Ft[:, j - 1])
+        jl = T["jl"]
+        eprev = -T["tail"]["l"][jl] * eprev + T["tail"]["sk"][jl] * (np.asarray(halo_hi) - Ft[:, CH])
+        hi_face = -eprev
+    return lo_face, hi_face

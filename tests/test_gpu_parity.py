@@ -222,7 +222,8 @@ def test_pthomas(C):
 # partitioned line on ONE device: all ranks' blocks processed in turn through the multi-rank entry points
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("axis,P,shape", [(2, 2, (64, 24, 40)), (2, 4, (128, 16, 34)), (2, 8, (256, 8, 32)),
-                                           (0, 4, (6, 10, 128)), (1, 2, (5, 80, 36))])
+                                           (0, 4, (6, 10, 128)), (1, 2, (5, 80, 36)), (2, 2, (132, 20, 40)),
+                                           (2, 3, (300, 6, 34)), (0, 2, (4, 6, 200)), (1, 4, (3, 512, 10))])
 def test_partitioned_line_emulated(C, axis, P, shape):
     import torch
     rng = np.random.default_rng(P + axis)
@@ -248,6 +249,32 @@ def test_partitioned_line_emulated(C, axis, P, shape):
     got = np.concatenate([o.cpu().numpy() for o in outs], axis=ax)
     assert relinf(got, want) <= TOL
     assert relinf(got, O.partition_derivative(f, axis, h, P)) <= TOL
+    if n >= 66:
+        # fused path: interface planes from the block ends, reduced solve folded into the one kernel
+        faces2 = torch.zeros_like(faces)
+        halos = []
+        for r in range(P):
+            lo = dev(np.take(blocks[r - 1], n - 1, axis=ax)) if r > 0 else None
+            hi = dev(np.take(blocks[r + 1], 0, axis=ax)) if r < P - 1 else None
+            halos.append((lo, hi))
+            solvers[r].edge_faces(dev(blocks[r]), faces2[2 * r:2 * r + 2], lo, hi)
+        assert (faces2 - faces).abs().max().item() <= 1e-13 * max(1.0, faces.abs().max().item())
+        outs2 = [solvers[r].apply_coupled(dev(blocks[r]), None, halos[r][0], halos[r][1], faces2) for r in range(P)]
+        got2 = np.concatenate([o.cpu().numpy() for o in outs2], axis=ax)
+        assert relinf(got2, want) <= TOL
+        # neighbour-only exchange: each rank sees its own faces and one plane from each neighbour
+        outs3 = []
+        for r in range(P):
+            pv, own = solvers[r].nb_layout()
+            nbuf = torch.zeros((2 * pv, plane), dtype=torch.float64, device="cuda")
+            nbuf[2 * own:2 * own + 2] = faces2[2 * r:2 * r + 2]
+            if r > 0:
+                nbuf[2 * own - 1] = faces2[2 * r - 1]
+            if r < P - 1:
+                nbuf[2 * own + 2] = faces2[2 * r + 2]
+            outs3.append(solvers[r].apply_coupled_nb(dev(blocks[r]), None, halos[r][0], halos[r][1], nbuf))
+        got3 = np.concatenate([o.cpu().numpy() for o in outs3], axis=ax)
+        assert relinf(got3, want) <= TOL
 
 
 def test_partition_nccl_two_gpus():

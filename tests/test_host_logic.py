@@ -8,7 +8,7 @@ import pytest
 
 from oracle import cfd_oracle as O
 from tests.conftest import ROOT
-from tests.emulate import PADE, stream_lines, tables
+from tests.emulate import PADE, edge_faces, stream_lines, tables
 
 
 def relinf(a, b):
@@ -114,3 +114,65 @@ def test_reduced_system_tables(n, size):
         np.testing.assert_allclose(ra, ra_w, rtol=1e-13, atol=1e-300)
         np.testing.assert_allclose(rb, rb_w, rtol=1e-13, atol=1e-300)
         np.testing.assert_allclose(rc, rc_w, rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("n,size", [(66, 2), (96, 3), (128, 4), (100, 2)])
+def test_fused_multirank_schedule(n, size):
+    """cfd_edge_faces + all-gather + cfd_apply_coupled (emulated with the library's tables) == one-rank derivative:
+    interface planes from the block ends only, reduced solve, interface unknowns folded into rows 0 / n-1."""
+    from compact_finite_differences_b200._lib import check, lib
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(n + size)
+    nl = 5
+    F = rng.random((nl, size * n))
+    h = 0.21
+    want = O.derivative(F.reshape(1, nl, size * n), 0, h).reshape(nl, size * n)
+    faces = np.zeros((2 * size, nl))
+    blocks = []
+    for r in range(size):
+        blk = F[:, r * n:(r + 1) * n]
+        lo = None if r == 0 else F[:, r * n - 1]
+        hi = None if r == size - 1 else F[:, (r + 1) * n]
+        co = O.partition_local_coeffs(r, size)
+        blocks.append((blk, co, lo, hi))
+        faces[2 * r], faces[2 * r + 1] = edge_faces(blk, co, h, r == 0, r == size - 1, lo, hi)
+        # the edge values equal the faces of the full block-local solve
+        xr = stream_lines(blk, co, h, lo_closure=r == 0, hi_closure=r == size - 1, halo_lo=lo, halo_hi=hi)
+        if r > 0:
+            np.testing.assert_allclose(faces[2 * r], -xr[:, 0], rtol=1e-13, atol=1e-15)
+        if r < size - 1:
+            np.testing.assert_allclose(faces[2 * r + 1], -xr[:, -1], rtol=1e-13, atol=1e-15)
+    ra, rb, rc = (np.zeros(2 * size) for _ in range(3))
+    check(lib().cfd_debug_secondary(n, 0, size, None, None, *(v.ctypes.data_as(dp) for v in (ra, rb, rc))))
+    sol = O.scipy_solve_banded(ra, rb, rc, faces)
+    for r in range(size):
+        blk, co, lo, hi = blocks[r]
+        got = stream_lines(blk, co, h, lo_closure=r == 0, hi_closure=r == size - 1, halo_lo=lo, halo_hi=hi,
+                           alpha=sol[2 * r], beta=sol[2 * r + 1])
+        assert relinf(got, want[:, r * n:(r + 1) * n]) < 1e-13
+
+
+@pytest.mark.parametrize("n,size", [(66, 2), (64, 3), (128, 4), (96, 8)])
+def test_neighbour_only_reduced_system(n, size):
+    """Neighbour-only interface system (ranks r-1, r, r+1) gives the same two unknowns as the full 2P system."""
+    from compact_finite_differences_b200._lib import check, lib
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    rng = np.random.default_rng(size)
+    faces = rng.standard_normal((2 * size, 7))
+    faces[0] = 0.0
+    faces[-1] = 0.0
+    ra, rb, rc = O.partition_reduced_matrix(n, size)
+    full = O.scipy_solve_banded(ra, rb, rc, faces)
+    for r in range(size):
+        pv, own = ctypes.c_int(), ctypes.c_int()
+        va, vb, vc = (np.zeros(6) for _ in range(3))
+        check(lib().cfd_debug_neighbour(n, r, size, ctypes.byref(pv), ctypes.byref(own),
+                                        *(v.ctypes.data_as(dp) for v in (va, vb, vc))))
+        pv, own = pv.value, own.value
+        lo = r - own
+        assert pv == (3 if 0 < r < size - 1 else 2) and 0 <= lo and lo + pv <= size
+        fv = faces[2 * lo:2 * (lo + pv)].copy()
+        fv[0] = 0.0
+        fv[-1] = 0.0
+        sol = O.scipy_solve_banded(va[:2 * pv], vb[:2 * pv], vc[:2 * pv], fv)
+        np.testing.assert_allclose(sol[2 * own:2 * own + 2], full[2 * r:2 * r + 2], rtol=1e-13, atol=1e-15)

@@ -30,7 +30,8 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import cfd_oracle as O
-        from compact_finite_differences_b200 import exchange_halo_planes, gather_interface_planes
+        from compact_finite_differences_b200 import (exchange_halo_planes, exchange_interface_planes,
+                                                     gather_interface_planes)
         from compact_finite_differences_b200._lib import check, lib
 
         rng = np.random.default_rng(1234)                  # same field on every rank
@@ -77,6 +78,20 @@ def _worker(rank, world, port, ret):
 
         want = O.derivative(f, 2, h)[rank * n:(rank + 1) * n]
         err = np.abs(out - want).max() / np.abs(want).max()
+
+        # (5) neighbour-only exchange carries exactly the planes the virtual layout expects
+        ip = ctypes.POINTER(ctypes.c_int)
+        pv, own = ctypes.c_int(), ctypes.c_int()
+        check(lib().cfd_debug_neighbour(n, rank, world, ctypes.byref(pv), ctypes.byref(own), None, None, None))
+        pv, own = pv.value, own.value
+        nb = torch.zeros((2 * pv, ny, nx), dtype=torch.float64)
+        nb[2 * own:2 * own + 2] = faces
+        exchange_interface_planes(nb, own, pv, rank, world)
+        lo_r = rank - own
+        expect = allf[2 * lo_r:2 * (lo_r + pv)].copy()
+        expect[0] = 0.0
+        expect[-1] = 0.0
+        assert np.array_equal(nb.numpy(), expect)
         ret[rank] = err
     finally:
         dist.destroy_process_group()
