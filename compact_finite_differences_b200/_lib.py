@@ -26,6 +26,9 @@ SIGNATURES = {
     "cfd_apply_coupled_nb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_nb_layout": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "cfd_debug_neighbour": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _dp, _dp, _dp]),
+    "cfd_push_planes": (_i, [_vp, _vp, _vp, _vp, _l, _vp, _vp, ctypes.c_ulonglong, _vp]),
+    "cfd_edge_faces_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
+    "cfd_wait_flags": (_i, [_vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_apply_host": (_i, [_vp, _vp, _vp, _i]),
     "cfd_plane_elems": (_l, [_vp]),
     "cfd_tables_size": (_i, []),

@@ -568,8 +568,55 @@ extern "C" int cfd_nb_layout(const cfd_plan *p, int *virtual_ranks, int *own_ind
     return CFD_OK;
 }
 
+static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
+                     double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
+                     unsigned long long seq, bool p2p, void *stream);
+
 extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,
                               double *faces, void *stream)
+{
+    return edge_impl(p, f, halo_lo, halo_hi, faces, nullptr, nullptr, nullptr, nullptr, 0, false, stream);
+}
+
+extern "C" int cfd_edge_faces_p2p(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,
+                                  double *faces, double *peer_lo, double *peer_hi, unsigned long long *flag_lo,
+                                  unsigned long long *flag_hi, unsigned long long seq, void *stream)
+{
+    return edge_impl(p, f, halo_lo, halo_hi, faces, peer_lo, peer_hi, flag_lo, flag_hi, seq, true, stream);
+}
+
+extern "C" int cfd_push_planes(const double *src0, double *dst0, const double *src1, double *dst1, long n,
+                               unsigned long long *flag0, unsigned long long *flag1, unsigned long long seq,
+                               void *stream)
+{
+    if (n < 2 || (n & 1)) return fail(CFD_EINVAL, "plane size %ld must be even", n);
+    if ((dst0 && !src0) || (dst1 && !src1)) return fail(CFD_EINVAL, "destination without source");
+    unsigned long long *done = nullptr;
+    int rc = counter_pair(&done);
+    if (rc) return rc;
+    const int bs = 256;
+    long blocks = (n / 2 + bs - 1) / bs;
+    if (blocks > 592) blocks = 592;
+    push_planes_kernel<<<(unsigned)blocks, bs, 0, (cudaStream_t)stream>>>(
+        (const double2 *)src0, (double2 *)dst0, (const double2 *)src1, (double2 *)dst1, n / 2, flag0, flag1, done, seq);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+extern "C" int cfd_wait_flags(const unsigned long long *flag0, const unsigned long long *flag1,
+                              unsigned long long seq, void *stream)
+{
+    if (!flag0 && !flag1) return CFD_OK;
+    wait_flags_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag0, flag1, seq);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
+                     double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
+                     unsigned long long seq, bool p2p, void *stream)
 {
     if (!p || !f || !faces) return fail(CFD_EINVAL, "NULL argument");
     if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no interfaces");
@@ -586,6 +633,11 @@ extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_l
     ep.sk_last = p->kp.tail.sk[p->g.jl]; ep.l_last = p->kp.tail.l[p->g.jl];
     ep.halo_lo = halo_lo; ep.halo_hi = halo_hi;
     ep.head = p->kp.head;
+    if (p2p) {
+        ep.peer_lo = peer_lo; ep.peer_hi = peer_hi; ep.flag_lo = flag_lo; ep.flag_hi = flag_hi; ep.seq = seq;
+        int rc = counter_pair(&ep.done);
+        if (rc) return rc;
+    }
     const int bs = 128;
     edge_faces_kernel<<<(unsigned)((ep.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(f, faces, ep);
     g_launches++;

@@ -521,19 +521,52 @@ struct EdgeP {
     int lo_closure, hi_closure;
     double sk_mid, l_mid, s0c, snc, sk_last, l_last;
     const double *halo_lo, *halo_hi;
+    // NVLink peer-memory variant: the two faces are also stored straight into the neighbours' interface
+    // buffers (peer addresses), and the last CTA to finish raises the neighbours' arrival flags to `seq`.
+    double *peer_lo, *peer_hi;                 // left neighbour's slot for our faces[0], right neighbour's for faces[1]
+    unsigned long long *flag_lo, *flag_hi;     // arrival flags in the neighbours' memory
+    unsigned long long *done;                  // local CTA counter (zero on entry, zero on exit)
+    unsigned long long seq;
     RowTab head;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{ asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Last CTA of a grid to arrive publishes `seq` to the (peer) flags; every CTA's stores were made visible
+// system-wide by its own __threadfence_system() before it arrived.
+__device__ __forceinline__ void publish_when_grid_done(unsigned long long *done, unsigned long long *flag_a,
+                                                       unsigned long long *flag_b, unsigned long long seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done, 1ULL) == (unsigned long long)gridDim.x - 1) {
+            *done = 0ULL;
+            __threadfence_system();
+            if (flag_a) st_release_sys(flag_a, seq);
+            if (flag_b) st_release_sys(flag_b, seq);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(128)
 edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, const __grid_constant__ EdgeP p)
 {
     const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (line >= p.nlines) return;
-    const long o = line / p.inner, col = line % p.inner;
+    const bool active = line < p.nlines;
+    const long o = active ? line / p.inner : 0, col = active ? line % p.inner : 0;
     const double *fl = f + (o * p.n) * p.inner + col;
     const long st = p.inner;
     double lo_face = 0.0, hi_face = 0.0;
-    if (!p.lo_closure) {
+    if (active && !p.lo_closure) {
         double F[CH + 1], e[CH];
 #pragma unroll
         for (int j = 0; j <= CH; j++) F[j] = __ldg(fl + (long)j * st);
@@ -549,7 +582,7 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         for (int j = CH - 1; j >= 0; j--) x = fma(-p.head.g[j], x, e[j]);
         lo_face = -x;
     }
-    if (!p.hi_closure) {
+    if (active && !p.hi_closure) {
         const int n = p.n;
         const double *ft = fl + (long)(n - CH - 2) * st;       // rows n-34 .. n-1
         double F[CH + 2];
@@ -563,8 +596,37 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         eprev = fma(-p.l_last, eprev, p.sk_last * (hval - F[CH]));   // row n-1: neighbour point from the halo
         hi_face = -eprev;
     }
-    faces[line] = lo_face;
-    faces[p.nlines + line] = hi_face;
+    if (active) {
+        faces[line] = lo_face;
+        faces[p.nlines + line] = hi_face;
+        if (p.peer_lo) p.peer_lo[line] = lo_face;        // NVLink store into the left neighbour's buffer
+        if (p.peer_hi) p.peer_hi[line] = hi_face;        // ... and the right neighbour's
+    }
+    if (p.done) publish_when_grid_done(p.done, p.flag_lo, p.flag_hi, p.seq);
+}
+
+// Halo push over NVLink: copy this rank's first / last plane of f into the neighbours' halo buffers (peer
+// addresses) and raise their arrival flags (replaces the NCCL send/recv pair of the halo exchange).
+__global__ void __launch_bounds__(256)
+push_planes_kernel(const double2 *__restrict__ src0, double2 *__restrict__ dst0, const double2 *__restrict__ src1,
+                   double2 *__restrict__ dst1, long n2, unsigned long long *flag0, unsigned long long *flag1,
+                   unsigned long long *done, unsigned long long seq)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        if (dst0) dst0[i] = src0[i];
+        if (dst1) dst1[i] = src1[i];
+    }
+    publish_when_grid_done(done, flag0, flag1, seq);
+}
+
+// Stream-ordered wait until the neighbours' data of call `seq` has landed in this rank's memory.
+__global__ void wait_flags_kernel(const unsigned long long *flag0, const unsigned long long *flag1,
+                                  unsigned long long seq)
+{
+    const long long t0 = clock64();
+    if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+    if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
 }
 
 // Thread-parallel Thomas over interleaved systems sharing one matrix (reference reducedSolverKernel,

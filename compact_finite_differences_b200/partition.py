@@ -88,6 +88,49 @@ def exchange_interface_planes(faces_nb, own, pv, rank, size, group=None):
     return faces_nb
 
 
+class PeerExchange:
+    """
+    NVLink peer-memory buffers of one rank for the d/dz exchange (comm="nvlink"): no NCCL on the data path.
+    One symmetric allocation per rank (torch.distributed._symmetric_memory), laid out in doubles as
+        halo  [2 parities][2][plane]   slot 0: last plane of rank-1, slot 1: first plane of rank+1
+        faces [2 parities][6][plane]   the neighbour-only interface buffer of cfd_apply_coupled_nb
+        flags [16]                     uint64 arrival counters: 0/1 halo from left/right, 2/3 face from left/right
+    Neighbours write into it with plain stores from libcfd_b200's kernels (cfd_push_planes, cfd_edge_faces_p2p)
+    and raise the flags to the call number; consumers wait with cfd_wait_flags.  Two parities + the monotone
+    call number make buffer re-use safe without any global barrier.
+    """
+
+    def __init__(self, plane, rank, size, group, device):
+        import torch.distributed._symmetric_memory as symm
+        self.plane, self.rank, self.size = int(plane), rank, size
+        total = 4 * self.plane + 12 * self.plane + 16
+        self.buf = symm.empty(total, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        dist.barrier(group)                      # every rank's flags are zero before anybody pushes
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.seq = 0
+
+    # byte addresses inside rank r's buffer
+    def halo(self, r, parity, slot):
+        return self.ptrs[r] + 8 * ((parity * 2 + slot) * self.plane)
+
+    def faces(self, r, parity, i):
+        return self.ptrs[r] + 8 * (4 * self.plane + (parity * 6 + i) * self.plane)
+
+    def flag(self, r, k):
+        return self.ptrs[r] + 8 * (16 * self.plane + k)
+
+    def local_halo(self, parity, slot):
+        o = (parity * 2 + slot) * self.plane
+        return self.buf[o:o + self.plane]
+
+    def local_faces(self, parity, n):
+        o = 4 * self.plane + parity * 6 * self.plane
+        return self.buf[o:o + n * self.plane]
+
+
 class ZPartitionedDerivative:
     """Derivative of a z-partitioned field; `local_shape` is this rank's slab [nz/P, ny, nx]."""
 
@@ -96,8 +139,11 @@ class ZPartitionedDerivative:
         mode "fused"     : edge faces -> exchange -> ONE coupled kernel (final derivative, no correction pass)
              "reference" : local solve -> pack -> all-gather -> correction sweep (the reference's order)
         comm "allgather" : every rank receives all 2P interface planes (the reference's Gather+Scatter, rootless)
-             "pairwise"  : one interface plane from each z-neighbour (exact in fp64 for slabs >= 64 planes;
-                           fused mode only)
+             "pairwise"  : one interface plane from each z-neighbour by NCCL send/recv (exact in fp64 for slabs
+                           >= 64 planes; fused mode only)
+             "nvlink"    : the same neighbour-only data flow, but the kernels store halo and interface planes
+                           straight into the neighbours' memory over NVLink/NVSwitch (symmetric memory) and
+                           synchronise with flags -- no NCCL call on the data path (fused mode only)
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
@@ -107,7 +153,8 @@ class ZPartitionedDerivative:
         self.local_shape = tuple(int(s) for s in local_shape)
         part = (self.rank, self.size) if self.direction == 2 else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
-        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise")
+        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink")
+        self._peer = None
         self.mode = mode if self.local_shape[0] >= 66 else "reference"
         self.comm = comm if self.mode == "fused" else "allgather"
         self._buf = None
@@ -123,8 +170,48 @@ class ZPartitionedDerivative:
             self._buf = (mk(ny, nx), mk(ny, nx), mk(2, ny, nx), mk(2 * self.size, ny, nx), faces_nb, pv, own)
         return self._buf
 
+    def _exchange_nvlink(self, f):
+        """Halo push -> edge faces written into the neighbours' buffers -> flags; all stream-ordered kernels."""
+        import ctypes
+        from ._lib import check, lib
+        nz, ny, nx = self.local_shape
+        if self._peer is None:
+            self._peer = PeerExchange(ny * nx, self.rank, self.size, self.group, f.device)
+        px, r, P = self._peer, self.rank, self.size
+        px.seq += 1
+        seq, par = px.seq, px.seq & 1
+        pv, own = self.solver.nb_layout()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)
+        left, right = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+        L = lib()
+        check(L.cfd_push_planes(
+            f[0].data_ptr() if left is not None else None, px.halo(left, par, 1) if left is not None else None,
+            f[-1].data_ptr() if right is not None else None, px.halo(right, par, 0) if right is not None else None,
+            ny * nx, px.flag(left, 1) if left is not None else None, px.flag(right, 0) if right is not None else None,
+            seq, stream))
+        check(L.cfd_wait_flags(px.flag(r, 0) if left is not None else None,
+                               px.flag(r, 1) if right is not None else None, seq, stream))
+        halo_lo = px.local_halo(par, 0) if left is not None else None
+        halo_hi = px.local_halo(par, 1) if right is not None else None
+        faces_nb = px.local_faces(par, 2 * pv)
+        own_left = 1 if (left is not None and left > 0) else 0
+        plan = self.solver._plan(self.solver.direction, self.solver.spacing)
+        check(L.cfd_edge_faces_p2p(
+            plan.handle, f.data_ptr(),
+            halo_lo.data_ptr() if halo_lo is not None else None, halo_hi.data_ptr() if halo_hi is not None else None,
+            faces_nb.data_ptr() + 8 * 2 * own * px.plane,
+            px.faces(left, par, 2 * own_left + 2) if left is not None else None,
+            px.faces(right, par, 1) if right is not None else None,
+            px.flag(left, 3) if left is not None else None, px.flag(right, 2) if right is not None else None,
+            seq, stream))
+        check(L.cfd_wait_flags(px.flag(r, 2) if left is not None else None,
+                               px.flag(r, 3) if right is not None else None, seq, stream))
+        return halo_lo, halo_hi, faces_nb
+
     def _exchange(self, f):
         """Steps (1)-(3) of the fused path; returns what the coupled kernel needs."""
+        if self.comm == "nvlink":
+            return self._exchange_nvlink(f)
         lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)
         halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)
         if self.comm == "pairwise":
@@ -161,7 +248,7 @@ class ZPartitionedDerivative:
             else:
                 halo_lo, halo_hi, planes = self._exchange(f)
             self._pending = None
-            if self.comm == "pairwise":
+            if self.comm in ("pairwise", "nvlink"):
                 return self.solver.apply_coupled_nb(f, out, halo_lo, halo_hi, planes)
             return self.solver.apply_coupled(f, out, halo_lo, halo_hi, planes)
         lo_buf, hi_buf, faces, faces_all = self._buffers(f)[:4]

@@ -97,6 +97,22 @@ int cfd_apply_coupled_nb(cfd_plan *plan, const double *f, double *df, const doub
                          const double *faces_nb, void *stream);
 int cfd_nb_layout(const cfd_plan *plan, int *virtual_ranks, int *own_index);
 
+/* NVLink peer-memory exchange (no NCCL on the data path).  The caller maps each neighbour's receive buffers and
+ * 64-bit arrival flags into this process (e.g. torch.distributed._symmetric_memory, cudaIpc) and passes the
+ * PEER addresses here; `seq` is a call counter that only grows, so flags never need resetting.
+ *   cfd_push_planes     copies two planes of n doubles to peer buffers (halo exchange) and raises the peers' flags;
+ *   cfd_edge_faces_p2p  = cfd_edge_faces that also stores faces[0] / faces[1] into the left / right neighbour's
+ *                         interface buffer and raises their flags when the whole grid has finished;
+ *   cfd_wait_flags      stream-ordered wait (one thread, bounded spin) until this rank's local flags reach seq.
+ * Null peer pointers / flags mean "no neighbour on that side". */
+int cfd_push_planes(const double *src0, double *dst0, const double *src1, double *dst1, long n,
+                    unsigned long long *flag0, unsigned long long *flag1, unsigned long long seq, void *stream);
+int cfd_edge_faces_p2p(cfd_plan *plan, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
+                       double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
+                       unsigned long long seq, void *stream);
+int cfd_wait_flags(const unsigned long long *flag0, const unsigned long long *flag1, unsigned long long seq,
+                   void *stream);
+
 /* Synchronous host-buffer form of cfd_apply for part_size == 1 (what the reference's OpenCL flavour
  * offers: ndarray in, ndarray out, code/ocl/compact.py:26-61).  Copies f to the device, runs the kernel,
  * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory. */

@@ -54,7 +54,8 @@ full = (torch.sin(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(
 nl = N // world
 ref = C.CompactFiniteDifferenceSolver((N, N, N), h, 2)(full)[rank * nl:(rank + 1) * nl]
 slab = full[rank * nl:(rank + 1) * nl].contiguous()
-for mode, comm in (("fused", "pairwise"), ("fused", "allgather"), ("reference", "allgather")):
+COMMS = os.environ.get("CFD_COMMS", "nvlink,pairwise,allgather").split(",")
+for mode, comm in [("fused", c) for c in COMMS] + [("reference", "allgather")]:
     op = C.ZPartitionedDerivative((nl, N, N), h, 2, mode=mode, comm=comm)
     got = op(slab)
     report(f"smooth {N}^3 d/dz P={world} mode={op.mode}/{op.comm} vs single-GPU",
@@ -78,7 +79,7 @@ for mode, comm in (("fused", "pairwise"), ("fused", "allgather"), ("reference", 
 # overlap: exchange of d/dz started before d/dx, d/dy of the same field
 opx = C.ZPartitionedDerivative((nl, N, N), h, 0)
 opy = C.ZPartitionedDerivative((nl, N, N), h, 1)
-opz = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm="pairwise")
+opz = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm=COMMS[0])
 o3 = [torch.empty_like(slab) for _ in range(3)]
 for overlap in (False, True):
     def step():

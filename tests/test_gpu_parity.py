@@ -289,3 +289,66 @@ def test_partition_nccl_two_gpus():
            "127.0.0.1", "--master-port", "29611", os.path.join(root, "scripts", "check_partition_nccl.py"), "256"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("P,shape", [(2, (132, 12, 34)), (4, (4 * 70, 6, 32))])
+def test_peer_memory_protocol_one_device(C, P, shape):
+    """comm="nvlink" kernels (cfd_push_planes, cfd_edge_faces_p2p, cfd_wait_flags, cfd_apply_coupled_nb) with all P
+    ranks' buffers on one device: "peer" addresses are plain local addresses, every producer is enqueued before
+    any consumer waits, so the single stream cannot deadlock.  Two consecutive calls exercise both parities."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import check, lib
+    L = lib()
+    rng = np.random.default_rng(P)
+    h = 0.17
+    n = shape[0] // P
+    plane = shape[1] * shape[2]
+    solvers = [C.CompactFiniteDifferenceSolver((n,) + shape[1:], h, 2, part=(r, P)) for r in range(P)]
+    bufs = [torch.zeros(16 * plane + 16, dtype=torch.float64, device="cuda") for _ in range(P)]
+    base = [b.data_ptr() for b in bufs]
+    halo = lambda r, par, s: base[r] + 8 * ((par * 2 + s) * plane)              # noqa: E731
+    faces = lambda r, par, i: base[r] + 8 * (4 * plane + (par * 6 + i) * plane)  # noqa: E731
+    flag = lambda r, k: base[r] + 8 * (16 * plane + k)                          # noqa: E731
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seq in (1, 2, 3):
+        f = rng.random(shape)
+        want = O.derivative(f, 2, h)
+        blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
+        par = seq & 1
+        for r in range(P):
+            lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+            check(L.cfd_push_planes(blocks[r][0].data_ptr() if lf is not None else None,
+                                    halo(lf, par, 1) if lf is not None else None,
+                                    blocks[r][-1].data_ptr() if rt is not None else None,
+                                    halo(rt, par, 0) if rt is not None else None, plane,
+                                    flag(lf, 1) if lf is not None else None, flag(rt, 0) if rt is not None else None,
+                                    seq, st))
+        for r in range(P):
+            lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+            pv, own = solvers[r].nb_layout()
+            check(L.cfd_wait_flags(flag(r, 0) if lf is not None else None, flag(r, 1) if rt is not None else None,
+                                   seq, st))
+            own_left = 1 if (lf is not None and lf > 0) else 0
+            plan = solvers[r]._plan(2, h)
+            check(L.cfd_edge_faces_p2p(plan.handle, blocks[r].data_ptr(),
+                                       halo(r, par, 0) if lf is not None else None,
+                                       halo(r, par, 1) if rt is not None else None,
+                                       faces(r, par, 2 * own),
+                                       faces(lf, par, 2 * own_left + 2) if lf is not None else None,
+                                       faces(rt, par, 1) if rt is not None else None,
+                                       flag(lf, 3) if lf is not None else None, flag(rt, 2) if rt is not None else None,
+                                       seq, st))
+        outs = []
+        for r in range(P):
+            lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+            check(L.cfd_wait_flags(flag(r, 2) if lf is not None else None, flag(r, 3) if rt is not None else None,
+                                   seq, st))
+            out = torch.empty_like(blocks[r])
+            plan = solvers[r]._plan(2, h)
+            check(L.cfd_apply_coupled_nb(plan.handle, blocks[r].data_ptr(), out.data_ptr(),
+                                         halo(r, par, 0) if lf is not None else None,
+                                         halo(r, par, 1) if rt is not None else None, faces(r, par, 0), st))
+            outs.append(out)
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert relinf(got, want) <= TOL
