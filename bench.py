@@ -214,7 +214,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, comm="pairwise", overlap=True):
+def workload_config(n_gpus, comm="nvlink", overlap=True):
     if n_gpus == 1:
         return {"workload": "512^3 fp64 field, derivative along x, y and z on 1 B200 (BASELINE configs[2])",
                 "grid": [512, 512, 512], "derivatives_per_step": 3, "partition": "none",
@@ -383,8 +383,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--comm", default="pairwise", choices=["pairwise", "allgather"],
-                    help="interface exchange of the partitioned d/dz: one plane per z-neighbour, or NCCL all-gather")
+    ap.add_argument("--comm", default="nvlink", choices=["nvlink", "pairwise", "allgather"],
+                    help="exchange of the partitioned d/dz: NVLink peer-memory stores from our kernels, NCCL send/recv per "
+                         "z-neighbour, or NCCL all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="do not start the d/dz exchange before d/dx, d/dy")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,7 +23,7 @@ SIGNATURES = {
     "cfd_reduced_correct": (_i, [_vp, _vp, _vp, _vp]),
     "cfd_edge_faces": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_apply_coupled": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "cfd_apply_coupled_nb": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_reduced_unknowns": (_i, [_vp, _vp, _i, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_nb_layout": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "cfd_debug_neighbour": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), _dp, _dp, _dp]),
     "cfd_push_planes": (_i, [_vp, _vp, _vp, _vp, _l, _vp, _vp, ctypes.c_ulonglong, _vp]),

@@ -152,7 +152,14 @@ class CompactFiniteDifferenceSolver:
                                    faces.data_ptr(), _stream_ptr(f)))
         return faces
 
-    def apply_coupled(self, f, out, halo_lo, halo_hi, faces_all):
+    def reduced_unknowns(self, faces, ab, neighbours_only=False, flag0=None, flag1=None, seq=0):
+        """alpha / beta planes of this rank from the gathered interface planes: cfd_reduced_unknowns."""
+        plan = self._plan(self.direction, self.spacing)
+        check(lib().cfd_reduced_unknowns(plan.handle, faces.data_ptr(), 1 if neighbours_only else 0, ab.data_ptr(),
+                                         flag0, flag1, int(seq), _stream_ptr(faces)))
+        return ab
+
+    def apply_coupled(self, f, out, halo_lo, halo_hi, ab):
         """Final derivative of the block in one pass, interface unknowns folded in: cfd_apply_coupled."""
         import torch
         plan = self._plan(self.direction, self.spacing)
@@ -161,7 +168,7 @@ class CompactFiniteDifferenceSolver:
         check(lib().cfd_apply_coupled(plan.handle, f.data_ptr(), out.data_ptr(),
                                       halo_lo.data_ptr() if halo_lo is not None else None,
                                       halo_hi.data_ptr() if halo_hi is not None else None,
-                                      faces_all.data_ptr(), _stream_ptr(f)))
+                                      ab.data_ptr(), _stream_ptr(f)))
         return out
 
     def nb_layout(self):
@@ -170,18 +177,6 @@ class CompactFiniteDifferenceSolver:
         pv, own = ctypes.c_int(), ctypes.c_int()
         check(lib().cfd_nb_layout(plan.handle, ctypes.byref(pv), ctypes.byref(own)))
         return pv.value, own.value
-
-    def apply_coupled_nb(self, f, out, halo_lo, halo_hi, faces_nb):
-        """As apply_coupled, with one interface plane from each neighbour only: cfd_apply_coupled_nb."""
-        import torch
-        plan = self._plan(self.direction, self.spacing)
-        if out is None:
-            out = torch.empty_like(f)
-        check(lib().cfd_apply_coupled_nb(plan.handle, f.data_ptr(), out.data_ptr(),
-                                         halo_lo.data_ptr() if halo_lo is not None else None,
-                                         halo_hi.data_ptr() if halo_hi is not None else None,
-                                         faces_nb.data_ptr(), _stream_ptr(f)))
-        return out
 
     def reduced_correct(self, df, faces_all):
         plan = self._plan(self.direction, self.spacing)

@@ -419,7 +419,6 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     // coupled multi-rank solve: known neighbour unknowns enter rows 0 / n-1 as Dirichlet data
     if (part_rank > 0) p->kp.head.l[0] = m.ai * p->kp.s0c;               // a_i * beta_0 (eprev starts at alpha)
     p->kp.snb = (part_rank < part_size - 1) ? p->kp.snc * m.ci : 0.0;     // beta_{n-1} * c_i
-    p->kp.P = part_size; p->kp.rank = part_rank;
     p->kp.s0c *= 1.0 / (2.0 * h);
     p->kp.snc *= 1.0 / (2.0 * h);
 
@@ -521,7 +520,7 @@ static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *
 }
 
 static int apply_impl(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
-                      const double *faces_all, void *stream, bool neighbours_only = false)
+                      const double *ab, void *stream)
 {
     if (!p || !f || !df) return fail(CFD_EINVAL, "NULL argument");
     if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
@@ -531,8 +530,7 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     if (rc) return rc;
     KParams kp = p->kp;
     kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
-    kp.faces_all = faces_all; kp.lu = p->d_lu;
-    if (neighbours_only) { kp.lu = p->d_lu_nb; kp.P = p->nb_pv; kp.rank = p->nb_own; }
+    kp.ab = ab; kp.nlines = p->g.nlines;
     if (p->g.contig) return launch_stream<true, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
     return launch_stream<false, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
 }
@@ -544,20 +542,28 @@ extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double 
 }
 
 extern "C" int cfd_apply_coupled(cfd_plan *p, const double *f, double *df, const double *halo_lo,
-                                 const double *halo_hi, const double *faces_all, void *stream)
+                                 const double *halo_hi, const double *ab, void *stream)
 {
     if (p && p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: use cfd_apply");
-    if (!faces_all) return fail(CFD_EINVAL, "faces_all is NULL");
-    return apply_impl(p, f, df, halo_lo, halo_hi, faces_all, stream);
+    if (!ab) return fail(CFD_EINVAL, "ab (interface unknowns) is NULL");
+    return apply_impl(p, f, df, halo_lo, halo_hi, ab, stream);
 }
 
-extern "C" int cfd_apply_coupled_nb(cfd_plan *p, const double *f, double *df, const double *halo_lo,
-                                    const double *halo_hi, const double *faces_nb, void *stream)
+extern "C" int cfd_reduced_unknowns(cfd_plan *p, const double *faces, int neighbours_only, double *ab,
+                                    const unsigned long long *flag0, const unsigned long long *flag1,
+                                    unsigned long long seq, void *stream)
 {
-    if (p && p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: use cfd_apply");
-    if (!faces_nb) return fail(CFD_EINVAL, "faces_nb is NULL");
-    if (p && p->g.n < 2 * CH) return fail(CFD_EUNSUPPORTED, "neighbour-only coupling needs >= %d rows per block", 2 * CH);
-    return apply_impl(p, f, df, halo_lo, halo_hi, faces_nb, stream, true);
+    if (!p || !faces || !ab) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no interfaces");
+    if (neighbours_only && p->g.n < 2 * CH)
+        return fail(CFD_EUNSUPPORTED, "neighbour-only coupling needs >= %d rows per block", 2 * CH);
+    const int bs = 256;
+    reduced_planes_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        faces, neighbours_only ? p->d_lu_nb : p->d_lu, p->g.nlines, neighbours_only ? p->nb_pv : p->size,
+        neighbours_only ? p->nb_own : p->rank, ab, flag0, flag1, seq);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
 }
 
 extern "C" int cfd_nb_layout(const cfd_plan *p, int *virtual_ranks, int *own_index)

@@ -54,11 +54,11 @@ struct KParams {
     double s0c, snc;   // beta_0/(2h), beta_{n-1}/(2h) for the closure rows
     const double *halo_lo, *halo_hi;   // neighbour planes of f (multi-rank), one value per line
     unsigned long long *counter;   // {next bundle, finished warps}, zero on entry, zero again on exit
-    // coupled multi-rank solve: interface unknowns from the all-gathered faces, folded into rows 0 and n-1
-    const double *faces_all;       // [2P][plane] or nullptr (block-local solve)
-    const double *lu;              // [6][2P] two-sided elimination tables of the reduced matrix
-    int P, rank;
-    double snb;                    // beta_{n-1} * c_i: weight of the right neighbour's first unknown in row n-1
+    // coupled multi-rank solve: the two interface unknowns of every line (alpha = last point of the left
+    // neighbour, beta = first point of the right neighbour) folded into rows 0 and n-1 as Dirichlet data
+    const double *ab;              // [2][plane] = alpha plane, beta plane; nullptr = block-local solve
+    long nlines;                   // plane size
+    double snb;                    // beta_{n-1} * c_i: weight of beta in row n-1
     RowTab head, tail;
 };
 
@@ -122,6 +122,16 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{ asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void st_stream(double *p, double v)
 { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
@@ -133,16 +143,16 @@ __device__ __forceinline__ void st_stream(double *p, double v)
 // and closed with a 2x2 solve, so it needs registers only.
 //   lu = [6][2P]: a_i, c_i, 1/p_i, c_i/p_i (top-down pivots p), 1/q_i, a_i/q_i (bottom-up pivots q).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void reduced_unknowns(const double *__restrict__ faces_all, const double *__restrict__ lu,
+__device__ __forceinline__ void reduced_unknowns(const double *faces_all, const double *__restrict__ lu,
                                                  long nlines, long line, int P, int rank, double &alpha, double &beta)
 {
     const int m = 2 * P;
     const double *a = lu, *c = lu + m, *ip = lu + 2 * m, *cp = lu + 3 * m, *iq = lu + 4 * m, *aq = lu + 5 * m;
     const int r0 = 2 * rank, r1 = 2 * rank + 1;
-    double t = __ldg(faces_all + line) * ip[0];
-    for (int i = 1; i <= r0; i++) t = (__ldg(faces_all + (long)i * nlines + line) - a[i] * t) * ip[i];
-    double u = __ldg(faces_all + (long)(m - 1) * nlines + line) * iq[m - 1];
-    for (int i = m - 2; i >= r1; i--) u = (__ldg(faces_all + (long)i * nlines + line) - c[i] * u) * iq[i];
+    double t = faces_all[line] * ip[0];
+    for (int i = 1; i <= r0; i++) t = (faces_all[(long)i * nlines + line] - a[i] * t) * ip[i];
+    double u = faces_all[(long)(m - 1) * nlines + line] * iq[m - 1];
+    for (int i = m - 2; i >= r1; i--) u = (faces_all[(long)i * nlines + line] - c[i] * u) * iq[i];
     // x[r0] = t - cp[r0]*x[r1];  x[r1] = u - aq[r1]*x[r0]
     alpha = (t - cp[r0] * u) / (1.0 - cp[r0] * aq[r1]);
     beta = u - aq[r1] * alpha;
@@ -334,6 +344,34 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
     uint32_t phase = 0;
     int oc0 = 0, oc2 = 0;         // STRIDED: first column / outer index of the bundle (TMA store coordinates)
 
+    // Per-line boundary data of a partitioned block (neighbour points of f, interface unknowns) are fetched
+    // one bundle ahead, while the previous bundle's last chunk is being computed, so that their global-load
+    // latency never sits in front of the forward recurrence.
+    long pf_id = -1;
+    double pf_lo = 0.0, pf_hi = 0.0, pf_a = 0.0, pf_b = 0.0;
+    auto prefetch_edge = [&](long nb_) {
+        long line;
+        bool lane_ok;
+        if constexpr (CONTIG) {
+            line = nb_ * CH + lane;
+            lane_ok = line < p.rows;
+        } else {
+            const int c0 = (int)(nb_ % p.inner_tiles) * CH;
+            lane_ok = c0 + lane < p.inner;
+            line = (nb_ / p.inner_tiles) * (long)p.inner + c0 + lane;
+        }
+        pf_lo = pf_hi = pf_a = pf_b = 0.0;
+        if (lane_ok) {
+            if (!p.lo_closure) pf_lo = __ldg(p.halo_lo + line);
+            if (!p.hi_closure) pf_hi = __ldg(p.halo_hi + line);
+            if (p.ab != nullptr) {
+                pf_a = __ldg(p.ab + line);
+                pf_b = __ldg(p.ab + p.nlines + line);
+            }
+        }
+        pf_id = nb_;
+    };
+
     for (;;) {
         if (k == 0) {
             b = tag[slot];
@@ -344,30 +382,22 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
             }
             eprev = 0.0; fm1 = 0.0; fm2 = 0.0; hval = 0.0; bval = 0.0;
             if constexpr (DERIV) {
-                if (!p.lo_closure || !p.hi_closure) {          // block of a partitioned line: neighbour planes of f
-                    long line;
-                    bool lane_ok;
-                    if constexpr (CONTIG) {
-                        line = b * CH + lane;
-                        lane_ok = line < p.rows;
-                    } else {
-                        lane_ok = oc0 + lane < p.inner;
-                        line = (long)oc2 * p.inner + oc0 + lane;
-                    }
-                    if (!p.lo_closure && lane_ok) fm1 = __ldg(p.halo_lo + line);
-                    if (!p.hi_closure && lane_ok) hval = __ldg(p.halo_hi + line);
-                    if (p.faces_all != nullptr && lane_ok) {
-                        // coupled solve: the interface unknowns become Dirichlet data of the block --
-                        // row 0 sees x_{-1} = alpha through l_0 = a_i*beta_0, row n-1 sees x_n = beta through snb
-                        double alpha;
-                        const long nlines = CONTIG ? p.rows : (long)p.inner * p.outer;
-                        reduced_unknowns(p.faces_all, p.lu, nlines, line, p.P, p.rank, alpha, bval);
-                        eprev = alpha;
-                    }
+                if (!p.lo_closure || !p.hi_closure) {      // block of a partitioned line
+                    if (pf_id != b) prefetch_edge(b);       // first bundle of this warp: nothing was prefetched
+                    fm1 = pf_lo;                            // f[-1]: neighbour plane of f
+                    hval = pf_hi;                           // f[n]
+                    eprev = pf_a;                           // coupled: row 0 sees x_{-1} = alpha through l_0 = a_i*beta_0
+                    bval = pf_b;                            //          row n-1 sees x_n = beta through snb
                 }
             }
         }
         const bool last = (k == K - 1);
+        if constexpr (DERIV) {
+            if (last && (!p.lo_closure || !p.hi_closure)) {
+                const long nxt = tag[(slot + 1 == NS) ? 0 : slot + 1];     // the next tile opens the next bundle
+                if (nxt >= 0) prefetch_edge(nxt);
+            }
+        }
         const unsigned char *st = wbase + slot * SLOT_BYTES;
         mbar_wait(bar0 + 8 * slot, phase);
         load_chunk<CONTIG>(st, lane, F);
@@ -507,6 +537,30 @@ __global__ void reduced_correct_kernel(double *__restrict__ x, const double *__r
     }
 }
 
+// Interface unknowns of every line of this rank: ab[0] = alpha plane, ab[1] = beta plane, from the gathered
+// interface planes (all 2P of them, or the neighbour-only buffer with its own small elimination table).
+// Optionally first waits (bounded spin) until the neighbours' planes of call `seq` have landed.
+__global__ void __launch_bounds__(256)
+reduced_planes_kernel(const double *__restrict__ faces, const double *__restrict__ lu, long nlines, int P, int rank,
+                      double *__restrict__ ab, const unsigned long long *flag0, const unsigned long long *flag1,
+                      unsigned long long seq)
+{
+    if (flag0 || flag1) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+            if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+        }
+        __syncthreads();
+    }
+    const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nlines) return;
+    double alpha, beta;
+    reduced_unknowns(faces, lu, nlines, line, P, rank, alpha, beta);
+    ab[line] = alpha;
+    ab[nlines + line] = beta;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Interface planes straight from f, WITHOUT the block solve: faces[0] = -x_R[0], faces[1] = -x_R[n-1]
 // (what negateAndCopyFaces, code/cuda/kernels.cu:76-113, extracts after the reference's full local solve).
@@ -529,16 +583,6 @@ struct EdgeP {
     unsigned long long seq;
     RowTab head;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{ asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Last CTA of a grid to arrive publishes `seq` to the (peer) flags; every CTA's stores were made visible
 // system-wide by its own __threadfence_system() before it arrived.

@@ -10,8 +10,9 @@ Here, for a grid split into P slabs along z:
     d/dz       : (1) send/recv ONE boundary plane of f with each z-neighbour;
                  (2) interface planes -x_R[first], -x_R[last] from the 33 + 34 planes next to the slab ends
                      (cfd_edge_faces: they do not depend on planes further away, to 5e-19);
-                 (3) ALL-GATHER them -- every rank then solves the identical 2P-unknown reduced system
-                     redundantly (no root, no scatter);
+                 (3) ALL-GATHER them (or, comm="pairwise"/"nvlink", one plane from each z-neighbour) -- every
+                     rank then solves the reduced system redundantly for its own two unknowns per line
+                     (cfd_reduced_unknowns; no root, no scatter);
                  (4) ONE fused kernel (cfd_apply_coupled): RHS + solve with the two interface unknowns folded
                      into rows 0 and n-1 -- the final derivative, no correction pass.
                  mode="reference" keeps the reference's order instead: local solve (cfd_apply) ->
@@ -168,6 +169,7 @@ class ZPartitionedDerivative:
             pv, own = self.solver.nb_layout() if self.size > 1 and self.direction == 2 else (1, 0)
             faces_nb = torch.zeros((2 * pv, ny, nx), dtype=torch.float64, device=f.device)
             self._buf = (mk(ny, nx), mk(ny, nx), mk(2, ny, nx), mk(2 * self.size, ny, nx), faces_nb, pv, own)
+            self._ab = mk(2, ny, nx)
         return self._buf
 
     def _exchange_nvlink(self, f):
@@ -204,12 +206,15 @@ class ZPartitionedDerivative:
             px.faces(right, par, 1) if right is not None else None,
             px.flag(left, 3) if left is not None else None, px.flag(right, 2) if right is not None else None,
             seq, stream))
-        check(L.cfd_wait_flags(px.flag(r, 2) if left is not None else None,
-                               px.flag(r, 3) if right is not None else None, seq, stream))
-        return halo_lo, halo_hi, faces_nb
+        self._buffers(f)
+        # wait for the neighbours' interface planes inside the (tiny) reduced-solve kernel, then alpha / beta
+        check(L.cfd_reduced_unknowns(plan.handle, faces_nb.data_ptr(), 1, self._ab.data_ptr(),
+                                     px.flag(r, 2) if left is not None else None,
+                                     px.flag(r, 3) if right is not None else None, seq, stream))
+        return halo_lo, halo_hi, self._ab
 
     def _exchange(self, f):
-        """Steps (1)-(3) of the fused path; returns what the coupled kernel needs."""
+        """Steps (1)-(3) of the fused path; returns (halo_lo, halo_hi, alpha/beta planes) for the coupled kernel."""
         if self.comm == "nvlink":
             return self._exchange_nvlink(f)
         lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)
@@ -217,10 +222,12 @@ class ZPartitionedDerivative:
         if self.comm == "pairwise":
             self.solver.edge_faces(f, faces_nb[2 * own:2 * own + 2], halo_lo, halo_hi)
             exchange_interface_planes(faces_nb, own, pv, self.rank, self.size, self.group)
-            return halo_lo, halo_hi, faces_nb
+            self.solver.reduced_unknowns(faces_nb, self._ab, neighbours_only=True)
+            return halo_lo, halo_hi, self._ab
         self.solver.edge_faces(f, faces, halo_lo, halo_hi)
         gather_interface_planes(faces, self.size, self.group, faces_all)
-        return halo_lo, halo_hi, faces_all
+        self.solver.reduced_unknowns(faces_all, self._ab)
+        return halo_lo, halo_hi, self._ab
 
     def begin(self, f):
         """Start the halo / interface exchange of d/dz on a side stream so that it overlaps whatever the caller
@@ -248,8 +255,6 @@ class ZPartitionedDerivative:
             else:
                 halo_lo, halo_hi, planes = self._exchange(f)
             self._pending = None
-            if self.comm in ("pairwise", "nvlink"):
-                return self.solver.apply_coupled_nb(f, out, halo_lo, halo_hi, planes)
             return self.solver.apply_coupled(f, out, halo_lo, halo_hi, planes)
         lo_buf, hi_buf, faces, faces_all = self._buffers(f)[:4]
         halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)

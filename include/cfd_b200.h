@@ -75,26 +75,32 @@ int cfd_interface_pack(cfd_plan *plan, const double *df, double *faces, void *st
  * round-off are touched. */
 int cfd_reduced_correct(cfd_plan *plan, double *df, const double *faces_all, void *stream);
 
-/* Fused multi-rank path (no correction pass).  cfd_edge_faces computes the same interface planes as
- * cfd_apply + cfd_interface_pack, but directly from f and from the 33 + 34 rows next to the block ends only
- * (x_R[first] / x_R[last] do not depend on rows further away, to 0.268^32 = 5e-19).  After the all-gather,
- * cfd_apply_coupled solves the reduced system per line inside the fused kernel and folds the two interface
- * unknowns into rows 0 and n-1 of the block system, so df leaves the kernel as the FINAL derivative:
- * computeRHS + solve + reducedSolverKernel + sumSolutions (code/cuda/compact.py:40-44) in one pass.
- * Needs >= 66 rows per block; shorter blocks use the three-call path above. */
+/* Fused multi-rank path (no correction pass).
+ *   cfd_edge_faces       the same interface planes as cfd_apply + cfd_interface_pack, but directly from f and from
+ *                        the 33 + 34 rows next to the block ends only (x_R[first] / x_R[last] do not depend on rows
+ *                        further away, to 0.268^32 = 5e-19).
+ *   cfd_reduced_unknowns solves the reduced system of every line for THIS rank's two unknowns (rows of
+ *                        code/cuda/compact.py:96-111, elimination of reducedSolverKernel kernels.cu:115-145):
+ *                        ab[0] = alpha plane (the left neighbour's last point), ab[1] = beta plane (the right
+ *                        neighbour's first point).  neighbours_only = 0: faces = all-gathered [2P][plane];
+ *                        neighbours_only = 1: faces = [2V][plane] over the V = cfd_nb_layout() "virtual ranks"
+ *                        (rank-1 if any, rank, rank+1 if any) -- planes 2*own, 2*own+1 are this rank's faces,
+ *                        plane 2*own-1 the left neighbour's faces[1], plane 2*own+2 the right neighbour's
+ *                        faces[0], the two outermost planes unused (zero).  For blocks of >= 64 rows the reduced
+ *                        matrix is block diagonal in fp64 (couplings ~0.268^64 = 1e-37), so this is exact and a
+ *                        rank needs ONE plane from each neighbour instead of 2P.
+ *                        flag0/flag1/seq: optional arrival flags to wait on first (peer-memory exchange below).
+ *   cfd_apply_coupled    the fused kernel with alpha, beta folded into rows 0 and n-1 of the block system, so df
+ *                        leaves it as the FINAL derivative: computeRHS + solve + sumSolutions
+ *                        (code/cuda/compact.py:40-44) in one pass.  Needs >= 66 rows per block; thinner blocks
+ *                        use the three-call path above. */
 int cfd_edge_faces(cfd_plan *plan, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
                    void *stream);
+int cfd_reduced_unknowns(cfd_plan *plan, const double *faces, int neighbours_only, double *ab,
+                         const unsigned long long *flag0, const unsigned long long *flag1, unsigned long long seq,
+                         void *stream);
 int cfd_apply_coupled(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
-                      const double *faces_all, void *stream);
-
-/* Neighbour-only variant of the coupled solve.  For blocks of >= 64 rows the reduced matrix is block diagonal
- * in fp64 (the couplings x_UH[last], x_LH[first] between successive interfaces are ~0.268^64 = 1e-37), so a
- * rank needs ONE interface plane from each neighbour instead of the all-gathered 2P planes.
- * faces_nb is [2*V][plane] over the V = cfd_nb_layout() "virtual ranks" (rank-1 if any, rank, rank+1 if any):
- * planes 2*own, 2*own+1 = this rank's faces (cfd_edge_faces writes them there), plane 2*own-1 = the left
- * neighbour's faces[1], plane 2*own+2 = the right neighbour's faces[0]; the two outermost planes are unused. */
-int cfd_apply_coupled_nb(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
-                         const double *faces_nb, void *stream);
+                      const double *ab, void *stream);
 int cfd_nb_layout(const cfd_plan *plan, int *virtual_ranks, int *own_index);
 
 /* NVLink peer-memory exchange (no NCCL on the data path).  The caller maps each neighbour's receive buffers and

@@ -259,7 +259,11 @@ def test_partitioned_line_emulated(C, axis, P, shape):
             halos.append((lo, hi))
             solvers[r].edge_faces(dev(blocks[r]), faces2[2 * r:2 * r + 2], lo, hi)
         assert (faces2 - faces).abs().max().item() <= 1e-13 * max(1.0, faces.abs().max().item())
-        outs2 = [solvers[r].apply_coupled(dev(blocks[r]), None, halos[r][0], halos[r][1], faces2) for r in range(P)]
+        ab = torch.empty((2, plane), dtype=torch.float64, device="cuda")
+        outs2 = []
+        for r in range(P):
+            solvers[r].reduced_unknowns(faces2, ab)
+            outs2.append(solvers[r].apply_coupled(dev(blocks[r]), None, halos[r][0], halos[r][1], ab))
         got2 = np.concatenate([o.cpu().numpy() for o in outs2], axis=ax)
         assert relinf(got2, want) <= TOL
         # neighbour-only exchange: each rank sees its own faces and one plane from each neighbour
@@ -272,7 +276,8 @@ def test_partitioned_line_emulated(C, axis, P, shape):
                 nbuf[2 * own - 1] = faces2[2 * r - 1]
             if r < P - 1:
                 nbuf[2 * own + 2] = faces2[2 * r + 2]
-            outs3.append(solvers[r].apply_coupled_nb(dev(blocks[r]), None, halos[r][0], halos[r][1], nbuf))
+            solvers[r].reduced_unknowns(nbuf, ab, neighbours_only=True)
+            outs3.append(solvers[r].apply_coupled(dev(blocks[r]), None, halos[r][0], halos[r][1], ab))
         got3 = np.concatenate([o.cpu().numpy() for o in outs3], axis=ax)
         assert relinf(got3, want) <= TOL
 
@@ -293,7 +298,7 @@ def test_partition_nccl_two_gpus():
 
 @pytest.mark.parametrize("P,shape", [(2, (132, 12, 34)), (4, (4 * 70, 6, 32))])
 def test_peer_memory_protocol_one_device(C, P, shape):
-    """comm="nvlink" kernels (cfd_push_planes, cfd_edge_faces_p2p, cfd_wait_flags, cfd_apply_coupled_nb) with all P
+    """comm="nvlink" kernels (cfd_push_planes, cfd_edge_faces_p2p, cfd_wait_flags, cfd_reduced_unknowns) with all P
     ranks' buffers on one device: "peer" addresses are plain local addresses, every producer is enqueued before
     any consumer waits, so the single stream cannot deadlock.  Two consecutive calls exercise both parities."""
     import ctypes
@@ -340,15 +345,17 @@ def test_peer_memory_protocol_one_device(C, P, shape):
                                        flag(lf, 3) if lf is not None else None, flag(rt, 2) if rt is not None else None,
                                        seq, st))
         outs = []
+        ab = torch.empty((2, plane), dtype=torch.float64, device="cuda")
         for r in range(P):
             lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
-            check(L.cfd_wait_flags(flag(r, 2) if lf is not None else None, flag(r, 3) if rt is not None else None,
-                                   seq, st))
             out = torch.empty_like(blocks[r])
             plan = solvers[r]._plan(2, h)
-            check(L.cfd_apply_coupled_nb(plan.handle, blocks[r].data_ptr(), out.data_ptr(),
-                                         halo(r, par, 0) if lf is not None else None,
-                                         halo(r, par, 1) if rt is not None else None, faces(r, par, 0), st))
+            check(L.cfd_reduced_unknowns(plan.handle, faces(r, par, 0), 1, ab.data_ptr(),
+                                         flag(r, 2) if lf is not None else None, flag(r, 3) if rt is not None else None,
+                                         seq, st))
+            check(L.cfd_apply_coupled(plan.handle, blocks[r].data_ptr(), out.data_ptr(),
+                                      halo(r, par, 0) if lf is not None else None,
+                                      halo(r, par, 1) if rt is not None else None, ab.data_ptr(), st))
             outs.append(out)
         got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
         assert relinf(got, want) <= TOL
