@@ -39,6 +39,7 @@ SIGNATURES = {
     "nt_create": (_i, [_pp, _i, _i, _i, _i, _dp]),
     "nt_solve": (_i, [_vp, _vp, _vp]),
     "nt_destroy": (None, [_vp]),
+    "nt_is_exact_two_pass": (_i, [_vp]),
     "cfd_pthomas": (_i, [_dp, _dp, _dp, _vp, _i, _l, _vp]),
     "cfd_set_launch": (_i, [_i, _i, _i]),
     "cfd_launch_count": (_l, []),

@@ -260,7 +260,11 @@ struct nt_plan {
     Geometry g;
     KParams kp;
     MapCache cache;
+    bool exact = false;               // two-pass exact solver (matrix refused by the one-pass kernel)
+    double *d_tab = nullptr;          // [4][K*32]: forward pc, qc; backward pc, qc
 };
+
+#define CFD_ESLOWPATH (-100)   /* internal: matrix needs the exact two-pass solver */
 
 static int fill_tables(KParams &kp, const Geometry &g, const LineCoeffs &m, double scale, bool need_fast)
 {
@@ -268,7 +272,7 @@ static int fill_tables(KParams &kp, const Geometry &g, const LineCoeffs &m, doub
     if (!pv.finite) return fail(CFD_EINVAL, "zero pivot: LU without pivoting breaks down for these coefficients");
     if (g.K > 2 && need_fast) {
         if (!pv.converged || std::pow(pv.decay, CH) > 1.2e-16)
-            return fail(CFD_EUNSUPPORTED,
+            return fail(CFD_ESLOWPATH,
                         "coefficients (ai,bi,ci) = (%g,%g,%g): LU pivots do not converge / coupling %.3f^32 above fp64 "
                         "round-off; the streaming solver needs a diagonally dominant interior for n > 64",
                         m.ai, m.bi, m.ci, pv.decay);
@@ -413,7 +417,7 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     p->h = h; p->rank = part_rank; p->size = part_size;
     const LineCoeffs m = pade_block(part_rank, part_size);
     rc = fill_tables(p->kp, p->g, m, 3.0 / (4.0 * h), true);
-    if (rc) { delete p; return rc; }
+    if (rc) { delete p; return rc == CFD_ESLOWPATH ? CFD_EUNSUPPORTED : rc; }
     p->kp.lo_closure = (part_rank == 0);
     p->kp.hi_closure = (part_rank == part_size - 1);
     // coupled multi-rank solve: known neighbour unknowns enter rows 0 / n-1 as Dirichlet data
@@ -704,6 +708,35 @@ extern "C" int cfd_apply_host(cfd_plan *p, const double *f_host, double *df_host
 // ------------------------------------------------------------------------------------------------
 // near-Toeplitz solver
 // ------------------------------------------------------------------------------------------------
+template <bool CONTIG, bool REVERSE>
+static int launch_recurrence(const Geometry &g, const double *pc, const double *qc, const CUtensorMap &tm_in,
+                             const CUtensorMap &tm_out, cudaStream_t stream)
+{
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
+    constexpr int per_warp = 4 * SLOT_BYTES + 3 * 16;
+    int warps = 4;
+    const long per_sm = (g.nb + dinfo.sms - 1) / dinfo.sms;
+    if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    const size_t smem = (size_t)warps * per_warp + 1024;
+    auto kern = recurrence_kernel<CONTIG, REVERSE>;
+    static size_t configured = 0;
+    if (configured < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * per_warp + 1024));
+        configured = 4 * per_warp + 1024;
+    }
+    RParams rp;
+    rp.K = g.K; rp.inner_tiles = g.inner_tiles; rp.nb = g.nb; rp.pc = pc; rp.qc = qc;
+    int rc = counter_pair(&rp.counter);
+    if (rc) return rc;
+    long blocks = (g.nb + warps - 1) / warps;
+    if (blocks > dinfo.sms) blocks = dinfo.sms;
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, rp);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
 extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const double coeffs[7])
 {
     if (!out || !coeffs) return fail(CFD_EINVAL, "NULL argument");
@@ -720,23 +753,62 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
     if (rc) { delete p; return rc; }
     const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
     rc = fill_tables(p->kp, p->g, m, 1.0, true);
+    if (rc == CFD_ESLOWPATH) {
+        // exact two-pass LU: per-row tables on the device
+        Pivots pv = build_pivots(p->g.n, m);
+        if (!pv.finite) { delete p; return fail(CFD_EINVAL, "zero pivot: LU without pivoting breaks down"); }
+        const int L = p->g.K * CH;
+        std::vector<double> tab(4 * (size_t)L, 0.0);
+        for (int i = 0; i < p->g.n; i++) {
+            tab[i] = pv.beta[i]; tab[L + i] = pv.l[i];            // forward
+            tab[2 * L + i] = 1.0; tab[3 * L + i] = pv.g[i];       // backward
+        }
+        if (cudaMalloc(&p->d_tab, tab.size() * sizeof(double)) != cudaSuccess) {
+            delete p;
+            return fail(CFD_ECUDA, "cudaMalloc of solver tables failed");
+        }
+        cudaMemcpy(p->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+        p->exact = true;
+        g_err.clear();
+        rc = CFD_OK;
+    }
     if (rc) { delete p; return rc; }
     p->kp.lo_closure = 1; p->kp.hi_closure = 1;
     *out = p;
     return CFD_OK;
 }
 
+extern "C" int nt_is_exact_two_pass(const nt_plan *p) { return p ? (p->exact ? 1 : 0) : 0; }
+
 extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
 {
     if (!p || !d) return fail(CFD_EINVAL, "NULL argument");
     int rc = get_maps(p->cache, p->g, d, d);
     if (rc) return rc;
+    if (p->exact) {
+        const long L = (long)p->g.K * CH;
+        const double *t = p->d_tab;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (p->g.contig) {
+            rc = launch_recurrence<true, false>(p->g, t, t + L, p->cache.tm_in, p->cache.tm_out, st);
+            if (rc) return rc;
+            return launch_recurrence<true, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
+        }
+        rc = launch_recurrence<false, false>(p->g, t, t + L, p->cache.tm_in, p->cache.tm_out, st);
+        if (rc) return rc;
+        return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
+    }
     KParams kp = p->kp;
     if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
     return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
 }
 
-extern "C" void nt_destroy(nt_plan *p) { delete p; }
+extern "C" void nt_destroy(nt_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_tab);
+    delete p;
+}
 
 // ------------------------------------------------------------------------------------------------
 // pThomas

@@ -476,6 +476,142 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact two-pass solver for matrices the one-pass kernel must refuse (pivots that do not converge, or an
+// interior coupling |g|^32 above fp64 round-off, e.g. the 6th-order scheme with alpha = 1/3 or the
+// non-dominant (1,2,3,4,5,6,7) test matrix at n > 64).  One launch per sweep of the LU solve, each a
+// first-order recurrence along the line with per-row coefficients from global tables:
+//     y_i = pc_i * v_i - qc_i * y_(i-1)    (REVERSE: y_(i+1)),
+// forward:  pc = beta_i,  qc = a_i*beta_i  (v = right-hand side, y = e)
+// backward: pc = 1,       qc = c_i*beta_i  (v = e,               y = x)
+// Same warp-autonomous TMA ring, dynamic bundle draw and staged TMA store as stream_kernel; 32 B/unknown.
+// ------------------------------------------------------------------------------------------------
+struct RParams {
+    int K, inner_tiles;
+    long nb;
+    const double *pc, *qc;         // [K*32] device tables, zero beyond row n-1
+    unsigned long long *counter;
+};
+
+template <bool CONTIG, bool REVERSE>
+__global__ void __launch_bounds__(224, 1)
+recurrence_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                  const __grid_constant__ RParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int NS = 3;
+    constexpr int PER_WARP = (NS + 1) * SLOT_BYTES;
+    constexpr int CTRL = NS * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *wbase = base + warp * PER_WARP;
+    unsigned char *oslot = wbase + NS * SLOT_BYTES;
+    unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
+    const uint32_t bar0 = smem_u32(ctrl);
+    volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
+    const int K = p.K;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    long ib = 0;
+    int ik = 0, islot = 0;
+    bool dry = false;
+    auto issue = [&]() {
+        if (ik == 0 && !dry) {
+            ib = (long)atomicAdd(p.counter, 1ULL);
+            dry = ib >= p.nb;
+        }
+        if (dry) {
+            tag[islot] = -1;
+        } else {
+            tag[islot] = ib;
+            const uint32_t bar = bar0 + 8 * islot;
+            const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
+            const int kc = REVERSE ? K - 1 - ik : ik;
+            mbar_expect_tx(bar, SLOT_BYTES);
+            if constexpr (CONTIG) {
+                tma_load_2d(dst, &tm_in, bar, kc * CH, (int)(ib * CH));
+                tma_load_2d(dst + 4096, &tm_in, bar, kc * CH + 16, (int)(ib * CH));
+            } else {
+                tma_load_3d(dst, &tm_in, bar, (int)(ib % p.inner_tiles) * CH, kc * CH, (int)(ib / p.inner_tiles));
+            }
+            if (++ik == K) ik = 0;
+        }
+        if (++islot == NS) islot = 0;
+    };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NS; s++) issue();
+    }
+    __syncwarp();
+
+    double F[CH];
+    double carry = 0.0;
+    long b = 0;
+    int k = 0, slot = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        if (k == 0) {
+            b = tag[slot];
+            if (b < 0) break;
+            carry = 0.0;
+        }
+        const int kc = REVERSE ? K - 1 - k : k;
+        mbar_wait(bar0 + 8 * slot, phase);
+        load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
+        __syncwarp();
+        if (lane == 0) issue();
+        __syncwarp();
+        const double *pc = p.pc + kc * CH, *qc = p.qc + kc * CH;
+#pragma unroll
+        for (int jj = 0; jj < CH; jj++) {
+            const int j = REVERSE ? CH - 1 - jj : jj;
+            carry = fma(-__ldg(qc + j), carry, __ldg(pc + j) * F[j]);
+            F[j] = carry;
+        }
+        if (lane == 0) tma_wait_read0();
+        __syncwarp();
+        if constexpr (CONTIG) {
+            const int sw = (lane & 7) << 4;
+#pragma unroll
+            for (int m = 0; m < 16; m++)
+                *reinterpret_cast<double2 *>(oslot + lane * 128 + (m >> 3) * 4096 + (((m & 7) << 4) ^ sw)) =
+                    make_double2(F[2 * m], F[2 * m + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; j++) reinterpret_cast<double *>(oslot)[j * CH + lane] = F[j];
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if constexpr (CONTIG) {
+                tma_store_2d(&tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
+                tma_store_2d(&tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
+            } else {
+                tma_store_3d(&tm_out, smem_u32(oslot), (int)(b % p.inner_tiles) * CH, kc * CH, (int)(b / p.inner_tiles));
+            }
+            tma_commit();
+        }
+        if (++k == K) k = 0;
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    }
+    if (lane == 0) {
+        tma_wait_all0();
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * nwarps;
+        if (atomicAdd(p.counter + 1, 1ULL) == total - 1) {
+            p.counter[0] = 0ULL;
+            p.counter[1] = 0ULL;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Multi-rank helpers (z-partition): interface planes, reduced system, correction.
 // Element (o, i, c) of a block lives at (o*n + i)*inner + c; its line index is o*inner + c.
 // ------------------------------------------------------------------------------------------------

@@ -32,6 +32,8 @@ class NearToeplitzSolver:
         self._handle = ctypes.c_void_p()
         co = (ctypes.c_double * 7)(*self.coeffs)
         check(lib().nt_create(ctypes.byref(self._handle), self.nz, self.ny, self.nx, self.axis, co))
+        #: True when the matrix is not diagonally dominant enough for the one-pass kernel (exact two-pass LU instead)
+        self.two_pass = bool(lib().nt_is_exact_two_pass(self._handle))
 
     def solve(self, x_d):
         """Solve in place: on entry x_d holds the right-hand sides, on exit the solutions."""

@@ -146,10 +146,14 @@ int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double 
  * Replaces NearToeplitzSolver(shape, coeffs) / .solve(x_d)
  * (code/cuda/solvers/templated/near_toeplitz.py:36-107; globalmem/near_toeplitz.py).
  * coeffs = [b1, c1, ai, bi, ci, an, bn]; solves, in place, every line of d[nz][ny][nx] along `axis`
- * (the reference solves along x only).
+ * (the reference solves along x only).  Any matrix with non-zero LU pivots is accepted: diagonally dominant
+ * ones (every compact scheme) run the one-pass streaming kernel, the rest an exact two-pass LU.
  * ------------------------------------------------------------------------------------------------- */
 int nt_create(nt_plan **plan, int nz, int ny, int nx, int axis, const double coeffs[7]);
 int nt_solve(nt_plan *plan, double *d, void *stream);
+/* 1 if the plan uses the exact two-pass LU (one launch per sweep, 32 B/unknown) because the matrix is not
+ * diagonally dominant enough for the one-pass kernel (pivots not converged by row 32, or |g|^32 > 1.2e-16). */
+int nt_is_exact_two_pass(const nt_plan *plan);
 void nt_destroy(nt_plan *plan);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -193,6 +193,29 @@ def test_near_toeplitz_general_coefficients(C):
     assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, co)) <= TOL
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("coeffs,tol", [((1., 2., 1. / 3, 1., 1. / 3, 2., 1.), 1e-12),      # 6th-order Pade: |g| = 0.38
+                                        ((3., 1., 1., 2.5, 1., 1., 3.), 1e-12),              # weakly dominant
+                                        ((1., 2., 3., 4., 5., 6., 7.), 1e-9)])               # not dominant at all
+def test_near_toeplitz_exact_two_pass(C, axis, coeffs, tol):
+    """Matrices the one-pass kernel refuses (slow decay / non-convergent pivots) go through the exact two-pass LU."""
+    rng = np.random.default_rng(axis)
+    shape = [6, 10, 40]
+    shape[2 - axis] = 200
+    d = rng.random(shape)
+    t = dev(d)
+    s = C.NearToeplitzSolver(shape, coeffs, axis=axis)
+    assert s.two_pass
+    s.solve(t)
+    want = O.near_toeplitz_solve(d, coeffs, axis)
+    assert relinf(t.cpu().numpy(), want) <= tol
+
+
+def test_one_pass_is_kept_for_pade(C):
+    assert not C.NearToeplitzSolver((4, 8, 512), O.PADE).two_pass
+    assert not C.NearToeplitzSolver((1, 1, 32), (1., 2., 3., 4., 5., 6., 7.)).two_pass     # <= 2 chunks: exact anyway
+
+
 def test_near_toeplitz_round_trip(C):
     """A x == d for the solved x (matrix applied with torch on the device), large batch."""
     import torch
