@@ -7,6 +7,7 @@ Drop-in for the derivative hot path of ashwinsrnth/compact-finite-differences:
     NearToeplitzSolver              code/cuda/solvers/templated/near_toeplitz.py:34-107
     ReducedSolver                   code/cuda/reduced.py:5-18
     ZPartitionedDerivative          the reference's multi-rank dfdx (compact.py:29-44) on a z-partition
+    HostGradient                    ndarray in / ndarrays out (code/ocl/compact.py:26-61), copies pipelined
 
 Python is a thin ctypes layer over libcfd_b200.so (hand-written sm_100a kernels); there is no CPU,
 PyTorch-eager or Triton path.  PyTorch is used for device memory, streams and torch.distributed only.
@@ -15,8 +16,9 @@ from ._lib import CfdError, lib  # noqa: F401
 from .compact import CompactFiniteDifferenceSolver  # noqa: F401
 from .near_toeplitz import NearToeplitzSolver  # noqa: F401
 from .reduced import ReducedSolver  # noqa: F401
+from .host import HostGradient  # noqa: F401
 from .partition import (ZPartitionedDerivative, exchange_halo_planes, exchange_interface_planes,  # noqa: F401
                         gather_interface_planes)
 
-__all__ = ["CompactFiniteDifferenceSolver", "NearToeplitzSolver", "ReducedSolver", "ZPartitionedDerivative",
+__all__ = ["CompactFiniteDifferenceSolver", "NearToeplitzSolver", "ReducedSolver", "ZPartitionedDerivative", "HostGradient",
            "exchange_halo_planes", "exchange_interface_planes", "gather_interface_planes", "CfdError", "lib"]

@@ -1,0 +1,94 @@
+"""
+HostGradient -- the OpenCL flavour's contract (host array in, host arrays out: code/ocl/compact.py:26-61
+`dfdx/dfdy/dfdz(f, d) -> ndarray`) for all three directions at once, with the host<->device copies pipelined
+against the kernels:
+
+    z-slab s of f:  H2D (copy stream)  ->  d/dx, d/dy of the slab (compute stream)  ->  D2H of both (copy-back stream)
+    after the last slab:                    d/dz of the whole field                 ->  D2H
+
+x and y lines never leave a z-slab, so their kernels start as soon as the first slab has landed and the
+device->host copies of the results overlap the remaining host->device copies (PCIe is full duplex).  Only the
+z derivative has to wait for the whole field.  All arithmetic runs in libcfd_b200's kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .compact import CompactFiniteDifferenceSolver
+
+
+class HostGradient:
+    def __init__(self, shape, spacings, slabs=8, device=None):
+        """
+        :param shape: (nz, ny, nx)
+        :param spacings: (dx, dy, dz)
+        :param slabs: number of z-slabs the transfers are pipelined in (nz is split as evenly as possible)
+        """
+        self.shape = tuple(int(s) for s in shape)
+        nz, ny, nx = self.shape
+        self.dx, self.dy, self.dz = (float(h) for h in spacings)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        slabs = max(1, min(int(slabs), nz))
+        cuts = [round(i * nz / slabs) for i in range(slabs + 1)]
+        self.slabs = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self._solvers = {}
+        for a, b in self.slabs:
+            if (b - a) not in self._solvers:
+                s = CompactFiniteDifferenceSolver((b - a, ny, nx))
+                self._solvers[b - a] = s
+        self._z = CompactFiniteDifferenceSolver(self.shape, self.dz, 2)
+        with torch.cuda.device(self.device):
+            self._f = torch.empty(self.shape, dtype=torch.float64, device=self.device)
+            self._d = [torch.empty(self.shape, dtype=torch.float64, device=self.device) for _ in range(3)]
+            self._s_in, self._s_comp, self._s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.h2d_bytes = self._f.numel() * 8
+        self.d2h_bytes = 3 * self._f.numel() * 8
+
+    @staticmethod
+    def _as_tensor(a):
+        if isinstance(a, np.ndarray):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+            return torch.from_numpy(a)
+        assert isinstance(a, torch.Tensor) and a.dtype == torch.float64 and not a.is_cuda and a.is_contiguous()
+        return a
+
+    def __call__(self, f_host, out=None):
+        """f_host: float64 host array/tensor [nz, ny, nx] (pinned memory gives full PCIe speed).
+        Returns (dfdx, dfdy, dfdz) as host tensors (pinned if allocated here, or `out` = three host buffers)."""
+        fh = self._as_tensor(f_host)
+        assert tuple(fh.shape) == self.shape
+        if out is None:
+            out = [torch.empty(self.shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+        oh = [self._as_tensor(o) for o in out]
+        s_in, s_comp, s_out = self._s_in, self._s_comp, self._s_out
+        cur = torch.cuda.current_stream(self.device)
+        for s in (s_in, s_comp, s_out):
+            s.wait_stream(cur)
+        f, d = self._f, self._d
+        for a, b in self.slabs:
+            with torch.cuda.stream(s_in):
+                f[a:b].copy_(fh[a:b], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_in)
+                sol = self._solvers[b - a]
+                sol.dfdx(f[a:b], self.dx, out=d[0][a:b])
+                sol.dfdy(f[a:b], self.dy, out=d[1][a:b])
+                ev_c = torch.cuda.Event()
+                ev_c.record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                oh[0][a:b].copy_(d[0][a:b], non_blocking=True)
+                oh[1][a:b].copy_(d[1][a:b], non_blocking=True)
+        with torch.cuda.stream(s_comp):
+            self._z(f, d[2])
+            ev_z = torch.cuda.Event()
+            ev_z.record(s_comp)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_z)
+            oh[2].copy_(d[2], non_blocking=True)
+        s_out.synchronize()
+        cur.wait_stream(s_out)
+        return tuple(out)

@@ -215,6 +215,23 @@ class ZPartitionedDerivative:
 
     def _exchange(self, f):
         """Steps (1)-(3) of the fused path; returns (halo_lo, halo_hi, alpha/beta planes) for the coupled kernel."""
+        if self.comm == "nvlink" and self._peer is None:
+            # symmetric memory is a torch-internal API: if it cannot be set up on this system, every rank falls
+            # back (collectively -- the outcome is agreed by all-reduce) to the NCCL send/recv exchange
+            nz, ny, nx = self.local_shape
+            ok = 1
+            try:
+                self._peer = PeerExchange(ny * nx, self.rank, self.size, self.group, f.device)
+            except Exception as e:                                   # pragma: no cover - depends on the box
+                import sys
+                print(f"[cfd_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
+                      file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=f.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if flag.item() == 0:
+                self._peer = None
+                self.comm = "pairwise"
         if self.comm == "nvlink":
             return self._exchange_nvlink(f)
         lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)

@@ -382,3 +382,21 @@ def test_peer_memory_protocol_one_device(C, P, shape):
             outs.append(out)
         got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
         assert relinf(got, want) <= TOL
+
+
+def test_host_gradient_pipeline(C):
+    """HostGradient (pinned host buffers, slab-pipelined copies) == oracle on every direction."""
+    import torch
+    rng = np.random.default_rng(21)
+    shape = (37, 48, 64)
+    f = rng.random(shape)
+    hs = (0.11, 0.07, 0.05)
+    hg = C.HostGradient(shape, hs, slabs=5)
+    fh = torch.from_numpy(f).pin_memory()
+    for _ in range(2):
+        dx, dy, dz = hg(fh)
+        for got, axis, h in ((dx, 0, hs[0]), (dy, 1, hs[1]), (dz, 2, hs[2])):
+            assert relinf(got.numpy(), O.derivative(f, axis, h)) <= TOL
+    outs = [np.empty(shape) for _ in range(3)]
+    hg(f, outs)                                   # NumPy in, NumPy out
+    assert relinf(outs[1], O.derivative(f, 1, hs[1])) <= TOL
