@@ -42,6 +42,7 @@ SIGNATURES = {
     "nt_is_exact_two_pass": (_i, [_vp]),
     "cfd_pthomas": (_i, [_dp, _dp, _dp, _vp, _i, _l, _vp]),
     "cfd_set_launch": (_i, [_i, _i, _i]),
+    "cfd_set_segments": (_i, [_i]),
     "cfd_launch_count": (_l, []),
 }
 

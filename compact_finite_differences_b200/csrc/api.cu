@@ -23,7 +23,7 @@ using namespace cfd;
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<long> g_launches{0};
-static int g_warps = 0, g_ctas = 0, g_slots = 0;
+static int g_warps = 0, g_ctas = 0, g_slots = 0, g_kseg = 0;
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -53,6 +53,13 @@ extern "C" int cfd_set_launch(int warps_per_cta, int ctas_per_sm, int ring_slots
     g_warps = warps_per_cta;
     g_ctas = ctas_per_sm;
     g_slots = ring_slots;
+    return CFD_OK;
+}
+
+extern "C" int cfd_set_segments(int chunks_per_segment)
+{
+    if (chunks_per_segment < 0) return fail(CFD_EINVAL, "chunks_per_segment must be >= 0 (0 = automatic)");
+    g_kseg = chunks_per_segment;
     return CFD_OK;
 }
 
@@ -185,20 +192,35 @@ static int counter_pair(unsigned long long **out)
 
 template <bool CONTIG, bool DERIV, int NSLOT>
 static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                            cudaStream_t stream)
+                            cudaStream_t stream, bool in_place)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
-    constexpr int per_warp = (NSLOT + 1) * SLOT_BYTES + NSLOT * 16;
+    constexpr int per_warp = (NSLOT + 2) * SLOT_BYTES + NSLOT * 16;
     // Measured on B200 at 512^3 (scripts/sweep_launch.py, profiles/r1_sweep_launch_512.txt): 4 warps per SM is
     // fastest for both layouts (x 0.337, y 0.333, z 0.341 ms); 5-7 warps cost 1-2 %, 3 warps 8-13 %.
-    // Shared memory (32 KiB per warp) caps a CTA at 7 warps.
-    const int max_warps = 7;
+    // Shared memory (40 KiB per warp: 3 ring slots + 2 staging slots) caps a CTA at 5 warps.
+    const int max_warps = 5;
     int warps = g_warps ? g_warps : 4;
     if (warps > max_warps) warps = max_warps;
     int ctas = g_ctas ? g_ctas : 1;
-    if (!g_warps) {   // small problems: spread the bundles over all SMs before stacking warps on one
-        const long per_sm = (g.nb + dinfo.sms - 1) / dinfo.sms;
+    // Long lines, few bundles (e.g. 1024 systems of 4096 unknowns = 32 bundles): cut the lines into segments of
+    // >= 8 chunks so that there are ~4 work items per warp; each cut costs two extra tiles of reads (look-ahead).
+    kp.kseg = g.K; kp.nseg = 1;
+    {
+        // In place (solver-only API) a segment's warm-up / look-ahead tiles belong to its neighbours' OUTPUT and
+        // may already have been overwritten: segmentation is for the out-of-place derivative only.
+        int kseg = in_place ? 0 : g_kseg;
+        if (!in_place && !kseg && g.K >= 16 && g.nb < 2L * dinfo.sms * warps) {
+            long want = (4L * dinfo.sms * warps + g.nb - 1) / g.nb;      // segments per line we would like
+            if (want > g.K / 8) want = g.K / 8;
+            if (want > 1) kseg = (int)((g.K + want - 1) / want);
+        }
+        if (kseg > 0 && kseg < g.K) { kp.kseg = kseg; kp.nseg = (g.K + kseg - 1) / kseg; }
+    }
+    const long nitems = g.nb * kp.nseg;
+    if (!g_warps) {   // small problems: spread the work items over all SMs before stacking warps on one
+        const long per_sm = (nitems + dinfo.sms - 1) / dinfo.sms;
         if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     }
     auto smem_for = [&](int w) { return (size_t)w * per_warp + 1024; };
@@ -213,7 +235,7 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
     }
     int rc = counter_pair(&kp.counter);
     if (rc) return rc;
-    long blocks = (g.nb + warps - 1) / warps;
+    long blocks = (nitems + warps - 1) / warps;
     const long cap = (long)dinfo.sms * ctas;
     if (blocks > cap) blocks = cap;
     kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, kp);
@@ -224,12 +246,12 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
 
 template <bool CONTIG, bool DERIV>
 static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                         cudaStream_t stream)
+                         cudaStream_t stream, bool in_place = false)
 {
     switch (g_slots ? g_slots : 3) {
-        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream);
-        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream);
-        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream);
+        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream, in_place);
+        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream, in_place);
+        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream, in_place);
         default: return fail(CFD_EINVAL, "ring slots must be 3, 4 or 5");
     }
 }
@@ -278,7 +300,7 @@ static int fill_tables(KParams &kp, const Geometry &g, const LineCoeffs &m, doub
                         m.ai, m.bi, m.ci, pv.decay);
     }
     memset(&kp, 0, sizeof kp);
-    kp.n = g.n; kp.K = g.K; kp.jl = g.jl;
+    kp.n = g.n; kp.K = g.K; kp.jl = g.jl; kp.kseg = g.K; kp.nseg = 1;
     kp.inner = (int)g.inner; kp.inner_tiles = g.inner_tiles; kp.outer = (int)g.outer;
     kp.nb = g.nb; kp.rows = g.nlines;
     kp.head = chunk_table(pv, g.n, 0, scale);
@@ -799,8 +821,8 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
         return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
     }
     KParams kp = p->kp;
-    if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
-    return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+    if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
+    return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
 }
 
 extern "C" void nt_destroy(nt_plan *p)

@@ -43,6 +43,7 @@ struct KParams {
     int n;             // rows per line
     int K;             // chunks per line = ceil(n / 32)
     int jl;            // position of row n-1 inside the last chunk
+    int kseg, nseg;    // line segmentation: chunks per segment, segments per line (nseg == 1: whole lines)
     int inner;         // STRIDED: extent of the contiguous dimension the lanes map to
     int inner_tiles;   // STRIDED: ceil(inner / 32)
     int outer;         // STRIDED: number of outer slices
@@ -118,6 +119,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src
 
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -280,14 +282,15 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
               const __grid_constant__ KParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int PER_WARP = (NS + 1) * SLOT_BYTES;     // ring + one result staging slot
+    constexpr int PER_WARP = (NS + 2) * SLOT_BYTES;     // ring + two result staging slots
     constexpr int CTRL = NS * 16;       // per warp: NS mbarriers + NS bundle tags
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     // 1 KiB alignment in the shared window (128B swizzle atom = 8 rows x 128 B)
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *wbase = base + warp * PER_WARP;
-    unsigned char *oslot = wbase + NS * SLOT_BYTES;
+    unsigned char *oslot = wbase + NS * SLOT_BYTES;      // staging slot in use; alternates with the one 8 KiB above/below
+    int ocur = 0;
     unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
     const uint32_t bar0 = smem_u32(ctrl);
     volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
@@ -302,20 +305,37 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
     }
     __syncwarp();
 
+    // A work item is (bundle, segment): output chunks [c0, c1) of the bundle's lines.  Its tile sequence runs
+    // from chunk max(c0-1, 0) -- a 32-row forward warm-up from a zero state, exact to 0.268^32 like the backward
+    // one -- to chunk min(c1, K-1), the look-ahead chunk of the last backward sweep.  With nseg == 1 an item is a
+    // whole bundle (the common case); long lines with few bundles are cut so that every warp finds work.
+    const int nseg = p.nseg, kseg = p.kseg;
+    const long nitems = nb * nseg;
+    auto item_range = [&](long w, long &bb, int &kb, int &ke, int &ko) {
+        if (nseg == 1) { bb = w; kb = 0; ke = K - 1; ko = 0; return; }     // whole lines: no 64-bit division
+        bb = w / nseg;
+        const int c0 = (int)(w % nseg) * kseg;
+        const int c1 = (c0 + kseg < K) ? c0 + kseg : K;
+        ko = c0;
+        kb = c0 > 0 ? c0 - 1 : 0;
+        ke = c1 < K ? c1 : K - 1;
+    };
+
     // ---- producer side (lane 0): one call per tile position, NS positions ahead of the consumer
-    long ib = 0;          // bundle being prefetched
-    int ik = 0;           // its next chunk
+    long iw = 0, ib = 0;  // item / bundle being prefetched
+    int ik = 1, ikend = 0, iko = 0;   // its next chunk, its last chunk
     int islot = 0;
     bool dry = false;
     auto issue = [&]() {
-        if (ik == 0 && !dry) {
-            ib = (long)atomicAdd(p.counter, 1ULL);
-            dry = ib >= nb;
+        if (ik > ikend && !dry) {
+            iw = (long)atomicAdd(p.counter, 1ULL);
+            dry = iw >= nitems;
+            if (!dry) item_range(iw, ib, ik, ikend, iko);
         }
         if (dry) {
             tag[islot] = -1;
         } else {
-            tag[islot] = ib;
+            tag[islot] = iw;
             const uint32_t bar = bar0 + 8 * islot;
             const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
             mbar_expect_tx(bar, SLOT_BYTES);
@@ -326,7 +346,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                 const int o = (int)(ib / p.inner_tiles), it = (int)(ib % p.inner_tiles);
                 tma_load_3d(dst, &tm_in, bar, it * CH, ik * CH, o);
             }
-            if (++ik == K) ik = 0;
+            ++ik;
         }
         if (++islot == NS) islot = 0;
     };
@@ -340,7 +360,8 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
     double eA[CH], eB[CH], F[CH];
     double eprev = 0.0, fm1 = 0.0, fm2 = 0.0, hval = 0.0, bval = 0.0;
     long b = 0;
-    int k = 0, slot = 0;
+    int k = 0, kbeg = 0, kend = 0, kout = 0, slot = 0;
+    bool fresh = true;            // the next tile opens a new work item
     uint32_t phase = 0;
     int oc0 = 0, oc2 = 0;         // STRIDED: first column / outer index of the bundle (TMA store coordinates)
 
@@ -373,9 +394,12 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
     };
 
     for (;;) {
-        if (k == 0) {
-            b = tag[slot];
-            if (b < 0) break;
+        if (fresh) {
+            const long w = tag[slot];
+            if (w < 0) break;
+            item_range(w, b, kbeg, kend, kout);
+            k = kbeg;
+            fresh = false;
             if constexpr (!CONTIG) {
                 oc2 = (int)(b / p.inner_tiles);
                 oc0 = (int)(b % p.inner_tiles) * CH;
@@ -393,9 +417,9 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         }
         const bool last = (k == K - 1);
         if constexpr (DERIV) {
-            if (last && (!p.lo_closure || !p.hi_closure)) {
-                const long nxt = tag[(slot + 1 == NS) ? 0 : slot + 1];     // the next tile opens the next bundle
-                if (nxt >= 0) prefetch_edge(nxt);
+            if (k == kend && (!p.lo_closure || !p.hi_closure)) {
+                const long nxt = tag[(slot + 1 == NS) ? 0 : slot + 1];     // the next tile opens the next item
+                if (nxt >= 0) prefetch_edge(nseg == 1 ? nxt : nxt / nseg);
             }
         }
         const unsigned char *st = wbase + slot * SLOT_BYTES;
@@ -403,7 +427,7 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         load_chunk<CONTIG>(st, lane, F);
         double peek = 0.0;
         if constexpr (DERIV) {
-            if (!last) {
+            if (k < kend) {               // the item's next tile is in the ring: peek at its first row
                 const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
                 const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;
                 mbar_wait(bar0 + 8 * s1, ph1);
@@ -432,9 +456,11 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                 }
                 tma_commit();
             }
+            ocur ^= 1;                   // next result tile goes to the other staging slot
+            oslot = wbase + (NS + ocur) * SLOT_BYTES;
         };
-        auto acquire_out = [&]() {       // the previous store must have drained the staging slot
-            if (lane == 0) tma_wait_read0();
+        auto acquire_out = [&]() {       // the store issued from THIS slot two tiles ago must have drained it;
+            if (lane == 0) tma_wait_read1();   // the most recent one (other slot) may still be in flight
             __syncwarp();
         };
         double x = 0.0;
@@ -443,23 +469,25 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
             if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane);
             else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane);
             flush(k);
-            if (k > 0) {
+            if (k > kbeg && k - 1 >= kout) {
                 acquire_out();
                 if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
                 else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
                 flush(k - 1);
             }
-        } else if (k > 0) {
+        } else if (k > kbeg) {
             bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane);   // 32-row warm-up
-            acquire_out();
-            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
-            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
-            flush(k - 1);
+            if (k - 1 >= kout) {                                  // (chunk kbeg of a later segment is warm-up only)
+                acquire_out();
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
+                flush(k - 1);
+            }
         }
 #pragma unroll
         for (int j = 0; j < CH; j++) eA[j] = eB[j];
 
-        if (++k == K) k = 0;
+        if (k == kend) fresh = true; else ++k;
         if (++slot == NS) { slot = 0; phase ^= 1u; }
     }
     if (lane == 0) {

@@ -166,6 +166,9 @@ int cfd_pthomas(const double *a, const double *b, const double *c, double *d, in
 
 /* Tuning knobs for experiments (0 = built-in default).  Not part of the reference surface. */
 int cfd_set_launch(int warps_per_cta, int ctas_per_sm, int ring_slots);
+/* Line segmentation of the streaming kernel: 32-row chunks per work item (0 = automatic: whole lines unless there
+ * are fewer bundles than warps and lines of >= 512 rows).  Any value is exact to fp64 (32-row warm-ups). */
+int cfd_set_segments(int chunks_per_segment);
 
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 long cfd_launch_count(void);

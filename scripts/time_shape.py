@@ -6,6 +6,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import compact_finite_differences_b200 as C
 
+if os.environ.get("CFD_KSEG"):
+    C.lib().cfd_set_segments(int(os.environ["CFD_KSEG"]))
 shapes = []
 args = [int(a) for a in sys.argv[1:]]
 while len(args) >= 3:

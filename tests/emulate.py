@@ -26,7 +26,7 @@ def tables(n, coeffs, scale):
 
 
 def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=None, halo_hi=None,
-                 alpha=None, beta=None):
+                 alpha=None, beta=None, kseg=None):
     """
     F: [nlines, n] (each row one line).  h given -> derivative (Pade RHS fused), else plain solve of F.
     Follows the kernel step by step: per chunk forward elimination with HEAD / MID / TAIL coefficients,
@@ -48,17 +48,22 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
         T["head"]["l"][0] = coeffs[2] * T["beta0"]                  # a_i * beta_0, as cfd_create does
     snb = T["betan"] * coeffs[4] if (coupled and not hi_closure) else 0.0
     bval = np.asarray(beta, dtype=np.float64) if coupled else np.zeros(nl)
-    eprev = np.asarray(alpha, dtype=np.float64).copy() if (coupled and not lo_closure) else np.zeros(nl)
-    fm1 = np.zeros(nl) if (lo_closure or not deriv) else np.asarray(halo_lo, dtype=np.float64).copy()
-    fm2 = np.zeros(nl)
+    state = {}
+
+    def reset_state():
+        state["eprev"] = np.asarray(alpha, dtype=np.float64).copy() if (coupled and not lo_closure) else np.zeros(nl)
+        state["fm1"] = np.zeros(nl) if (lo_closure or not deriv) else np.asarray(halo_lo, dtype=np.float64).copy()
+        state["fm2"] = np.zeros(nl)
+
+    reset_state()
     hval = np.zeros(nl) if (hi_closure or not deriv) else np.asarray(halo_hi, dtype=np.float64)
     eA = None
 
-    def fwd(k):
-        nonlocal eprev, fm1, fm2
+    def fwd(k, kend):
+        eprev, fm1, fm2 = state["eprev"], state["fm1"], state["fm2"]
         Fc = Fp[:, k * CH:(k + 1) * CH]
         last = (k == K - 1)
-        peek = np.zeros(nl) if last else Fp[:, (k + 1) * CH]
+        peek = Fp[:, (k + 1) * CH] if k < kend else np.zeros(nl)     # the item's next tile, if it has one
         e = np.zeros((nl, CH))
         mode = 1 if k == 0 else (2 if last else 0)
         tab = T["head"] if mode == 1 else T["tail"]
@@ -89,6 +94,7 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
                     r = tab["sk"][j] * Fc[:, j]
                 eprev = -tab["l"][j] * eprev + r
             e[:, j] = eprev
+        state["eprev"], state["fm1"], state["fm2"] = eprev, fm1, fm2
         return e
 
     def bwd(e, x, mode, k_out):
@@ -100,18 +106,27 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
                 out[:, k_out * CH + j] = x
         return x
 
-    for k in range(K):
-        eB = fwd(k)
-        last = (k == K - 1)
-        x = np.zeros(nl)
-        if last:
-            x = bwd(eB, x, 1 if k == 0 else 2, k)
-            if k > 0:
-                x = bwd(eA, x, 1 if k == 1 else 0, k - 1)
-        elif k > 0:
-            x = bwd(eB, x, 0, None)
-            x = bwd(eA, x, 1 if k == 1 else 0, k - 1)
-        eA = eB
+    kseg = K if not kseg else min(int(kseg), K)
+    nseg = (K + kseg - 1) // kseg
+    for seg in range(nseg):                       # work items of one bundle (kernel: item_range)
+        c0 = seg * kseg
+        c1 = min(c0 + kseg, K)
+        kbeg, kend, kout = max(c0 - 1, 0), min(c1, K - 1), c0
+        reset_state()
+        eA = None
+        for k in range(kbeg, kend + 1):
+            eB = fwd(k, kend)
+            last = (k == K - 1)
+            x = np.zeros(nl)
+            if last:
+                x = bwd(eB, x, 1 if k == 0 else 2, k)
+                if k > kbeg and k - 1 >= kout:
+                    x = bwd(eA, x, 1 if k == 1 else 0, k - 1)
+            elif k > kbeg:
+                x = bwd(eB, x, 0, None)
+                if k - 1 >= kout:
+                    x = bwd(eA, x, 1 if k == 1 else 0, k - 1)
+            eA = eB
     return out[:, :n]
 
 

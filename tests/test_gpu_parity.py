@@ -400,3 +400,35 @@ def test_host_gradient_pipeline(C):
     outs = [np.empty(shape) for _ in range(3)]
     hg(f, outs)                                   # NumPy in, NumPy out
     assert relinf(outs[1], O.derivative(f, 1, hs[1])) <= TOL
+
+
+@pytest.mark.parametrize("kseg", [1, 2, 8])
+def test_segmented_lines(C, kseg):
+    """Forced line segmentation (cfd_set_segments): every axis, derivative and solver, ragged sizes."""
+    rng = np.random.default_rng(kseg)
+    try:
+        C.lib().cfd_set_segments(kseg)
+        for shape in [(6, 10, 400), (300, 6, 34), (5, 530, 36)]:
+            f = rng.random(shape)
+            for axis in range(3):
+                if shape[2 - axis] < 4:
+                    continue
+                got = C.CompactFiniteDifferenceSolver(shape, 0.3, axis)(dev(f)).cpu().numpy()
+                assert relinf(got, O.derivative(f, axis, 0.3)) <= TOL
+                t = dev(f)
+                C.NearToeplitzSolver(shape, O.PADE, axis=axis).solve(t)
+                assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(f, O.PADE, axis)) <= TOL
+    finally:
+        C.lib().cfd_set_segments(0)
+
+
+def test_auto_segmentation_small_batch(C):
+    """32 bundles of 4096-long lines: the launcher cuts the lines automatically (out-of-place derivative only; the
+    in-place solver keeps whole lines); results unchanged."""
+    rng = np.random.default_rng(5)
+    d = rng.random((1, 1024, 4096))
+    t = dev(d)
+    C.NearToeplitzSolver(d.shape, O.PADE).solve(t)
+    assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, O.PADE)) <= TOL
+    got = C.CompactFiniteDifferenceSolver(d.shape, 0.2, 0)(dev(d)).cpu().numpy()
+    assert relinf(got, O.derivative(d, 0, 0.2)) <= TOL

@@ -176,3 +176,18 @@ def test_neighbour_only_reduced_system(n, size):
         fv[-1] = 0.0
         sol = O.scipy_solve_banded(va[:2 * pv], vb[:2 * pv], vc[:2 * pv], fv)
         np.testing.assert_allclose(sol[2 * own:2 * own + 2], full[2 * r:2 * r + 2], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("n,kseg", [(200, 2), (256, 1), (512, 8), (1000, 8), (4096, 16), (97, 1), (64, 1)])
+def test_segmented_schedule(n, kseg):
+    """Lines cut into segments (work items of the streaming kernel for long lines / few bundles): a 32-row forward
+    warm-up before and the usual look-ahead chunk after every cut keep the result exact to fp64."""
+    rng = np.random.default_rng(n + kseg)
+    F = rng.random((3, n))
+    h = 0.4
+    want = O.derivative(F.reshape(1, 3, n), 0, h).reshape(3, n)
+    got = stream_lines(F, PADE, h, kseg=kseg)
+    assert not np.isnan(got).any()
+    assert relinf(got, want) < 1e-14
+    want2 = O.near_toeplitz_solve(F.reshape(1, 3, n), PADE).reshape(3, n)
+    assert relinf(stream_lines(F, PADE, kseg=kseg), want2) < 1e-14
