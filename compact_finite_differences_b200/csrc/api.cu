@@ -284,6 +284,10 @@ struct nt_plan {
     MapCache cache;
     bool exact = false;               // two-pass exact solver (matrix refused by the one-pass kernel)
     double *d_tab = nullptr;          // [4][K*32]: forward pc, qc; backward pc, qc
+    // Starved shape (long lines, fewer bundles than warps): the lines are cut into segments, which is only safe
+    // out of place -- solve into this scratch field, then copy it back over d (both tiny by definition).
+    double *d_scratch = nullptr;
+    MapCache scratch_cache;
 };
 
 #define CFD_ESLOWPATH (-100)   /* internal: matrix needs the exact two-pass solver */
@@ -796,6 +800,11 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
     }
     if (rc) { delete p; return rc; }
     p->kp.lo_closure = 1; p->kp.hi_closure = 1;
+    // (measured, scripts/sweep_solver.py: the detour pays below ~256 bundles; at 512 the plain in-place kernel wins)
+    if (!p->exact && p->g.K >= 16 && p->g.nb <= 256) {
+        const size_t bytes = (size_t)p->g.nlines * p->g.n * sizeof(double);
+        if (cudaMalloc(&p->d_scratch, bytes) != cudaSuccess) { cudaGetLastError(); p->d_scratch = nullptr; }
+    }
     *out = p;
     return CFD_OK;
 }
@@ -821,6 +830,18 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
         return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
     }
     KParams kp = p->kp;
+    if (p->d_scratch) {
+        rc = get_maps(p->scratch_cache, p->g, d, p->d_scratch);
+        if (rc) return rc;
+        rc = p->g.contig ? launch_stream<true, false>(p->g, kp, p->scratch_cache.tm_in, p->scratch_cache.tm_out,
+                                                      (cudaStream_t)stream, false)
+                         : launch_stream<false, false>(p->g, kp, p->scratch_cache.tm_in, p->scratch_cache.tm_out,
+                                                       (cudaStream_t)stream, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d, p->d_scratch, (size_t)p->g.nlines * p->g.n * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return CFD_OK;
+    }
     if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
     return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
 }
@@ -829,6 +850,7 @@ extern "C" void nt_destroy(nt_plan *p)
 {
     if (!p) return;
     cudaFree(p->d_tab);
+    cudaFree(p->d_scratch);
     delete p;
 }
 
