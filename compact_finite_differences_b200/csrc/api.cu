@@ -175,18 +175,29 @@ static int device_info(DeviceInfo &d)
 // Work counters: a ring of {next bundle, finished warps} pairs, one pair per in-flight launch.
 // Each kernel leaves its pair zeroed, so re-use after COUNTER_RING launches needs no memset.
 constexpr int COUNTER_RING = 4096;
-static unsigned long long *g_counters = nullptr;
+constexpr int MAX_DEVICES = 64;
+static unsigned long long *g_counters[MAX_DEVICES] = {nullptr};     // one ring per device of this process
 static std::atomic<unsigned long> g_launch_seq{0};
+
+static int current_device(int &dev)
+{
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(CFD_EUNSUPPORTED, "device ordinal %d out of range", dev);
+    return CFD_OK;
+}
 
 static int counter_pair(unsigned long long **out)
 {
-    if (!g_counters) {
+    int dev = 0;
+    int rc = current_device(dev);
+    if (rc) return rc;
+    if (!g_counters[dev]) {
         unsigned long long *p = nullptr;
         CUDA_TRY(cudaMalloc(&p, sizeof(unsigned long long) * 2 * COUNTER_RING));
         CUDA_TRY(cudaMemset(p, 0, sizeof(unsigned long long) * 2 * COUNTER_RING));
-        g_counters = p;
+        g_counters[dev] = p;
     }
-    *out = g_counters + 2 * (g_launch_seq++ % COUNTER_RING);
+    *out = g_counters[dev] + 2 * (g_launch_seq++ % COUNTER_RING);
     return CFD_OK;
 }
 
@@ -228,10 +239,12 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
     const size_t smem = smem_for(warps);
     if (smem > 232448) return fail(CFD_EUNSUPPORTED, "ring of %d slots does not fit shared memory", NSLOT);
     auto kern = stream_kernel<CONTIG, DERIV, NSLOT>;
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[MAX_DEVICES] = {0};
+    int dev = 0;
+    { int rc = current_device(dev); if (rc) return rc; }
+    if (configured[dev] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev] = smem;
     }
     int rc = counter_pair(&kp.counter);
     if (rc) return rc;
@@ -453,7 +466,7 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     p->kp.snc *= 1.0 / (2.0 * h);
 
     if (part_size > 1) {
-        const int n = p->g.n, P = part_size, mm = 2 * P;
+        const int n = p->g.n, P = part_size;
         secondary_systems(n, part_rank, P, p->x_uh, p->x_lh);
         reduced_matrix(n, P, p->ra, p->rb, p->rc);
         p->lu = elimination_table(p->ra, p->rb, p->rc);
@@ -746,10 +759,12 @@ static int launch_recurrence(const Geometry &g, const double *pc, const double *
     if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     const size_t smem = (size_t)warps * per_warp + 1024;
     auto kern = recurrence_kernel<CONTIG, REVERSE>;
-    static size_t configured = 0;
-    if (configured < smem) {
+    static size_t configured[MAX_DEVICES] = {0};
+    int dev = 0;
+    { int rc = current_device(dev); if (rc) return rc; }
+    if (configured[dev] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * per_warp + 1024));
-        configured = 4 * per_warp + 1024;
+        configured[dev] = 4 * per_warp + 1024;
     }
     RParams rp;
     rp.K = g.K; rp.inner_tiles = g.inner_tiles; rp.nb = g.nb; rp.pc = pc; rp.qc = qc;

@@ -432,3 +432,35 @@ def test_auto_segmentation_small_batch(C):
     assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, O.PADE)) <= TOL
     got = C.CompactFiniteDifferenceSolver(d.shape, 0.2, 0)(dev(d)).cpu().numpy()
     assert relinf(got, O.derivative(d, 0, 0.2)) <= TOL
+
+
+def test_very_long_lines(C):
+    """n = 16384 (512 chunks per line; the reference caps nx at 2048): derivative and solver vs the oracle."""
+    rng = np.random.default_rng(16384)
+    f = rng.random((2, 40, 16384))
+    got = C.CompactFiniteDifferenceSolver(f.shape, 0.01, 0)(dev(f)).cpu().numpy()
+    assert relinf(got, O.derivative(f, 0, 0.01)) <= TOL
+    t = dev(f)
+    C.NearToeplitzSolver(f.shape, O.PADE).solve(t)
+    assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(f, O.PADE)) <= TOL
+    g = np.ascontiguousarray(f.transpose(2, 1, 0))            # the same lines along z
+    got = C.CompactFiniteDifferenceSolver(g.shape, 0.01, 2)(dev(g)).cpu().numpy()
+    assert relinf(got, O.derivative(g, 2, 0.01)) <= TOL
+
+
+def test_maximum_size_round_trip(C):
+    """2^30 unknowns (8 GiB, the cap of BASELINE configs[4]): A x == d in place, checked on the device."""
+    import torch
+    n, batch = 1024, 2 ** 20
+    d = torch.rand((1, batch, n), dtype=torch.float64, device="cuda")
+    chk = d[0, ::4099].clone()                                 # keep a sample of the right-hand sides
+    C.NearToeplitzSolver((1, batch, n), O.PADE).solve(d)
+    x = d[0, ::4099]
+    ax = x.clone()
+    ax[:, 1:-1] = 0.25 * x[:, :-2] + x[:, 1:-1] + 0.25 * x[:, 2:]
+    ax[:, 0] = x[:, 0] + 2 * x[:, 1]
+    ax[:, -1] = 2 * x[:, -2] + x[:, -1]
+    assert (ax - chk).abs().max().item() < 1e-13
+    lines = x[:8].cpu().numpy()
+    want = O.near_toeplitz_solve(chk[:8].cpu().numpy().reshape(1, 8, n), O.PADE).reshape(8, n)
+    assert relinf(lines, want) <= TOL
