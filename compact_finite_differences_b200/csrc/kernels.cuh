@@ -197,9 +197,12 @@ __device__ __forceinline__ double load_first(const unsigned char *slot, int lane
 //   DERIV: r_i is the Pade stencil of f (code/cuda/kernels.cu:34-44), else r_i = tile value.
 // State carried along the line: eprev = e_{i-1}, fm1 = f_{i-1}, fm2 = f_{i-2}.
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool DERIV>
+//   TAILPOS: where row n-1 sits in this chunk, resolved at compile time when possible so that the common
+//   shapes pay no per-row selects: -1 = not in this chunk, 31 = last row of the chunk (n a multiple of 32),
+//   -2 = anywhere (run-time p.jl; ragged n, or a one-chunk line).
+template <int MODE, bool DERIV, int TAILPOS>
 __device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH], double peek, double hval, double bval,
-                                          bool is_last, double (&e)[CH], double &eprev, double &fm1, double &fm2)
+                                          double (&e)[CH], double &eprev, double &fm1, double &fm2)
 {
     if constexpr (MODE == 0) {
         const double sk = p.sk_mid, nl = -p.l_mid;
@@ -219,17 +222,20 @@ __device__ __forceinline__ void fwd_chunk(const KParams &p, const double (&F)[CH
         if constexpr (DERIV) fm2 = F[CH - 2];
     } else {
         const RowTab &T = (MODE == 1) ? p.head : p.tail;
-        const int jl = is_last ? p.jl : -1;
+        const int jl = (TAILPOS == -2) ? p.jl : TAILPOS;
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             double r;
             if constexpr (DERIV) {
+                const bool at_end = (TAILPOS == -2) ? (j == jl) : (j == TAILPOS);
                 double nxt = (j < CH - 1) ? F[j + 1] : peek;
-                if (j == jl && !p.hi_closure) nxt = hval;
+                if (at_end && !p.hi_closure) nxt = hval;
                 r = T.sk[j] * (nxt - fm1);
                 if (MODE == 1 && j == 0 && p.lo_closure) r = p.s0c * (-5.0 * F[0] + 4.0 * F[1] + F[2]);
-                if (j == jl && p.hi_closure) r = p.snc * (5.0 * F[j] - 4.0 * fm1 - fm2);
-                if (j == jl && !p.hi_closure) r = fma(-p.snb, bval, r);      // coupled: - beta_{n-1} c x_n
+                if (at_end) {
+                    if (p.hi_closure) r = p.snc * (5.0 * F[j] - 4.0 * fm1 - fm2);
+                    else              r = fma(-p.snb, bval, r);      // coupled: - beta_{n-1} c x_n
+                }
                 fm2 = fm1;
                 fm1 = F[j];
             } else {
@@ -434,9 +440,15 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
                 peek = load_first<CONTIG>(wbase + s1 * SLOT_BYTES, lane);
             }
         }
-        if (k == 0)    fwd_chunk<1, DERIV>(p, F, peek, hval, bval, last, eB, eprev, fm1, fm2);
-        else if (last) fwd_chunk<2, DERIV>(p, F, peek, hval, bval, true, eB, eprev, fm1, fm2);
-        else           fwd_chunk<0, DERIV>(p, F, peek, hval, bval, false, eB, eprev, fm1, fm2);
+        if (k == 0) {
+            if (last) fwd_chunk<1, DERIV, -2>(p, F, peek, hval, bval, eB, eprev, fm1, fm2);     // one-chunk line
+            else      fwd_chunk<1, DERIV, -1>(p, F, peek, hval, bval, eB, eprev, fm1, fm2);
+        } else if (last) {
+            if (p.jl == CH - 1) fwd_chunk<2, DERIV, CH - 1>(p, F, peek, hval, bval, eB, eprev, fm1, fm2);
+            else                fwd_chunk<2, DERIV, -2>(p, F, peek, hval, bval, eB, eprev, fm1, fm2);
+        } else {
+            fwd_chunk<0, DERIV, -1>(p, F, peek, hval, bval, eB, eprev, fm1, fm2);
+        }
 
         // the slot has been consumed into registers: refill it (tile position t + NS)
         __syncwarp();
