@@ -11,8 +11,8 @@
 //    them in chunks of CH = 32 rows.  Tiles of 32 rows x 32 lines x 8 B = 8 KiB arrive through
 //    TMA (cp.async.bulk.tensor) into a private 3-slot shared-memory ring guarded by the warp's own
 //    mbarriers; no CTA-wide barrier exists anywhere, so warps drift freely and hide each other's
-//    latencies.  Warps are persistent: the flat tile sequence (bundle, chunk) is prefetched NS
-//    tiles ahead, across bundle boundaries.
+//    latencies.  Warps are persistent and draw their bundles from a global counter; the flat tile
+//    sequence (bundle, chunk) is prefetched NS tiles ahead, across bundle boundaries.
 //  * LU WITH CONSTANT PIVOTS + LOOK-AHEAD BACK-SUBSTITUTION.  The forward elimination
 //    e_i = s*r_i - l*e_{i-1} is carried exactly along the whole line in registers.  The backward
 //    sweep x_i = e_i - g*x_{i+1} of chunk k-1 is started one chunk to the right, at the end of
@@ -133,9 +133,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-
-__device__ __forceinline__ void st_stream(double *p, double v)
-{ asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // Reduced (interface) system of one line, solved for this rank's two unknowns only:
