@@ -42,7 +42,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML, 10 ms period; nvidia-smi query
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, 2 ms period; nvidia-smi query
     of the same fields as a fallback -- B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -99,7 +99,7 @@ class ClockSampler:
                 self.n += 1
             except Exception:
                 pass
-            self._stop.wait(0.01 if self._nvml else 0.1)
+            self._stop.wait(0.002 if self._nvml else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
