@@ -464,3 +464,59 @@ def test_maximum_size_round_trip(C):
     lines = x[:8].cpu().numpy()
     want = O.near_toeplitz_solve(chk[:8].cpu().numpy().reshape(1, 8, n), O.PADE).reshape(8, n)
     assert relinf(lines, want) <= TOL
+
+
+def test_reentrant_on_two_streams(C):
+    """Plans are immutable and every launch takes its own work-counter pair: concurrent calls on distinct streams
+    (same plan, different fields) must not disturb each other."""
+    import torch
+    rng = np.random.default_rng(77)
+    shape = (96, 128, 160)
+    fa, fb = rng.random(shape), rng.random(shape)
+    da, db = dev(fa), dev(fb)
+    oa, ob = torch.empty_like(da), torch.empty_like(db)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for axis in range(3):
+        op = C.CompactFiniteDifferenceSolver(shape, 0.1, axis)
+        op2 = C.CompactFiniteDifferenceSolver(shape, 0.1, axis)
+        for _ in range(5):
+            with torch.cuda.stream(s1):
+                op(da, oa)
+            with torch.cuda.stream(s2):
+                op2(db, ob)
+        torch.cuda.synchronize()
+        assert relinf(oa.cpu().numpy(), O.derivative(fa, axis, 0.1)) <= TOL
+        assert relinf(ob.cpu().numpy(), O.derivative(fb, axis, 0.1)) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 4), (1, 1, 4), (2, 5, 6), (1, 4, 2), (4, 1, 2)])
+def test_tiny_shapes(C, shape):
+    rng = np.random.default_rng(sum(shape))
+    f = rng.random(shape)
+    for axis in range(3):
+        if shape[2 - axis] < 4:
+            continue
+        got = C.CompactFiniteDifferenceSolver(shape, 0.5, axis)(dev(f)).cpu().numpy()
+        assert relinf(got, O.derivative(f, axis, 0.5)) <= TOL
+
+
+def test_error_codes(C):
+    """Shape / argument errors come back as exceptions carrying the C error text, never as a crash."""
+    import torch
+    with pytest.raises(C.CfdError):
+        C.CompactFiniteDifferenceSolver((8, 8, 7), 0.1, 0)            # nx odd
+    with pytest.raises(C.CfdError):
+        C.CompactFiniteDifferenceSolver((8, 8, 8), -1.0, 0)           # spacing
+    with pytest.raises(C.CfdError):
+        C.CompactFiniteDifferenceSolver((2, 8, 8), 0.1, 2)            # fewer than 3 rows along the axis
+    with pytest.raises(C.CfdError):
+        C.CompactFiniteDifferenceSolver((3, 8, 8), 0.1, 2)            # the 3-row closure matrix is singular
+    with pytest.raises(C.CfdError):
+        C.NearToeplitzSolver((4, 4, 8), (0., 1., 1., 1., 1., 1., 1.))  # zero pivot
+    s = C.CompactFiniteDifferenceSolver((8, 8, 8), 0.1, 0)
+    f = torch.zeros((8, 8, 8), dtype=torch.float64, device="cuda")
+    with pytest.raises(AssertionError):
+        s(f, out=f)                                                   # in-place derivative
+    with pytest.raises(AssertionError):
+        s(f.float())
