@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -191,6 +192,8 @@ static int counter_pair(unsigned long long **out)
     int dev = 0;
     int rc = current_device(dev);
     if (rc) return rc;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     if (!g_counters[dev]) {
         unsigned long long *p = nullptr;
         CUDA_TRY(cudaMalloc(&p, sizeof(unsigned long long) * 2 * COUNTER_RING));
@@ -272,7 +275,10 @@ static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap
 // ------------------------------------------------------------------------------------------------
 // plans
 // ------------------------------------------------------------------------------------------------
-struct MapCache { const void *in = nullptr, *out = nullptr; CUtensorMap tm_in, tm_out; };
+// Last encoded descriptor pair of a plan.  Guarded by a mutex and handed out BY VALUE, so concurrent calls on one
+// plan from several host threads (distinct streams, distinct fields) never see a half-updated descriptor.
+struct MapCache { std::mutex mu; const void *in = nullptr, *out = nullptr; CUtensorMap tm_in, tm_out; };
+struct MapPair { CUtensorMap tm_in, tm_out; };
 
 struct cfd_plan {
     Geometry g;
@@ -553,12 +559,15 @@ extern "C" int cfd_debug_tables(int n, const double coeffs[7], double scale, dou
     return CFD_OK;
 }
 
-static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *out)
+static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *out, MapPair &m)
 {
-    if (c.in == in && c.out == out) return CFD_OK;
-    int rc = encode_maps(g, in, out, &c.tm_in, &c.tm_out);
-    if (rc) { c.in = c.out = nullptr; return rc; }
-    c.in = in; c.out = out;
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (!(c.in == in && c.out == out)) {
+        int rc = encode_maps(g, in, out, &c.tm_in, &c.tm_out);
+        if (rc) { c.in = c.out = nullptr; return rc; }
+        c.in = in; c.out = out;
+    }
+    m.tm_in = c.tm_in; m.tm_out = c.tm_out;
     return CFD_OK;
 }
 
@@ -569,13 +578,14 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
     if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
     if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
-    int rc = get_maps(p->cache, p->g, f, df);
+    MapPair mp;
+    int rc = get_maps(p->cache, p->g, f, df, mp);
     if (rc) return rc;
     KParams kp = p->kp;
     kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
     kp.ab = ab; kp.nlines = p->g.nlines;
-    if (p->g.contig) return launch_stream<true, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
-    return launch_stream<false, true>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream);
+    if (p->g.contig) return launch_stream<true, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream);
+    return launch_stream<false, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream);
 }
 
 extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
@@ -829,36 +839,38 @@ extern "C" int nt_is_exact_two_pass(const nt_plan *p) { return p ? (p->exact ? 1
 extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
 {
     if (!p || !d) return fail(CFD_EINVAL, "NULL argument");
-    int rc = get_maps(p->cache, p->g, d, d);
+    MapPair mp;
+    int rc = get_maps(p->cache, p->g, d, d, mp);
     if (rc) return rc;
     if (p->exact) {
         const long L = (long)p->g.K * CH;
         const double *t = p->d_tab;
         cudaStream_t st = (cudaStream_t)stream;
         if (p->g.contig) {
-            rc = launch_recurrence<true, false>(p->g, t, t + L, p->cache.tm_in, p->cache.tm_out, st);
+            rc = launch_recurrence<true, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st);
             if (rc) return rc;
-            return launch_recurrence<true, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
+            return launch_recurrence<true, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st);
         }
-        rc = launch_recurrence<false, false>(p->g, t, t + L, p->cache.tm_in, p->cache.tm_out, st);
+        rc = launch_recurrence<false, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st);
         if (rc) return rc;
-        return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, p->cache.tm_in, p->cache.tm_out, st);
+        return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st);
     }
     KParams kp = p->kp;
     if (p->d_scratch) {
-        rc = get_maps(p->scratch_cache, p->g, d, p->d_scratch);
+        MapPair ms;
+        rc = get_maps(p->scratch_cache, p->g, d, p->d_scratch, ms);
         if (rc) return rc;
-        rc = p->g.contig ? launch_stream<true, false>(p->g, kp, p->scratch_cache.tm_in, p->scratch_cache.tm_out,
+        rc = p->g.contig ? launch_stream<true, false>(p->g, kp, ms.tm_in, ms.tm_out,
                                                       (cudaStream_t)stream, false)
-                         : launch_stream<false, false>(p->g, kp, p->scratch_cache.tm_in, p->scratch_cache.tm_out,
+                         : launch_stream<false, false>(p->g, kp, ms.tm_in, ms.tm_out,
                                                        (cudaStream_t)stream, false);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d, p->d_scratch, (size_t)p->g.nlines * p->g.n * sizeof(double),
                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return CFD_OK;
     }
-    if (p->g.contig) return launch_stream<true, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
-    return launch_stream<false, false>(p->g, kp, p->cache.tm_in, p->cache.tm_out, (cudaStream_t)stream, true);
+    if (p->g.contig) return launch_stream<true, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, true);
+    return launch_stream<false, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, true);
 }
 
 extern "C" void nt_destroy(nt_plan *p)
