@@ -13,12 +13,12 @@ Python is a thin ctypes layer over libcfd_b200.so (hand-written sm_100a kernels)
 PyTorch-eager or Triton path.  PyTorch is used for device memory, streams and torch.distributed only.
 """
 from ._lib import CfdError, lib  # noqa: F401
-from .compact import CompactFiniteDifferenceSolver  # noqa: F401
+from .compact import CompactFiniteDifferenceSolver, LineDA  # noqa: F401
 from .near_toeplitz import NearToeplitzSolver  # noqa: F401
 from .reduced import ReducedSolver  # noqa: F401
 from .host import HostGradient  # noqa: F401
 from .partition import (ZPartitionedDerivative, exchange_halo_planes, exchange_interface_planes,  # noqa: F401
                         gather_interface_planes)
 
-__all__ = ["CompactFiniteDifferenceSolver", "NearToeplitzSolver", "ReducedSolver", "ZPartitionedDerivative", "HostGradient",
+__all__ = ["CompactFiniteDifferenceSolver", "LineDA", "NearToeplitzSolver", "ReducedSolver", "ZPartitionedDerivative", "HostGradient",
            "exchange_halo_planes", "exchange_interface_planes", "gather_interface_planes", "CfdError", "lib"]

@@ -48,15 +48,36 @@ class _Plan:
             self.handle = None
 
 
+class LineDA:
+    """The handful of attributes of the reference's line distributed-array object that the derivative operator
+    reads (code/cuda/gpuDA.py:154-180 `get_line_DA`; used at code/cuda/compact.py:49,159-166): local block shape and
+    the position of the block along the derivative line."""
+
+    def __init__(self, local_dims, rank=0, size=1, direction=0):
+        self.nz, self.ny, self.nx = (int(s) for s in local_dims)
+        self.rank, self.size, self.direction = int(rank), int(size), int(direction)
+        self.mx, self.npx = self.rank, self.size            # names used by the reference kernels (kernels.cu:36,42)
+
+
 class CompactFiniteDifferenceSolver:
-    def __init__(self, shape, spacing=None, direction=None, part=(0, 1)):
+    def __init__(self, shape, spacing=None, direction=None, part=(0, 1), solver=None):
         """
+        Reference spelling: ``CompactFiniteDifferenceSolver(line_da, solver='templated')`` (code/cuda/compact.py:18)
+        with any object carrying ``nz, ny, nx, rank, size`` (e.g. :class:`LineDA`); `solver` is accepted and
+        ignored (there is one kernel).  Native spelling:
+
         :param shape: (nz, ny, nx) of the (local) block, C order, x fastest
         :param spacing: grid spacing along `direction` (may instead be given per call to dfdx/dfdy/dfdz)
         :param direction: 0 = x, 1 = y, 2 = z (numbering of code/cuda/gpuDA.py:162)
         :param part: (rank, size) of this block along the derivative line -- the reference's
                      (line_da.rank, line_da.size), code/cuda/compact.py:159-166.  (0, 1) = whole line here.
         """
+        if hasattr(shape, "nz") and hasattr(shape, "rank"):            # a line_da of the reference
+            da = shape
+            part = (da.rank, da.size)
+            if direction is None:
+                direction = getattr(da, "direction", 0)
+            shape = (da.nz, da.ny, da.nx)
         assert len(shape) == 3, "shape is (nz, ny, nx)"
         self.shape = tuple(int(s) for s in shape)
         self.part = (int(part[0]), int(part[1]))

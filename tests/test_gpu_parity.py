@@ -520,3 +520,21 @@ def test_error_codes(C):
         s(f, out=f)                                                   # in-place derivative
     with pytest.raises(AssertionError):
         s(f.float())
+
+
+def test_reference_call_shape(C):
+    """The reference's own call sequence (code/cuda/test/test_compact.py:19-31): a line_da, dfdx(f_d, dx, x_d,
+    f_local_d) filling x_d; decimal=2 against cos(x), plus oracle parity."""
+    import torch
+    shape = (32, 32, 32)
+    x, y, z = smooth(shape)
+    line_da = C.LineDA(shape)                              # one rank along the line
+    cfd = C.CompactFiniteDifferenceSolver(line_da, solver='templated')
+    f = np.sin(x)
+    f_d = dev(f)
+    x_d = torch.empty_like(f_d)
+    f_local_d = torch.empty((34, 34, 34), dtype=torch.float64, device="cuda")     # the reference's ghosted scratch
+    dx = x[0, 0, 1] - x[0, 0, 0]
+    cfd.dfdx(f_d, dx, x_d, f_local_d)
+    np.testing.assert_almost_equal(np.cos(x), x_d.cpu().numpy(), decimal=2)
+    assert relinf(x_d.cpu().numpy(), O.derivative(f, 0, dx)) <= TOL

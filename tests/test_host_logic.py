@@ -191,3 +191,17 @@ def test_segmented_schedule(n, kseg):
     assert relinf(got, want) < 1e-14
     want2 = O.near_toeplitz_solve(F.reshape(1, 3, n), PADE).reshape(3, n)
     assert relinf(stream_lines(F, PADE, kseg=kseg), want2) < 1e-14
+
+
+def test_chunk_schedule_random_property():
+    """Randomised sweep over line lengths, segmentations and block positions: the kernel schedule (emulated with the
+    library's tables) stays within 1e-13 of the oracle."""
+    rng = np.random.default_rng(2026)
+    for _ in range(40):
+        n = int(rng.integers(4, 700))
+        kseg = int(rng.integers(0, 6))
+        F = rng.standard_normal((2, n))
+        h = float(rng.uniform(0.01, 2.0))
+        want = O.derivative(F.reshape(1, 2, n), 0, h).reshape(2, n)
+        got = stream_lines(F, PADE, h, kseg=kseg or None)
+        assert relinf(got, want) < 1e-13, (n, kseg)
