@@ -538,3 +538,34 @@ def test_reference_call_shape(C):
     cfd.dfdx(f_d, dx, x_d, f_local_d)
     np.testing.assert_almost_equal(np.cos(x), x_d.cpu().numpy(), decimal=2)
     assert relinf(x_d.cpu().numpy(), O.derivative(f, 0, dx)) <= TOL
+
+
+def test_cuda_graph_capture(C):
+    """apply() makes no allocation and no synchronisation, so a gradient step can be captured into a CUDA graph
+    (small grids are launch-bound: 64^3 is ~5 us of kernel per derivative); replays must reproduce the result."""
+    import torch
+    n = 64
+    rng = np.random.default_rng(64)
+    f = rng.random((n, n, n))
+    fd = dev(f)
+    outs = [torch.empty_like(fd) for _ in range(3)]
+    ops = [C.CompactFiniteDifferenceSolver((n, n, n), 0.1, a) for a in range(3)]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for a in range(3):                       # warm-up outside capture (first-call attribute set-up)
+            ops[a](fd, outs[a])
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for a in range(3):
+            ops[a](fd, outs[a])
+    for rep in range(3):
+        fd.copy_(dev(f * (rep + 1)))
+        for o in outs:
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for a in range(3):
+            assert relinf(outs[a].cpu().numpy(), O.derivative(f * (rep + 1), a, 0.1)) <= TOL
