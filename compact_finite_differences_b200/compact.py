@@ -158,6 +158,51 @@ class CompactFiniteDifferenceSolver:
         assert self.spacing is not None and self.direction == axis, f"spacing along {_AXIS_NAMES[axis]} not given"
         return self.spacing
 
+    # -- the reference's stage methods (code/cuda/compact.py:46-154), each on its own kernel ------------------
+    def compute_RHS(self, f, dx=None, x=None, f_local=None, halo_lo=None, halo_hi=None):
+        """x = Pade right-hand side of f (compact.py:46-51).  f_local (ghosted scratch) is accepted and ignored;
+        blocks that do not own a physical end take the neighbour planes as halo_lo / halo_hi."""
+        import torch
+        h = self._h(dx, self._axis())
+        plan = self._plan(self._axis(), h)
+        if x is None:
+            x = torch.empty_like(f)
+        check(lib().cfd_compute_rhs(plan.handle, f.data_ptr(), x.data_ptr(),
+                                    halo_lo.data_ptr() if halo_lo is not None else None,
+                                    halo_hi.data_ptr() if halo_hi is not None else None, _stream_ptr(f)))
+        return x
+
+    def solve_primary_system(self, x):
+        """In-place block-local tridiagonal solve of the right-hand sides in x (compact.py:62-64)."""
+        from .near_toeplitz import NearToeplitzSolver
+        if getattr(self, "_primary", None) is None:
+            plan = self._plan(self._axis(), self._h(None, self._axis()))
+            co = (ctypes.c_double * 7)()
+            check(lib().cfd_plan_coeffs(plan.handle, co))
+            self._primary = NearToeplitzSolver(self.shape, list(co), axis=self._axis())
+        return self._primary.solve(x)
+
+    def solve_secondary_systems(self):
+        """(x_UH, x_LH): unit responses of the block matrix (compact.py:128-154), as CUDA tensors."""
+        import torch
+        plan = self._plan(self._axis(), self._h(None, self._axis()))
+        n = self.shape[2 - self._axis()]
+        dp = ctypes.POINTER(ctypes.c_double)
+        xu, xl = np.zeros(n), np.zeros(n)
+        check(lib().cfd_plan_secondary(plan.handle, xu.ctypes.data_as(dp), xl.ctypes.data_as(dp), None, None, None))
+        return torch.from_numpy(xu).cuda(), torch.from_numpy(xl).cuda()
+
+    def sum_solutions(self, x_R, alpha, beta):
+        """x_R += alpha * x_UH + beta * x_LH over the whole block (compact.py:52-61); the secondary solutions are
+        the plan's own."""
+        plan = self._plan(self._axis(), self._h(None, self._axis()))
+        check(lib().cfd_sum_solutions(plan.handle, x_R.data_ptr(), alpha.data_ptr(), beta.data_ptr(), _stream_ptr(x_R)))
+        return x_R
+
+    def _axis(self):
+        assert self.direction is not None, "construct with direction= (or a line_da) to use the stage methods"
+        return self.direction
+
     # -- multi-rank pieces (used by partition.ZPartitionedDerivative) -----------------------------------
     def interface_pack(self, df, faces):
         plan = self._plan(self.direction, self.spacing)

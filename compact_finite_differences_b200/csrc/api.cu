@@ -704,6 +704,46 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
     return CFD_OK;
 }
 
+extern "C" int cfd_compute_rhs(cfd_plan *p, const double *f, double *rhs, const double *halo_lo, const double *halo_hi,
+                               void *stream)
+{
+    if (!p || !f || !rhs) return fail(CFD_EINVAL, "NULL argument");
+    if (f == rhs) return fail(CFD_EINVAL, "the right-hand side is computed out of place");
+    if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
+    if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
+    const long total = p->g.nlines * p->g.n;
+    const int bs = 256;
+    rhs_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        f, rhs, total, p->g.n, p->g.inner, p->h, p->kp.lo_closure, p->kp.hi_closure, halo_lo, halo_hi);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+extern "C" int cfd_sum_solutions(cfd_plan *p, double *x, const double *alpha, const double *beta, void *stream)
+{
+    if (!p || !x || !alpha || !beta) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no secondary solutions");
+    const long total = p->g.nlines * p->g.n;
+    const int bs = 256;
+    sum_solutions_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        x, alpha, beta, p->d_x_uh, p->d_x_lh, total, p->g.n, p->g.inner);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+// Block-local coefficient list [b1, c1, ai, bi, ci, an, bn] of the plan (code/cuda/compact.py:159-166), so that a
+// caller can build the matching NearToeplitzSolver for the reference's solve_primary_system stage.
+extern "C" int cfd_plan_coeffs(const cfd_plan *p, double coeffs[7])
+{
+    if (!p || !coeffs) return fail(CFD_EINVAL, "NULL argument");
+    const LineCoeffs m = pade_block(p->rank, p->size);
+    coeffs[0] = m.b1; coeffs[1] = m.c1; coeffs[2] = m.ai; coeffs[3] = m.bi; coeffs[4] = m.ci; coeffs[5] = m.an;
+    coeffs[6] = m.bn;
+    return CFD_OK;
+}
+
 extern "C" int cfd_interface_pack(cfd_plan *p, const double *df, double *faces, void *stream)
 {
     if (!p || !df || !faces) return fail(CFD_EINVAL, "NULL argument");

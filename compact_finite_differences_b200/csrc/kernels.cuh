@@ -846,6 +846,46 @@ __global__ void wait_flags_kernel(const unsigned long long *flag0, const unsigne
     if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
 }
 
+// ------------------------------------------------------------------------------------------------
+// The reference's individual stages, for callers that drive the path stage by stage the way
+// CompactFiniteDifferenceSolver.dfdx does (code/cuda/compact.py:40-44).  The fused kernels above do not use them.
+// ------------------------------------------------------------------------------------------------
+// computeRHS (code/cuda/kernels.cu:4-47) without the ghosted copy: one thread per point, neighbours `stride` apart,
+// one-sided closures at physical ends, halo planes at block ends.  Memory order = thread order (coalesced).
+__global__ void __launch_bounds__(256)
+rhs_kernel(const double *__restrict__ f, double *__restrict__ rhs, long total, int n, long stride, double h,
+           int lo_closure, int hi_closure, const double *__restrict__ halo_lo, const double *__restrict__ halo_hi)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const long i = (p / stride) % n;                       // coordinate along the derivative axis
+    const long line = (p / (stride * n)) * stride + (p % stride);
+    const double k = 3. / (4 * h);
+    double r;
+    if (i == 0) {
+        if (lo_closure) r = (1. / (2 * h)) * (-5 * f[p] + 4 * f[p + stride] + f[p + 2 * stride]);
+        else            r = k * (f[p + stride] - halo_lo[line]);
+    } else if (i == n - 1) {
+        if (hi_closure) r = -(1. / (2 * h)) * (-5 * f[p] + 4 * f[p - stride] + f[p - 2 * stride]);
+        else            r = k * (halo_hi[line] - f[p - stride]);
+    } else {
+        r = k * (f[p + stride] - f[p - stride]);
+    }
+    rhs[p] = r;
+}
+
+// sumSolutions (code/cuda/kernels.cu:49-74): x += alpha[line]*x_UH[i] + beta[line]*x_LH[i] over the WHOLE block.
+__global__ void __launch_bounds__(256)
+sum_solutions_kernel(double *__restrict__ x, const double *__restrict__ alpha, const double *__restrict__ beta,
+                     const double *__restrict__ x_uh, const double *__restrict__ x_lh, long total, int n, long stride)
+{
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const long i = (p / stride) % n;
+    const long line = (p / (stride * n)) * stride + (p % stride);
+    x[p] += alpha[line] * x_uh[i] + beta[line] * x_lh[i];
+}
+
 // Thread-parallel Thomas over interleaved systems sharing one matrix (reference reducedSolverKernel,
 // code/cuda/kernels.cu:115-145).  lu = [3][n]: a_i, 1/pivot_i, c_i/pivot_i.
 __global__ void pthomas_kernel(double *__restrict__ d, const double *__restrict__ lu, int n, long nsys)

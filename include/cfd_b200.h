@@ -63,6 +63,19 @@ void cfd_destroy(cfd_plan *plan);
 int cfd_apply(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
               void *stream);
 
+/* The reference's stages one by one, for callers that drive the path the way dfdx does (compact.py:40-44); the
+ * fused entry points above never call them.
+ *   cfd_compute_rhs   rhs = Pade right-hand side of f (computeRHS, code/cuda/kernels.cu:4-47, without the ghosted
+ *                     copy of gpuDA.global_to_local); out of place.
+ *   cfd_plan_coeffs   [b1,c1,ai,bi,ci,an,bn] of the block (compact.py:159-166) for a matching nt_create:
+ *                     solve_primary_system (compact.py:62-64) = nt_solve on rhs.
+ *   cfd_sum_solutions x += alpha*x_UH + beta*x_LH over the whole block (sumSolutions, kernels.cu:49-74), alpha and
+ *                     beta planes as produced by cfd_reduced_unknowns. */
+int cfd_compute_rhs(cfd_plan *plan, const double *f, double *rhs, const double *halo_lo, const double *halo_hi,
+                    void *stream);
+int cfd_plan_coeffs(const cfd_plan *plan, double coeffs[7]);
+int cfd_sum_solutions(cfd_plan *plan, double *x, const double *alpha, const double *beta, void *stream);
+
 /* Interface right-hand side of the reduced system: faces[0] = -x_R[first], faces[1] = -x_R[last], zero
  * at physical ends.  faces is [2][plane].  Replaces negateAndCopyFaces (code/cuda/kernels.cu:76-113). */
 int cfd_interface_pack(cfd_plan *plan, const double *df, double *faces, void *stream);

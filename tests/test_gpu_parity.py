@@ -569,3 +569,49 @@ def test_cuda_graph_capture(C):
         torch.cuda.synchronize()
         for a in range(3):
             assert relinf(outs[a].cpu().numpy(), O.derivative(f * (rep + 1), a, 0.1)) <= TOL
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_reference_stages_one_by_one(C, axis):
+    """The reference's dfdx body (code/cuda/compact.py:40-44) stage by stage on a 3-rank line, every stage checked
+    against the oracle's restatement of that stage: compute_RHS, solve_primary_system, solve_secondary_systems,
+    the reduced system, sum_solutions."""
+    import torch
+    P, h = 3, 0.23
+    shape = [10, 12, 14]
+    shape[2 - axis] = 3 * 40
+    rng = np.random.default_rng(axis + 30)
+    f = rng.random(shape)
+    ax = 2 - axis
+    n = shape[ax] // P
+    blocks = [np.ascontiguousarray(np.take(f, range(r * n, (r + 1) * n), axis=ax)) for r in range(P)]
+    plane = blocks[0].size // n
+    faces = torch.zeros((2 * P, plane), dtype=torch.float64, device="cuda")
+    xr, cfds = [], []
+    for r in range(P):
+        lo = np.take(blocks[r - 1], n - 1, axis=ax) if r > 0 else None
+        hi = np.take(blocks[r + 1], 0, axis=ax) if r < P - 1 else None
+        cfd = C.CompactFiniteDifferenceSolver(C.LineDA(blocks[r].shape, r, P, axis), solver="templated")
+        cfd.spacing = h
+        x_d = cfd.compute_RHS(dev(blocks[r]), h, None, None, None if lo is None else dev(lo), None if hi is None else dev(hi))
+        want_rhs = O.rhs(blocks[r], axis, h, halo_lo=lo, halo_hi=hi)
+        assert relinf(x_d.cpu().numpy(), want_rhs) <= 1e-15                               # a1 computeRHS
+        cfd.solve_primary_system(x_d)
+        want_xr = O.scipy_solve_axis(want_rhs, O.partition_local_coeffs(r, P), axis)
+        assert relinf(x_d.cpu().numpy(), want_xr) <= TOL                                  # a3 primary solve
+        xu, xl = cfd.solve_secondary_systems()
+        xu_w, xl_w = O.partition_secondary(n, r, P)
+        np.testing.assert_allclose(xu.cpu().numpy(), xu_w, rtol=1e-13, atol=1e-300)       # a4 secondary systems
+        np.testing.assert_allclose(xl.cpu().numpy(), xl_w, rtol=1e-13, atol=1e-300)
+        cfd.interface_pack(x_d, faces[2 * r:2 * r + 2])                                   # a5 negateAndCopyFaces
+        xr.append(x_d)
+        cfds.append(cfd)
+    ra, rb, rc = O.partition_reduced_matrix(n, P)
+    sol = O.scipy_solve_banded(ra, rb, rc, faces.cpu().numpy())
+    ab = torch.empty((2, plane), dtype=torch.float64, device="cuda")
+    for r in range(P):
+        cfds[r].reduced_unknowns(faces, ab)                                               # a6 reduced system
+        np.testing.assert_allclose(ab.cpu().numpy(), sol[2 * r:2 * r + 2], rtol=1e-12, atol=1e-14)
+        cfds[r].sum_solutions(xr[r], ab[0], ab[1])                                        # a7 sumSolutions
+    got = np.concatenate([x.cpu().numpy() for x in xr], axis=ax)
+    assert relinf(got, O.derivative(f, axis, h)) <= TOL                                   # a9 the whole dfdx
