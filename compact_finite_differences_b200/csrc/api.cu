@@ -230,6 +230,14 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
             if (want > g.K / 8) want = g.K / 8;
             if (want > 1) kseg = (int)((g.K + want - 1) / want);
         }
+        // Contiguous lines of >= 1024 rows with fewer than ~8 bundles per warp: the dynamic draw gets coarse (a
+        // warp's last bundle is 1/4..1/8 of its work).  Segments of >= 16 chunks shorten the tail; measured on
+        // [128,1024,1024]: d/dx 0.362 -> 0.348 ms (strided lines did not gain and keep whole lines).
+        if (CONTIG && !in_place && !kseg && g.K >= 32 && g.nb < 8L * dinfo.sms * warps) {
+            long want = (8L * dinfo.sms * warps + g.nb - 1) / g.nb;
+            if (want > g.K / 16) want = g.K / 16;
+            if (want > 1) kseg = (int)((g.K + want - 1) / want);
+        }
         if (kseg > 0 && kseg < g.K) { kp.kseg = kseg; kp.nseg = (g.K + kseg - 1) / kseg; }
     }
     const long nitems = g.nb * kp.nseg;
@@ -938,8 +946,8 @@ extern "C" int cfd_pthomas(const double *a, const double *b, const double *c, do
     }
     double *d_lu = nullptr;
     CUDA_TRY(cudaMallocAsync(&d_lu, lu.size() * sizeof(double), (cudaStream_t)stream));
+    // lu is pageable host memory: the runtime stages it before cudaMemcpyAsync returns, so it may die with this frame
     CUDA_TRY(cudaMemcpyAsync(d_lu, lu.data(), lu.size() * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // lu is a stack-lifetime host buffer
     const int bs = 128;
     pthomas_kernel<<<(unsigned)((nsys + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(d, d_lu, n, nsys);
     g_launches++;
