@@ -19,6 +19,7 @@ SIGNATURES = {
     "cfd_create": (_i, [_pp, _i, _i, _i, _i, _d, _i, _i]),
     "cfd_destroy": (None, [_vp]),
     "cfd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_apply_xy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_compute_rhs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_plan_coeffs": (_i, [_vp, _dp]),
     "cfd_sum_solutions": (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "api.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "tables.h")] + \
+DEPS = SRC + [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "kernels_xy.cuh", "tables.h")] + \
     [os.path.join(HERE, "..", "include", "cfd_b200.h")]
 OUT = os.path.join(HERE, "libcfd_b200.so")
 

@@ -141,6 +141,24 @@ class CompactFiniteDifferenceSolver:
         planes of f where this block does not own the physical end."""
         return self._apply(self.direction, self.spacing, f, out, halo_lo, halo_hi)
 
+    def dfdxy(self, f, dx, dy, out_x=None, out_y=None):
+        """d/dx and d/dy of f in ONE launch (cfd_apply_xy): the two derivatives share the HBM reads of f through L2."""
+        import torch
+        px, py = self._plan(0, float(dx)), self._plan(1, float(dy))
+        assert f.is_cuda and f.dtype == torch.float64 and f.is_contiguous() and tuple(f.shape) == self.shape
+        out_x = torch.empty_like(f) if out_x is None else out_x
+        out_y = torch.empty_like(f) if out_y is None else out_y
+        check(lib().cfd_apply_xy(px.handle, py.handle, f.data_ptr(), out_x.data_ptr(), out_y.data_ptr(), _stream_ptr(f)))
+        return out_x, out_y
+
+    def gradient(self, f, spacings, out=None):
+        """(df/dx, df/dy, df/dz) with spacings = (dx, dy, dz): x and y in one launch, z in a second."""
+        dx, dy, dz = spacings
+        out = (None, None, None) if out is None else out
+        gx, gy = self.dfdxy(f, dx, dy, out[0], out[1])
+        gz = self.dfdz(f, dz, out[2])
+        return gx, gy, gz
+
     # reference spellings (code/ocl/compact.py:26,41,52; code/cuda/compact.py:29)
     def dfdx(self, f, dx=None, out=None, f_local=None):
         """f_local (the reference's ghosted scratch array) is accepted and ignored: no ghost copy is made."""

@@ -16,6 +16,7 @@
 
 #include "../../include/cfd_b200.h"
 #include "kernels.cuh"
+#include "kernels_xy.cuh"
 
 using namespace cfd;
 
@@ -303,6 +304,10 @@ struct cfd_plan {
     // host staging
     double *d_f = nullptr, *d_df = nullptr;
     cudaStream_t hstream = nullptr;
+    // cfd_apply_xy: draw order of the (plane, bundle) items (axis-0 plans only)
+    std::mutex xy_mu;
+    int *d_xy_order = nullptr;
+    double xy_active = -1.0;
 };
 
 struct nt_plan {
@@ -512,7 +517,7 @@ extern "C" void cfd_destroy(cfd_plan *p)
 {
     if (!p) return;
     cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu); cudaFree(p->d_lu_nb);
-    cudaFree(p->d_f); cudaFree(p->d_df);
+    cudaFree(p->d_f); cudaFree(p->d_df); cudaFree(p->d_xy_order);
     if (p->hstream) cudaStreamDestroy(p->hstream);
     delete p;
 }
@@ -638,6 +643,105 @@ extern "C" int cfd_nb_layout(const cfd_plan *p, int *virtual_ranks, int *own_ind
 static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
                      double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
                      unsigned long long seq, bool p2p, void *stream);
+
+// d/dx and d/dy of one field in one launch (kernels_xy.cuh).  A plane of f is a grid of 32 x 32 tiles (j, k):
+// x-bundle j walks tiles (j, 0), (j, 1), ... and y-bundle k walks (0, k), (1, k), ...  When x-bundle j and y-bundle j
+// both start j tile-times after their plane's first bundles, the two readers of EVERY tile (j, k) ask for it at the
+// same moment, j + k tile-times in: one of them brings it from HBM, the other finds it in L2.  The draw order below
+// produces that wavefront with dynamically scheduled warps: per slot (= one tile-time) every active plane
+// contributes its next (x, y) bundle pair, and `active` planes are in flight so that a slot's worth of items is
+// what all resident warps draw in one tile-time (active = warps / (2 K)).
+static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
+{
+    const int ipp = nxp + nyp, M = nxp > nyp ? nxp : nyp;
+    std::vector<int> order;
+    order.reserve((size_t)nz * ipp);
+    if (active <= 0.0) {                       // plain plane-by-plane order
+        for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)w);
+        return order;
+    }
+    const double sigma = (double)M / active;   // slots between the starts of consecutive planes
+    auto start = [&](int z) { return (long)std::floor(z * sigma); };
+    int zlo = 0;
+    for (long s = 0; zlo < nz; s++) {
+        for (int z = zlo; z < nz && start(z) <= s; z++) {
+            const long j = s - start(z);
+            if (j >= M) { if (z == zlo) zlo++; continue; }
+            if (j < nxp) order.push_back(z * ipp + (int)j);
+            if (j < nyp) order.push_back(z * ipp + nxp + (int)j);
+        }
+    }
+    return order;
+}
+
+extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double *dfdx, double *dfdy, void *stream)
+{
+    if (!px || !py || !f || !dfdx || !dfdy) return fail(CFD_EINVAL, "NULL argument");
+    if (px->g.axis != 0 || py->g.axis != 1) return fail(CFD_EINVAL, "plans must be for axis 0 (x) and axis 1 (y)");
+    if (px->g.nz != py->g.nz || px->g.ny != py->g.ny || px->g.nx != py->g.nx)
+        return fail(CFD_EINVAL, "plans are for different shapes");
+    if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "cfd_apply_xy serves unpartitioned x / y lines");
+    if (f == dfdx || f == dfdy || dfdx == dfdy) return fail(CFD_EINVAL, "f, dfdx, dfdy must be three different fields");
+    const long nitems_l = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
+    if (px->g.ny % CH != 0 || nitems_l > 0x7fffffffL || getenv("CFD_NO_XY")) {
+        int rc = cfd_apply(px, f, dfdx, nullptr, nullptr, stream);
+        if (rc) return rc;
+        return cfd_apply(py, f, dfdy, nullptr, nullptr, stream);
+    }
+    MapPair mx, my;
+    int rc = get_maps(px->cache, px->g, f, dfdx, mx);
+    if (rc) return rc;
+    rc = get_maps(py->cache, py->g, f, dfdy, my);
+    if (rc) return rc;
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { rc = device_info(dinfo); if (rc) return rc; }
+    constexpr int NSLOT = 3;
+    constexpr int per_warp = (NSLOT + 2) * SLOT_BYTES + NSLOT * 16;
+    XYParams q;
+    q.nxp = px->g.ny / CH;
+    q.nyp = py->g.inner_tiles;
+    q.nitems = nitems_l;
+    int warps = g_warps ? g_warps : 4;
+    if (warps > 5) warps = 5;
+    const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
+    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    {
+        // planes in flight: what the resident warps draw in one tile-time (CFD_XY_ACTIVE overrides; 0 = plane order)
+        const double kavg = 0.5 * (px->g.K + py->g.K);
+        double active = (double)dinfo.sms * warps / (2.0 * kavg);
+        if (const char *e = getenv("CFD_XY_ACTIVE")) active = atof(e);
+        if (active > 0.0 && active < 1.0) active = 1.0;
+        std::lock_guard<std::mutex> lock(px->xy_mu);
+        if (!px->d_xy_order || px->xy_active != active) {
+            const std::vector<int> order = xy_order(px->g.nz, q.nxp, q.nyp, active);
+            if ((long)order.size() != q.nitems) return fail(CFD_EINVAL, "internal: xy order has %ld of %ld items", (long)order.size(), q.nitems);
+            if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+            px->xy_active = active;
+        }
+        q.order = px->d_xy_order;
+    }
+    const size_t smem = (size_t)warps * per_warp + 1024;
+    auto kern = stream_kernel_xy<NSLOT>;
+    static size_t configured[MAX_DEVICES] = {0};
+    int dev = 0;
+    rc = current_device(dev);
+    if (rc) return rc;
+    if (configured[dev] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    rc = counter_pair(&q.counter);
+    if (rc) return rc;
+    KParams kx = px->kp, ky = py->kp;
+    kx.ab = nullptr; ky.ab = nullptr;
+    long blocks = (q.nitems + warps - 1) / warps;
+    if (blocks > dinfo.sms) blocks = dinfo.sms;
+    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
 
 extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,
                               double *faces, void *stream)

@@ -1,0 +1,198 @@
+// kernels_xy.cuh -- d/dx and d/dy of the same field in ONE launch, with the work interleaved plane by plane.
+//
+// Both derivatives are still the one-pass streaming solve of kernels.cuh (same chunk primitives, same tables), and
+// each still writes its own 8 B/point.  What changes is the ORDER of the work: the item list is
+//     plane 0: x-bundles (32 rows of the plane each), y-bundles (32 columns each); plane 1: ...; ...
+// and warps draw items from it dynamically.  At any time the ~600 resident warps work on a window of ~20 planes,
+// so every tile of f is fetched from HBM by whichever of its two readers comes first and served from L2 to the
+// other a few microseconds later: 24 B/point of DRAM traffic for the two derivatives instead of 32.
+// The reference computes the directions by separate passes (and host transposes, code/ocl/compact.py:41-61).
+#pragma once
+#include "kernels.cuh"
+
+namespace cfd {
+
+struct XYParams {
+    long nitems;        // nz * (nxp + nyp)
+    int nxp, nyp;       // x-bundles (ny/32) and y-bundles (ceil(nx/32)) per plane
+    unsigned long long *counter;
+    const int *order;   // draw position -> item (plane * (nxp + nyp) + index in plane); nullptr = identity
+};
+
+// One item = all chunks of one bundle, x (CONTIG) or y (STRIDED).  Ring state is shared across items.
+template <bool CONTIG, int NS, class Issue>
+__device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap *tm_out, long b, int oc0, int oc2,
+                                            unsigned char *wbase, uint32_t bar0, int lane, int &slot, uint32_t &phase,
+                                            int &ocur, Issue &issue)
+{
+    const int K = p.K;
+    double eA[CH], eB[CH], F[CH];
+    double eprev = 0.0, fm1 = 0.0, fm2 = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+        const bool last = (k == K - 1);
+        mbar_wait(bar0 + 8 * slot, phase);
+        load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
+        double peek = 0.0;
+        if (!last) {
+            const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
+            const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;
+            mbar_wait(bar0 + 8 * s1, ph1);
+            peek = load_first<CONTIG>(wbase + s1 * SLOT_BYTES, lane);
+        }
+        if (k == 0) {
+            if (last) fwd_chunk<1, true, -2>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
+            else      fwd_chunk<1, true, -1>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
+        } else if (last) {
+            if (p.jl == CH - 1) fwd_chunk<2, true, CH - 1>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
+            else                fwd_chunk<2, true, -2>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
+        } else {
+            fwd_chunk<0, true, -1>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
+        }
+        __syncwarp();
+        if (lane == 0) issue();
+        __syncwarp();
+
+        unsigned char *oslot = wbase + (NS + ocur) * SLOT_BYTES;
+        auto flush = [&](int kc) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CONTIG) {
+                    tma_store_2d(tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
+                    tma_store_2d(tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
+                } else {
+                    tma_store_3d(tm_out, smem_u32(oslot), oc0, kc * CH, oc2);
+                }
+                tma_commit();
+            }
+            ocur ^= 1;
+            oslot = wbase + (NS + ocur) * SLOT_BYTES;
+        };
+        auto acquire_out = [&]() {
+            if (lane == 0) tma_wait_read1();
+            __syncwarp();
+        };
+        double x = 0.0;
+        if (last) {
+            acquire_out();
+            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane);
+            else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane);
+            flush(k);
+            if (k > 0) {
+                acquire_out();
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
+                flush(k - 1);
+            }
+        } else if (k > 0) {
+            bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane);
+            acquire_out();
+            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
+            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
+            flush(k - 1);
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) eA[j] = eB[j];
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(224, 1)
+stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_constant__ CUtensorMap tmx_out,
+                 const __grid_constant__ CUtensorMap tmy_in, const __grid_constant__ CUtensorMap tmy_out,
+                 const __grid_constant__ KParams px, const __grid_constant__ KParams py,
+                 const __grid_constant__ XYParams q)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int PER_WARP = (NS + 2) * SLOT_BYTES;
+    constexpr int CTRL = NS * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *wbase = base + warp * PER_WARP;
+    unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
+    const uint32_t bar0 = smem_u32(ctrl);
+    volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
+    const int ipp = q.nxp + q.nyp;       // items per plane
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+
+    // item -> (direction, bundle, plane)
+    auto decode = [&](long w, bool &contig, long &b, int &c0, int &c2) {
+        const long z = w / ipp;
+        const int r = (int)(w - z * ipp);
+        contig = r < q.nxp;
+        if (contig) { b = z * q.nxp + r; c0 = 0; c2 = 0; }
+        else        { b = z * q.nyp + (r - q.nxp); c0 = (r - q.nxp) * CH; c2 = (int)z; }
+    };
+
+    // ---- producer (lane 0)
+    long iw = 0, ib = 0;
+    int ik = 1, iK = 0, ic0 = 0, ic2 = 0, islot = 0;
+    bool icontig = true, dry = false;
+    auto issue = [&]() {
+        if (ik >= iK && !dry) {
+            iw = (long)atomicAdd(q.counter, 1ULL);
+            dry = iw >= q.nitems;
+            if (!dry) {
+                if (q.order) iw = q.order[iw];
+                decode(iw, icontig, ib, ic0, ic2);
+                ik = 0;
+                iK = icontig ? px.K : py.K;
+            }
+        }
+        if (dry) {
+            tag[islot] = -1;
+        } else {
+            tag[islot] = iw;
+            const uint32_t bar = bar0 + 8 * islot;
+            const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
+            mbar_expect_tx(bar, SLOT_BYTES);
+            if (icontig) {
+                tma_load_2d(dst, &tmx_in, bar, ik * CH, (int)(ib * CH));
+                tma_load_2d(dst + 4096, &tmx_in, bar, ik * CH + 16, (int)(ib * CH));
+            } else {
+                tma_load_3d(dst, &tmy_in, bar, ic0, ik * CH, ic2);
+            }
+            ++ik;
+        }
+        if (++islot == NS) islot = 0;
+    };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NS; s++) issue();
+    }
+    __syncwarp();
+
+    // ---- consumer
+    int slot = 0, ocur = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        const long w = tag[slot];
+        if (w < 0) break;
+        bool contig;
+        long b;
+        int c0, c2;
+        decode(w, contig, b, c0, c2);
+        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, ocur, issue);
+        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, ocur, issue);
+    }
+    if (lane == 0) {
+        tma_wait_all0();
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * nwarps;
+        if (atomicAdd(q.counter + 1, 1ULL) == total - 1) {
+            q.counter[0] = 0ULL;
+            q.counter[1] = 0ULL;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace cfd

@@ -63,6 +63,12 @@ void cfd_destroy(cfd_plan *plan);
 int cfd_apply(cfd_plan *plan, const double *f, double *df, const double *halo_lo, const double *halo_hi,
               void *stream);
 
+/* d/dx and d/dy of the same field in ONE launch (plans for axis 0 and axis 1 of the same shape, part_size 1).
+ * Each derivative is the same one-pass solve as cfd_apply; the work of the two is interleaved plane by plane so
+ * that every tile of f comes from HBM once and from L2 the second time.  Replaces two dfdx / dfdy calls of the
+ * reference (code/ocl/compact.py:26-50).  Falls back to two launches when ny is not a multiple of 32. */
+int cfd_apply_xy(cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy, void *stream);
+
 /* The reference's stages one by one, for callers that drive the path the way dfdx does (compact.py:40-44); the
  * fused entry points above never call them.
  *   cfd_compute_rhs   rhs = Pade right-hand side of f (computeRHS, code/cuda/kernels.cu:4-47, without the ghosted
