@@ -674,35 +674,25 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
     return order;
 }
 
-extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double *dfdx, double *dfdy, void *stream)
+template <int NSLOT>
+static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPair &my, long nitems, cudaStream_t stream)
 {
-    if (!px || !py || !f || !dfdx || !dfdy) return fail(CFD_EINVAL, "NULL argument");
-    if (px->g.axis != 0 || py->g.axis != 1) return fail(CFD_EINVAL, "plans must be for axis 0 (x) and axis 1 (y)");
-    if (px->g.nz != py->g.nz || px->g.ny != py->g.ny || px->g.nx != py->g.nx)
-        return fail(CFD_EINVAL, "plans are for different shapes");
-    if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "cfd_apply_xy serves unpartitioned x / y lines");
-    if (f == dfdx || f == dfdy || dfdx == dfdy) return fail(CFD_EINVAL, "f, dfdx, dfdy must be three different fields");
-    const long nitems_l = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
-    if (px->g.ny % CH != 0 || nitems_l > 0x7fffffffL || getenv("CFD_NO_XY")) {
-        int rc = cfd_apply(px, f, dfdx, nullptr, nullptr, stream);
-        if (rc) return rc;
-        return cfd_apply(py, f, dfdy, nullptr, nullptr, stream);
-    }
-    MapPair mx, my;
-    int rc = get_maps(px->cache, px->g, f, dfdx, mx);
-    if (rc) return rc;
-    rc = get_maps(py->cache, py->g, f, dfdy, my);
-    if (rc) return rc;
     static DeviceInfo dinfo;
+    int rc;
     if (!dinfo.ok) { rc = device_info(dinfo); if (rc) return rc; }
-    constexpr int NSLOT = 3;
-    constexpr int per_warp = (NSLOT + 2) * SLOT_BYTES + NSLOT * 16;
+    // The ring is all the shared memory a warp has (results are staged in the slot just consumed): 8 warps per SM
+    // fit with 3 slots (also the limit of 255 registers per thread), 7 with 4.  Measured at 512^3 (scripts/time_xy.py,
+    // profiles/r1k_time_xy.txt): 4 slots x 6 warps 0.532 ms, 4 x 7 0.546, 3 x 8 0.546, 4 x 5 0.564; the old
+    // 3 + 2 staging slots x 5 warps 0.553; d/dx then d/dy as two launches 0.673.
+    constexpr int per_warp = NSLOT * SLOT_BYTES + NSLOT * 16;
+    const int max_warps = NSLOT == 3 ? 8 : 7;
+    const int def_warps = NSLOT == 3 ? 8 : 6;
     XYParams q;
     q.nxp = px->g.ny / CH;
     q.nyp = py->g.inner_tiles;
-    q.nitems = nitems_l;
-    int warps = g_warps ? g_warps : 4;
-    if (warps > 5) warps = 5;
+    q.nitems = nitems;
+    int warps = g_warps ? g_warps : def_warps;
+    if (warps > max_warps) warps = max_warps;
     const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     {
@@ -737,10 +727,36 @@ extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double 
     kx.ab = nullptr; ky.ab = nullptr;
     long blocks = (q.nitems + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
-    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
+}
+
+extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double *dfdx, double *dfdy, void *stream)
+{
+    if (!px || !py || !f || !dfdx || !dfdy) return fail(CFD_EINVAL, "NULL argument");
+    if (px->g.axis != 0 || py->g.axis != 1) return fail(CFD_EINVAL, "plans must be for axis 0 (x) and axis 1 (y)");
+    if (px->g.nz != py->g.nz || px->g.ny != py->g.ny || px->g.nx != py->g.nx)
+        return fail(CFD_EINVAL, "plans are for different shapes");
+    if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "cfd_apply_xy serves unpartitioned x / y lines");
+    if (f == dfdx || f == dfdy || dfdx == dfdy) return fail(CFD_EINVAL, "f, dfdx, dfdy must be three different fields");
+    const long nitems = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
+    if (px->g.ny % CH != 0 || nitems > 0x7fffffffL || getenv("CFD_NO_XY")) {
+        int rc = cfd_apply(px, f, dfdx, nullptr, nullptr, stream);
+        if (rc) return rc;
+        return cfd_apply(py, f, dfdy, nullptr, nullptr, stream);
+    }
+    MapPair mx, my;
+    int rc = get_maps(px->cache, px->g, f, dfdx, mx);
+    if (rc) return rc;
+    rc = get_maps(py->cache, py->g, f, dfdy, my);
+    if (rc) return rc;
+    switch (g_slots ? g_slots : 4) {
+        case 3: return launch_xy<3>(px, py, mx, my, nitems, (cudaStream_t)stream);
+        case 4: return launch_xy<4>(px, py, mx, my, nitems, (cudaStream_t)stream);
+        default: return fail(CFD_EINVAL, "cfd_apply_xy: ring slots must be 3 or 4");
+    }
 }
 
 extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,

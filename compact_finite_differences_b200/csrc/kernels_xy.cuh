@@ -20,10 +20,16 @@ struct XYParams {
 };
 
 // One item = all chunks of one bundle, x (CONTIG) or y (STRIDED).  Ring state is shared across items.
+//
+// Shared memory per warp is the NS-slot tile ring and nothing else: the slot a tile was just consumed from (into
+// registers) doubles as the staging slot of the result tile this step emits, and is refilled ONE STEP LATER, once
+// the TMA store has finished reading it.  24 KiB per warp instead of 40 puts 8 warps on an SM (two per scheduler):
+// with one warp per scheduler every fixed-latency dependency of the recurrences is exposed and the pair of
+// derivatives is latency-bound (0.825 / 0.641 / 0.553 ms with 3 / 4 / 5 warps, time x warps = const).
 template <bool CONTIG, int NS, class Issue>
 __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap *tm_out, long b, int oc0, int oc2,
                                             unsigned char *wbase, uint32_t bar0, int lane, int &slot, uint32_t &phase,
-                                            int &ocur, Issue &issue)
+                                            bool &first_step, Issue &issue)
 {
     const int K = p.K;
     double eA[CH], eB[CH], F[CH];
@@ -31,8 +37,9 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
         const bool last = (k == K - 1);
+        unsigned char *cur = wbase + slot * SLOT_BYTES;
         mbar_wait(bar0 + 8 * slot, phase);
-        load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
+        load_chunk<CONTIG>(cur, lane, F);
         double peek = 0.0;
         if (!last) {
             const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
@@ -49,47 +56,44 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
         } else {
             fwd_chunk<0, true, -1>(p, F, peek, 0.0, 0.0, eB, eprev, fm1, fm2);
         }
+        // refill the slot of the PREVIOUS step: its result tile (if any) has had a forward sweep's time to leave
         __syncwarp();
-        if (lane == 0) issue();
+        if (lane == 0 && !first_step) {
+            tma_wait_read0();
+            issue();
+        }
+        first_step = false;
         __syncwarp();
 
-        unsigned char *oslot = wbase + (NS + ocur) * SLOT_BYTES;
-        auto flush = [&](int kc) {
+        auto flush = [&](int kc) {       // ship the result tile staged in the current slot
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 if constexpr (CONTIG) {
-                    tma_store_2d(tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
-                    tma_store_2d(tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
+                    tma_store_2d(tm_out, smem_u32(cur), kc * CH, (int)(b * CH));
+                    tma_store_2d(tm_out, smem_u32(cur) + 4096, kc * CH + 16, (int)(b * CH));
                 } else {
-                    tma_store_3d(tm_out, smem_u32(oslot), oc0, kc * CH, oc2);
+                    tma_store_3d(tm_out, smem_u32(cur), oc0, kc * CH, oc2);
                 }
                 tma_commit();
             }
-            ocur ^= 1;
-            oslot = wbase + (NS + ocur) * SLOT_BYTES;
-        };
-        auto acquire_out = [&]() {
-            if (lane == 0) tma_wait_read1();
-            __syncwarp();
         };
         double x = 0.0;
         if (last) {
-            acquire_out();
-            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, oslot, lane);
-            else        bwd_chunk<2, true, CONTIG>(p, eB, x, oslot, lane);
+            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, cur, lane);
+            else        bwd_chunk<2, true, CONTIG>(p, eB, x, cur, lane);
             flush(k);
             if (k > 0) {
-                acquire_out();
-                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
-                else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
+                if (lane == 0) tma_wait_read0();      // the line's last two tiles share the slot
+                __syncwarp();
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, cur, lane);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, cur, lane);
                 flush(k - 1);
             }
         } else if (k > 0) {
-            bwd_chunk<0, false, CONTIG>(p, eB, x, oslot, lane);
-            acquire_out();
-            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, oslot, lane);
-            else        bwd_chunk<0, true, CONTIG>(p, eA, x, oslot, lane);
+            bwd_chunk<0, false, CONTIG>(p, eB, x, cur, lane);
+            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, cur, lane);
+            else        bwd_chunk<0, true, CONTIG>(p, eA, x, cur, lane);
             flush(k - 1);
         }
 #pragma unroll
@@ -99,14 +103,14 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(256, 1)
 stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_constant__ CUtensorMap tmx_out,
                  const __grid_constant__ CUtensorMap tmy_in, const __grid_constant__ CUtensorMap tmy_out,
                  const __grid_constant__ KParams px, const __grid_constant__ KParams py,
                  const __grid_constant__ XYParams q)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int PER_WARP = (NS + 2) * SLOT_BYTES;
+    constexpr int PER_WARP = NS * SLOT_BYTES;
     constexpr int CTRL = NS * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -132,7 +136,7 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         else        { b = z * q.nyp + (r - q.nxp); c0 = (r - q.nxp) * CH; c2 = (int)z; }
     };
 
-    // ---- producer (lane 0)
+    // ---- producer (lane 0): one call per tile position; after the initial fill it runs NS - 1 positions ahead
     long iw = 0, ib = 0;
     int ik = 1, iK = 0, ic0 = 0, ic2 = 0, islot = 0;
     bool icontig = true, dry = false;
@@ -171,8 +175,9 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
     __syncwarp();
 
     // ---- consumer
-    int slot = 0, ocur = 0;
+    int slot = 0;
     uint32_t phase = 0;
+    bool first_step = true;
     for (;;) {
         const long w = tag[slot];
         if (w < 0) break;
@@ -180,8 +185,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         long b;
         int c0, c2;
         decode(w, contig, b, c0, c2);
-        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, ocur, issue);
-        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, ocur, issue);
+        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue);
+        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue);
     }
     if (lane == 0) {
         tma_wait_all0();

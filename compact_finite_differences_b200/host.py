@@ -74,8 +74,7 @@ class HostGradient:
             with torch.cuda.stream(s_comp):
                 s_comp.wait_event(ev_in)
                 sol = self._solvers[b - a]
-                sol.dfdx(f[a:b], self.dx, out=d[0][a:b])
-                sol.dfdy(f[a:b], self.dy, out=d[1][a:b])
+                sol.dfdxy(f[a:b], self.dx, self.dy, d[0][a:b], d[1][a:b])     # one launch, f read from HBM once
                 ev_c = torch.cuda.Event()
                 ev_c.record(s_comp)
             with torch.cuda.stream(s_out):

@@ -162,6 +162,82 @@ def test_512_cubed_properties(C):
 
 
 # ---------------------------------------------------------------------------------------------------
+# d/dx and d/dy in one launch (cfd_apply_xy) and the gradient built on it
+# ---------------------------------------------------------------------------------------------------
+XY_SHAPES = [(1, 32, 4), (3, 32, 34), (5, 64, 64), (2, 96, 130), (17, 128, 66), (9, 32, 256), (4, 256, 32), (70, 64, 96),
+             (6, 40, 34)]      # the last one has ny % 32 != 0: two-launch fallback inside the same call
+
+
+@pytest.mark.parametrize("shape", XY_SHAPES)
+def test_fused_xy_random(C, shape):
+    rng = np.random.default_rng(hash(shape) % 2 ** 32)
+    f = rng.random(shape)
+    hx, hy = 0.013, 0.21
+    s = C.CompactFiniteDifferenceSolver(shape)
+    gx, gy = s.dfdxy(dev(f), hx, hy)
+    assert relinf(gx.cpu().numpy(), O.derivative(f, 0, hx)) <= TOL
+    assert relinf(gy.cpu().numpy(), O.derivative(f, 1, hy)) <= TOL
+
+
+@pytest.mark.parametrize("warps,slots", [(1, 3), (8, 3), (2, 4), (7, 4)])
+def test_fused_xy_launch_shapes(C, warps, slots):
+    """Every ring / warp configuration of stream_kernel_xy, and the plain plane-by-plane draw order."""
+    shape = (11, 96, 160)
+    rng = np.random.default_rng(7)
+    f = rng.random(shape)
+    want = O.derivative(f, 0, 0.1), O.derivative(f, 1, 0.2)
+    s = C.CompactFiniteDifferenceSolver(shape)
+    try:
+        C.lib().cfd_set_launch(warps, 0, slots)
+        for active in ("", "0", "3"):
+            if active:
+                os.environ["CFD_XY_ACTIVE"] = active
+            gx, gy = s.dfdxy(dev(f), 0.1, 0.2)
+            assert relinf(gx.cpu().numpy(), want[0]) <= TOL and relinf(gy.cpu().numpy(), want[1]) <= TOL
+    finally:
+        os.environ.pop("CFD_XY_ACTIVE", None)
+        C.lib().cfd_set_launch(0, 0, 0)
+
+
+def test_gradient_256_cubed(C):
+    """BASELINE configs[1] through gradient(): one fused d/dx + d/dy launch and one d/dz launch, full-field parity."""
+    n = 256
+    x, y, z = smooth((n, n, n))
+    f = x * np.cos(x * y) + y * np.sin(z)                  # reference demo field, perf-test/multi-GPU/PyCUDA/run.py:29-30
+    h = 2 * np.pi / (n - 1)
+    O.port().oracle_set_num_threads(os.cpu_count() or 1)
+    g = C.CompactFiniteDifferenceSolver((n, n, n)).gradient(dev(f), (h, h, h))
+    for axis in range(3):
+        assert relinf(g[axis].cpu().numpy(), O.derivative(f, axis, h)) <= TOL
+
+
+def test_fused_xy_512_cubed_matches_separate_launches(C):
+    """At BASELINE's full size the fused launch runs the same arithmetic per line as dfdx / dfdy: bit-identical."""
+    import torch
+    n = 512
+    f = torch.rand((n, n, n), dtype=torch.float64, device="cuda")
+    s = C.CompactFiniteDifferenceSolver((n, n, n))
+    gx, gy = s.dfdxy(f, 0.1, 0.2)
+    assert torch.equal(gx, s.dfdx(f, 0.1))
+    assert torch.equal(gy, s.dfdy(f, 0.2))
+
+
+def test_fused_xy_rejects_bad_arguments(C):
+    import torch
+    f = torch.rand((4, 32, 32), dtype=torch.float64, device="cuda")
+    s = C.CompactFiniteDifferenceSolver((4, 32, 32))
+    px, py, pz = s._plan(0, 0.1), s._plan(1, 0.1), s._plan(2, 0.1)
+    o1, o2 = torch.empty_like(f), torch.empty_like(f)
+    L = C.lib()                                   # -1 = CFD_EINVAL
+    assert L.cfd_apply_xy(py.handle, px.handle, f.data_ptr(), o1.data_ptr(), o2.data_ptr(), None) == -1
+    assert L.cfd_apply_xy(px.handle, pz.handle, f.data_ptr(), o1.data_ptr(), o2.data_ptr(), None) == -1
+    assert L.cfd_apply_xy(px.handle, py.handle, f.data_ptr(), o1.data_ptr(), o1.data_ptr(), None) == -1
+    assert L.cfd_apply_xy(px.handle, py.handle, f.data_ptr(), f.data_ptr(), o2.data_ptr(), None) == -1
+    assert L.cfd_apply_xy(px.handle, py.handle, None, o1.data_ptr(), o2.data_ptr(), None) == -1
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------
 # solver-only API
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [32, 64, 128, 512, 1024, 4096])
