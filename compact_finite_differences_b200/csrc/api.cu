@@ -457,6 +457,71 @@ extern "C" int cfd_debug_neighbour(int n, int part_rank, int part_size, int *vir
     return CFD_OK;
 }
 
+// d/dx and d/dy of one field in one launch (kernels_xy.cuh).  A plane of f is a grid of 32 x 32 tiles (j, k):
+// x-bundle j walks tiles (j, 0), (j, 1), ... and y-bundle k walks (0, k), (1, k), ...  When x-bundle j and y-bundle j
+// both start j tile-times after their plane's first bundles, the two readers of EVERY tile (j, k) ask for it at the
+// same moment, j + k tile-times in: one of them brings it from HBM, the other finds it in L2.  The draw order below
+// produces that wavefront with dynamically scheduled warps: per slot (= one tile-time) every active plane
+// contributes its next (x, y) bundle pair, and `active` planes are in flight so that a slot's worth of items is
+// what all resident warps draw in one tile-time (active = warps / (2 K)).
+static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
+{
+    const int ipp = nxp + nyp, M = nxp > nyp ? nxp : nyp;
+    std::vector<int> order;
+    order.reserve((size_t)nz * ipp);
+    if (active <= 0.0) {                       // plain plane-by-plane order
+        for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)w);
+        return order;
+    }
+    const double sigma = (double)M / active;   // slots between the starts of consecutive planes
+    auto start = [&](int z) { return (long)std::floor(z * sigma); };
+    int zlo = 0;
+    for (long s = 0; zlo < nz; s++) {
+        for (int z = zlo; z < nz && start(z) <= s; z++) {
+            const long j = s - start(z);
+            if (j >= M) { if (z == zlo) zlo++; continue; }
+            if (j < nxp) order.push_back(z * ipp + (int)j);
+            if (j < nyp) order.push_back(z * ipp + nxp + (int)j);
+        }
+    }
+    return order;
+}
+
+// Default launch shape of stream_kernel_xy and the planes-in-flight figure that goes with it.
+static void xy_shape(const Geometry &gx, int sms, int nslot, int &warps, double &active)
+{
+    const int max_warps = nslot == 3 ? 8 : 7, def_warps = nslot == 3 ? 8 : 6;
+    const int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
+    const long nitems = (long)gx.nz * (gx.ny / CH + (gx.nx + CH - 1) / CH);
+    warps = g_warps ? g_warps : def_warps;
+    if (warps > max_warps) warps = max_warps;
+    const long per_sm = (nitems + sms - 1) / sms;
+    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    active = (double)sms * warps / (Kx + Ky);          // = warps / (2 K) for square planes
+    if (const char *e = getenv("CFD_XY_ACTIVE")) active = atof(e);      // 0 = plain plane-by-plane order
+    if (active > 0.0 && active < 1.0) active = 1.0;
+}
+
+// (Re)build the draw-order table of an axis-0 plan.  Called from cfd_create with the default launch shape, so that
+// cfd_apply_xy neither allocates nor synchronises; it only runs again if the launch knobs were changed afterwards.
+static int xy_prepare(cfd_plan *px, double active)
+{
+    std::lock_guard<std::mutex> lock(px->xy_mu);
+    if (px->d_xy_order && px->xy_active == active) return CFD_OK;
+    const int nxp = px->g.ny / CH, nyp = (px->g.nx + CH - 1) / CH;
+    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active);
+    if ((long)order.size() != (long)px->g.nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
+    if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    px->xy_active = active;
+    return CFD_OK;
+}
+
+static bool xy_eligible(const Geometry &g)
+{
+    return g.axis == 0 && g.ny % CH == 0 && (long)g.nz * (g.ny / CH + (g.nx + CH - 1) / CH) <= 0x7fffffffL;
+}
+
 extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size)
 {
     if (!out) return fail(CFD_EINVAL, "plan pointer is NULL");
@@ -508,6 +573,14 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
         cudaMemcpy(p->d_x_lh, p->x_lh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(p->d_lu, p->lu.data(), p->lu.size() * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(p->d_lu_nb, p->lu_nb.data(), p->lu_nb.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    if (part_size == 1 && xy_eligible(p->g)) {        // draw order of cfd_apply_xy, default launch shape
+        DeviceInfo di;
+        int warps = 0;
+        double active = 0.0;
+        rc = device_info(di);
+        if (!rc) { xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, warps, active); rc = xy_prepare(p, active); }
+        if (rc) { cfd_destroy(p); return rc; }
     }
     *out = p;
     return CFD_OK;
@@ -644,36 +717,6 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
                      double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
                      unsigned long long seq, bool p2p, void *stream);
 
-// d/dx and d/dy of one field in one launch (kernels_xy.cuh).  A plane of f is a grid of 32 x 32 tiles (j, k):
-// x-bundle j walks tiles (j, 0), (j, 1), ... and y-bundle k walks (0, k), (1, k), ...  When x-bundle j and y-bundle j
-// both start j tile-times after their plane's first bundles, the two readers of EVERY tile (j, k) ask for it at the
-// same moment, j + k tile-times in: one of them brings it from HBM, the other finds it in L2.  The draw order below
-// produces that wavefront with dynamically scheduled warps: per slot (= one tile-time) every active plane
-// contributes its next (x, y) bundle pair, and `active` planes are in flight so that a slot's worth of items is
-// what all resident warps draw in one tile-time (active = warps / (2 K)).
-static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
-{
-    const int ipp = nxp + nyp, M = nxp > nyp ? nxp : nyp;
-    std::vector<int> order;
-    order.reserve((size_t)nz * ipp);
-    if (active <= 0.0) {                       // plain plane-by-plane order
-        for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)w);
-        return order;
-    }
-    const double sigma = (double)M / active;   // slots between the starts of consecutive planes
-    auto start = [&](int z) { return (long)std::floor(z * sigma); };
-    int zlo = 0;
-    for (long s = 0; zlo < nz; s++) {
-        for (int z = zlo; z < nz && start(z) <= s; z++) {
-            const long j = s - start(z);
-            if (j >= M) { if (z == zlo) zlo++; continue; }
-            if (j < nxp) order.push_back(z * ipp + (int)j);
-            if (j < nyp) order.push_back(z * ipp + nxp + (int)j);
-        }
-    }
-    return order;
-}
-
 template <int NSLOT>
 static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPair &my, long nitems, cudaStream_t stream)
 {
@@ -685,32 +728,16 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     // profiles/r1k_time_xy.txt): 4 slots x 6 warps 0.532 ms, 4 x 7 0.546, 3 x 8 0.546, 4 x 5 0.564; the old
     // 3 + 2 staging slots x 5 warps 0.553; d/dx then d/dy as two launches 0.673.
     constexpr int per_warp = NSLOT * SLOT_BYTES + NSLOT * 16;
-    const int max_warps = NSLOT == 3 ? 8 : 7;
-    const int def_warps = NSLOT == 3 ? 8 : 6;
     XYParams q;
     q.nxp = px->g.ny / CH;
     q.nyp = py->g.inner_tiles;
     q.nitems = nitems;
-    int warps = g_warps ? g_warps : def_warps;
-    if (warps > max_warps) warps = max_warps;
-    const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
-    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
-    {
-        // planes in flight: what the resident warps draw in one tile-time (CFD_XY_ACTIVE overrides; 0 = plane order)
-        const double kavg = 0.5 * (px->g.K + py->g.K);
-        double active = (double)dinfo.sms * warps / (2.0 * kavg);
-        if (const char *e = getenv("CFD_XY_ACTIVE")) active = atof(e);
-        if (active > 0.0 && active < 1.0) active = 1.0;
-        std::lock_guard<std::mutex> lock(px->xy_mu);
-        if (!px->d_xy_order || px->xy_active != active) {
-            const std::vector<int> order = xy_order(px->g.nz, q.nxp, q.nyp, active);
-            if ((long)order.size() != q.nitems) return fail(CFD_EINVAL, "internal: xy order has %ld of %ld items", (long)order.size(), q.nitems);
-            if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
-            CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
-            px->xy_active = active;
-        }
-        q.order = px->d_xy_order;
-    }
+    int warps = 0;
+    double active = 0.0;
+    xy_shape(px->g, dinfo.sms, NSLOT, warps, active);
+    rc = xy_prepare(px, active);        // no-op unless the launch knobs changed since cfd_create
+    if (rc) return rc;
+    q.order = px->d_xy_order;
     const size_t smem = (size_t)warps * per_warp + 1024;
     auto kern = stream_kernel_xy<NSLOT>;
     static size_t configured[MAX_DEVICES] = {0};
@@ -742,7 +769,7 @@ extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double 
     if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "cfd_apply_xy serves unpartitioned x / y lines");
     if (f == dfdx || f == dfdy || dfdx == dfdy) return fail(CFD_EINVAL, "f, dfdx, dfdy must be three different fields");
     const long nitems = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
-    if (px->g.ny % CH != 0 || nitems > 0x7fffffffL || getenv("CFD_NO_XY")) {
+    if (!xy_eligible(px->g) || getenv("CFD_NO_XY")) {
         int rc = cfd_apply(px, f, dfdx, nullptr, nullptr, stream);
         if (rc) return rc;
         return cfd_apply(py, f, dfdy, nullptr, nullptr, stream);
