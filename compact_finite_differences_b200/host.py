@@ -19,11 +19,13 @@ from .compact import CompactFiniteDifferenceSolver
 
 
 class HostGradient:
-    def __init__(self, shape, spacings, slabs=8, device=None):
+    def __init__(self, shape, spacings, slabs=8, device=None, ddz=None):
         """
         :param shape: (nz, ny, nx)
         :param spacings: (dx, dy, dz)
         :param slabs: number of z-slabs the transfers are pipelined in (nz is split as evenly as possible)
+        :param ddz: optional d/dz operator `ddz(f, out)` for the resident block, e.g. a ZPartitionedDerivative when
+                    this block is one rank's slab of a z-partitioned field (d/dx, d/dy never leave the slab)
         """
         self.shape = tuple(int(s) for s in shape)
         nz, ny, nx = self.shape
@@ -37,7 +39,7 @@ class HostGradient:
             if (b - a) not in self._solvers:
                 s = CompactFiniteDifferenceSolver((b - a, ny, nx))
                 self._solvers[b - a] = s
-        self._z = CompactFiniteDifferenceSolver(self.shape, self.dz, 2)
+        self._z = ddz if ddz is not None else CompactFiniteDifferenceSolver(self.shape, self.dz, 2)
         with torch.cuda.device(self.device):
             self._f = torch.empty(self.shape, dtype=torch.float64, device=self.device)
             self._d = [torch.empty(self.shape, dtype=torch.float64, device=self.device) for _ in range(3)]

@@ -132,19 +132,27 @@ class PeerExchange:
         return self.buf[o:o + n * self.plane]
 
 
-class ZPartitionedDerivative:
-    """Derivative of a z-partitioned field; `local_shape` is this rank's slab [nz/P, ny, nx]."""
+class PartitionedDerivative:
+    """
+    Derivative along `direction` of one block of a field whose lines along `direction` are cut into `size` blocks,
+    one per rank of `group` (the reference's line communicator, code/cuda/gpuDA.py:154-180 `get_line_DA`; its dfdx
+    runs on exactly such a line, code/cuda/compact.py:18-27).  `local_shape` is this rank's block [nz, ny, nx]; the
+    rank order inside `group` is the block order along the line.  With a Cartesian process grid (grid.DA) every
+    direction gets its own line groups; ZPartitionedDerivative below is the z-slab special case of BASELINE configs[3].
+    """
+    _part_axis = None               # None: the partitioned axis is `direction` itself
 
     def __init__(self, local_shape, spacing, direction, group=None, mode="fused", comm="allgather"):
         """
         mode "fused"     : edge faces -> exchange -> ONE coupled kernel (final derivative, no correction pass)
              "reference" : local solve -> pack -> all-gather -> correction sweep (the reference's order)
         comm "allgather" : every rank receives all 2P interface planes (the reference's Gather+Scatter, rootless)
-             "pairwise"  : one interface plane from each z-neighbour by NCCL send/recv (exact in fp64 for slabs
-                           >= 64 planes; fused mode only)
+             "pairwise"  : one interface plane from each line neighbour by NCCL send/recv (exact in fp64 for blocks
+                           >= 64 rows; fused mode only)
              "nvlink"    : the same neighbour-only data flow, but the kernels store halo and interface planes
                            straight into the neighbours' memory over NVLink/NVSwitch (symmetric memory) and
-                           synchronise with flags -- no NCCL call on the data path (fused mode only)
+                           synchronise with flags -- no NCCL call on the data path (fused mode, z lines only:
+                           their boundary planes are contiguous; other directions use "pairwise")
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
@@ -152,24 +160,48 @@ class ZPartitionedDerivative:
         self.size = dist.get_world_size(group)
         self.direction = int(direction)
         self.local_shape = tuple(int(s) for s in local_shape)
-        part = (self.rank, self.size) if self.direction == 2 else (0, 1)
+        part = (self.rank, self.size) if self._partitioned else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
         assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink")
         self._peer = None
-        self.mode = mode if self.local_shape[0] >= 66 else "reference"
+        self.mode = mode if self.local_shape[self._dim] >= 66 else "reference"
         self.comm = comm if self.mode == "fused" else "allgather"
+        if self.comm == "nvlink" and self._dim != 0:
+            self.comm = "pairwise"
         self._buf = None
         self._side = None          # (stream, event) of an exchange started early by begin()
         self._pending = None
 
+    # -- geometry of the line ------------------------------------------------------------------------------
+    @property
+    def _partitioned(self):
+        axis = self.direction if self._part_axis is None else self._part_axis
+        return axis == self.direction
+
+    @property
+    def _dim(self):
+        """Tensor dimension of [nz, ny, nx] the derivative runs along (direction 0 = x = last dimension)."""
+        return 2 - self.direction
+
+    @property
+    def plane_shape(self):
+        """Shape of one boundary plane: the block with the derivative axis removed (one value per line)."""
+        return tuple(s for d, s in enumerate(self.local_shape) if d != self._dim)
+
+    def _ends(self, f):
+        """First and last plane of the block along the line, contiguous (z planes are views, x / y planes are packed:
+        the face packs of code/cuda/gpuDA.py:76-83)."""
+        first, last = f.select(self._dim, 0), f.select(self._dim, f.shape[self._dim] - 1)
+        return first.contiguous(), last.contiguous()
+
     def _buffers(self, f):
         if self._buf is None or self._buf[0].device != f.device:
-            nz, ny, nx = self.local_shape
+            ps = self.plane_shape
             mk = lambda *s: torch.empty(s, dtype=torch.float64, device=f.device)  # noqa: E731
-            pv, own = self.solver.nb_layout() if self.size > 1 and self.direction == 2 else (1, 0)
-            faces_nb = torch.zeros((2 * pv, ny, nx), dtype=torch.float64, device=f.device)
-            self._buf = (mk(ny, nx), mk(ny, nx), mk(2, ny, nx), mk(2 * self.size, ny, nx), faces_nb, pv, own)
-            self._ab = mk(2, ny, nx)
+            pv, own = self.solver.nb_layout() if self.size > 1 and self._partitioned else (1, 0)
+            faces_nb = torch.zeros((2 * pv,) + ps, dtype=torch.float64, device=f.device)
+            self._buf = (mk(*ps), mk(*ps), mk(2, *ps), mk(2 * self.size, *ps), faces_nb, pv, own)
+            self._ab = mk(2, *ps)
         return self._buf
 
     def _exchange_nvlink(self, f):
@@ -235,7 +267,8 @@ class ZPartitionedDerivative:
         if self.comm == "nvlink":
             return self._exchange_nvlink(f)
         lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)
-        halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)
+        first, last = self._ends(f)
+        halo_lo, halo_hi = exchange_halo_planes(first, last, self.rank, self.size, self.group, lo_buf, hi_buf)
         if self.comm == "pairwise":
             self.solver.edge_faces(f, faces_nb[2 * own:2 * own + 2], halo_lo, halo_hi)
             exchange_interface_planes(faces_nb, own, pv, self.rank, self.size, self.group)
@@ -247,10 +280,10 @@ class ZPartitionedDerivative:
         return halo_lo, halo_hi, self._ab
 
     def begin(self, f):
-        """Start the halo / interface exchange of d/dz on a side stream so that it overlaps whatever the caller
-        launches next on the current stream (typically d/dx and d/dy of the same field).  The next __call__ with
-        the same f picks the result up.  No-op where there is nothing to exchange."""
-        if self.direction != 2 or self.size == 1 or self.mode != "fused":
+        """Start the halo / interface exchange on a side stream so that it overlaps whatever the caller launches
+        next on the current stream (typically the derivatives of the same field along the other directions).  The
+        next __call__ with the same f picks the result up.  No-op where there is nothing to exchange."""
+        if not self._partitioned or self.size == 1 or self.mode != "fused":
             return
         if self._side is None:
             self._side = torch.cuda.Stream(device=f.device)
@@ -263,7 +296,7 @@ class ZPartitionedDerivative:
         self._pending = (f.data_ptr(), res, ev)
 
     def __call__(self, f, out=None):
-        if self.direction != 2 or self.size == 1:
+        if not self._partitioned or self.size == 1:
             return self.solver(f, out)
         if self.mode == "fused":
             if self._pending is not None and self._pending[0] == f.data_ptr():
@@ -274,9 +307,16 @@ class ZPartitionedDerivative:
             self._pending = None
             return self.solver.apply_coupled(f, out, halo_lo, halo_hi, planes)
         lo_buf, hi_buf, faces, faces_all = self._buffers(f)[:4]
-        halo_lo, halo_hi = exchange_halo_planes(f[0], f[-1], self.rank, self.size, self.group, lo_buf, hi_buf)
+        first, last = self._ends(f)
+        halo_lo, halo_hi = exchange_halo_planes(first, last, self.rank, self.size, self.group, lo_buf, hi_buf)
         out = self.solver.apply_local(f, out, halo_lo, halo_hi)
         self.solver.interface_pack(out, faces)
         gather_interface_planes(faces, self.size, self.group, faces_all)
         self.solver.reduced_correct(out, faces_all)
         return out
+
+
+class ZPartitionedDerivative(PartitionedDerivative):
+    """Derivative of a z-partitioned field; `local_shape` is this rank's slab [nz/P, ny, nx].  d/dx and d/dy
+    (direction 0, 1) never leave the slab; d/dz is the partitioned line."""
+    _part_axis = 2

@@ -101,6 +101,30 @@ for overlap in (False, True):
     if rank == 0:
         print(f"gradient step (x, y, z) {N}^3 on {world} GPUs, overlap={overlap}: {ms.item():.3f} ms -> "
               f"{3 * N ** 3 / ms.item() * 1e3:.3e} pts/s per derivative", flush=True)
+
+# (c) Cartesian process grids (grid.DA): x-, y- and z-partitioned lines through PartitionedDerivative, field
+#     generated per block on the device with DA_arange, result gathered with DA_gather_blocks and checked on rank 0
+#     against the oracle on the global field (the reference's 2x2x2 test layout, code/cuda/test/test_compact.py:19-57)
+GRIDS = {2: [(1, 1, 2), (1, 2, 1), (2, 1, 1)], 4: [(1, 2, 2), (2, 2, 1), (2, 1, 2)], 8: [(2, 2, 2)]}.get(world, [])
+local = (68, 72, 80)
+for proc_sizes in GRIDS:
+    da = C.DA(None, local, proc_sizes)
+    x, y, z = C.DA_arange(da, (0.0, 2 * np.pi), (0.0, 2 * np.pi), (0.0, 2 * np.pi), device=dev)
+    fb = (x * torch.cos(x * y) + y * torch.sin(z)).contiguous()          # reference demo field, run.py:29-30
+    NZ, NY, NX = da.global_dims
+    hs = (2 * np.pi / (NX - 1), 2 * np.pi / (NY - 1), 2 * np.pi / (NZ - 1))
+    fg = C.DA_gather_blocks(da, fb)
+    for direction in range(3):
+        for mode, comm in (("fused", "pairwise"), ("fused", "allgather"), ("reference", "allgather")):
+            if da.line(direction)[2] == 1 and (mode, comm) != ("fused", "pairwise"):
+                continue
+            op = da.derivative(direction, hs[direction], mode=mode, comm=comm)
+            got = C.DA_gather_blocks(da, op(fb))
+            err = 0.0
+            if rank == 0:
+                want = O.derivative(fg.cpu().numpy(), direction, hs[direction])
+                err = float(np.abs(got.cpu().numpy() - want).max() / np.abs(want).max())
+            report(f"process grid {proc_sizes} local {local} d/d{'xyz'[direction]} {mode}/{comm} vs oracle", err)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

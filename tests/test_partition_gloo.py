@@ -112,12 +112,29 @@ class _OracleBlockSolver:
     orchestration of ZPartitionedDerivative (mode / comm switching, buffers, call order) can run under gloo.
     Test-only: the product class always talks to libcfd_b200."""
 
-    def __init__(self, local_shape, h, rank, size):
+    def __init__(self, local_shape, h, rank, size, direction=2):
         from oracle import cfd_oracle as O
         self.O, self.shape, self.h, self.rank, self.size = O, tuple(local_shape), h, rank, size
-        self.n = local_shape[0]
+        self.direction, self.spacing = direction, h
+        self.ax = 2 - direction                    # tensor dimension of the line
+        self.n = local_shape[self.ax]
         self.co = O.partition_local_coeffs(rank, size)
-        self.direction, self.spacing = 2, h
+
+    def _first(self, a):
+        return np.take(a, 0, axis=self.ax)
+
+    def _last(self, a):
+        return np.take(a, self.n - 1, axis=self.ax)
+
+    def _along(self, v):
+        """A per-row vector shaped to broadcast along the line axis of the block."""
+        sh = [1, 1, 1]
+        sh[self.ax] = self.n
+        return v.reshape(sh)
+
+    def _planes(self, p):
+        """A per-line plane shaped to broadcast over the rows of the block."""
+        return np.expand_dims(np.asarray(p), self.ax)
 
     def nb_layout(self):
         lo = self.rank - 1 if self.rank > 0 else self.rank
@@ -126,10 +143,12 @@ class _OracleBlockSolver:
 
     def _local(self, f, lo, hi):
         O = self.O
-        rr = O.rhs(f.numpy(), 2, self.h, halo_lo=None if lo is None else lo.numpy(),
+        rr = O.rhs(f.numpy(), self.direction, self.h, halo_lo=None if lo is None else lo.numpy(),
                    halo_hi=None if hi is None else hi.numpy())
         a, b, c = O.banded_abc(self.n, self.co)
-        return rr, O.scipy_solve_banded(a, b, c, rr.reshape(self.n, -1)).reshape(rr.shape)
+        rows_first = np.moveaxis(rr, self.ax, 0)
+        x = O.scipy_solve_banded(a, b, c, rows_first.reshape(self.n, -1)).reshape(rows_first.shape)
+        return rr, np.ascontiguousarray(np.moveaxis(x, 0, self.ax))
 
     def apply_local(self, f, out, lo, hi):
         out = torch.empty_like(f) if out is None else out
@@ -138,13 +157,13 @@ class _OracleBlockSolver:
 
     def edge_faces(self, f, faces, lo=None, hi=None):
         xr = self._local(f, lo, hi)[1]
-        faces[0] = 0.0 if self.rank == 0 else torch.from_numpy(-xr[0])
-        faces[1] = 0.0 if self.rank == self.size - 1 else torch.from_numpy(-xr[-1])
+        faces[0] = 0.0 if self.rank == 0 else torch.from_numpy(-self._first(xr))
+        faces[1] = 0.0 if self.rank == self.size - 1 else torch.from_numpy(-self._last(xr))
         return faces
 
     def interface_pack(self, df, faces):
-        faces[0] = 0.0 if self.rank == 0 else -df[0]
-        faces[1] = 0.0 if self.rank == self.size - 1 else -df[-1]
+        faces[0] = 0.0 if self.rank == 0 else torch.from_numpy(-self._first(df.numpy()))
+        faces[1] = 0.0 if self.rank == self.size - 1 else torch.from_numpy(-self._last(df.numpy()))
         return faces
 
     def _unknowns(self, faces, neighbours_only):
@@ -172,7 +191,7 @@ class _OracleBlockSolver:
         O = self.O
         xu, xl = O.partition_secondary(self.n, self.rank, self.size)
         xr = self._local(f, lo, hi)[1]
-        res = xr + ab[0].numpy() * xu[:, None, None] + ab[1].numpy() * xl[:, None, None]
+        res = xr + self._planes(ab[0].numpy()) * self._along(xu) + self._planes(ab[1].numpy()) * self._along(xl)
         out = torch.empty_like(f) if out is None else out
         out.copy_(torch.from_numpy(res))
         return out
@@ -181,7 +200,7 @@ class _OracleBlockSolver:
         O = self.O
         al, be = self._unknowns(faces_all, False)
         xu, xl = O.partition_secondary(self.n, self.rank, self.size)
-        df += torch.from_numpy(al * xu[:, None, None] + be * xl[:, None, None])
+        df += torch.from_numpy(self._planes(al) * self._along(xu) + self._planes(be) * self._along(xl))
         return df
 
 
@@ -221,5 +240,91 @@ def test_partitioned_derivative_orchestration_gloo(world):
     port = _free_port()
     ret = mp.Manager().dict()
     mp.spawn(_worker_class, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r] < 1e-13, f"rank {r}: rel L-inf {ret[r]}"
+
+
+# ---------------------------------------------------------------------------------------------------
+# Cartesian process grids (grid.DA): line groups, DA_arange, block gather / scatter, derivatives along x and y lines
+# ---------------------------------------------------------------------------------------------------
+def _worker_grid(rank, world, port, proc_sizes, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import cfd_oracle as O
+        from compact_finite_differences_b200.grid import DA, DA_arange, DA_gather_blocks, DA_scatter_blocks
+        from compact_finite_differences_b200.partition import PartitionedDerivative
+
+        local = (70, 68, 66)
+        da = DA(None, local, proc_sizes)
+        npz, npy, npx = proc_sizes
+        assert (da.mz, da.my, da.mx) == np.unravel_index(rank, proc_sizes)          # MPI_Cart row-major coordinates
+        for direction, m, n in ((0, da.mx, npx), (1, da.my, npy), (2, da.mz, npz)):
+            lda = da.get_line_DA(direction)
+            assert (lda.rank, lda.size, lda.direction) == (m, n, direction)
+            g, r, sz = da.line(direction)
+            if sz > 1:                                         # the line group really is the line: sum of coordinates
+                t = torch.tensor([float(rank)])
+                dist.all_reduce(t, group=g)
+                idx = [da.mz, da.my, da.mx]
+                want = 0
+                for k in range(sz):
+                    idx[2 - direction] = k
+                    want += int(np.ravel_multi_index(idx, proc_sizes))
+                assert int(t.item()) == want
+
+        # DA_arange: the blocks tile the global linspace grid (gpuDA.py:402-432; test_misc.py:15-28)
+        x, y, z = DA_arange(da, (0, 1), (0, 2), (0, 3))
+        NZ, NY, NX = da.global_dims
+        gz, gy, gx = np.meshgrid(np.linspace(0, 3, NZ), np.linspace(0, 2, NY), np.linspace(0, 1, NX), indexing="ij")
+        z0, y0, x0 = da.block_start
+        sl = (slice(z0, z0 + local[0]), slice(y0, y0 + local[1]), slice(x0, x0 + local[2]))
+        assert np.allclose(x, gx[sl], atol=1e-14) and np.allclose(y, gy[sl], atol=1e-14) and np.allclose(z, gz[sl], atol=1e-14)
+        xt, yt, zt = DA_arange(da, (0, 1), (0, 2), (0, 3), device="cpu")
+        assert np.allclose(xt.numpy(), x, atol=1e-14) and np.allclose(zt.numpy(), z, atol=1e-14)
+
+        # scatter / gather round trip of a global field held by rank 0
+        rng = np.random.default_rng(5)
+        f = rng.random(da.global_dims)                      # same on every rank (seeded)
+        blk = torch.empty(local, dtype=torch.float64)
+        DA_scatter_blocks(da, torch.from_numpy(f) if rank == 0 else None, blk)
+        assert np.array_equal(blk.numpy(), f[sl])
+        back = DA_gather_blocks(da, blk)
+        if rank == 0:
+            assert np.array_equal(back.numpy(), f)
+        else:
+            assert back is None
+
+        # derivative along every direction through the line groups, block kernels replaced by the oracle
+        worst = 0.0
+        for direction in range(3):
+            h = 0.1 + 0.03 * direction
+            g, r, sz = da.line(direction)
+            want = O.derivative(f, direction, h)[sl]
+            if sz == 1:
+                continue                                     # a local line: CompactFiniteDifferenceSolver, GPU tests
+            for mode, comm in (("fused", "pairwise"), ("fused", "allgather"), ("reference", "allgather")):
+                op = PartitionedDerivative.__new__(PartitionedDerivative)
+                op.group, op.rank, op.size, op.direction = g, r, sz, direction
+                op.local_shape = local
+                op.solver = _OracleBlockSolver(local, h, r, sz, direction)
+                op.mode, op.comm = mode, comm
+                op._buf, op._side, op._pending, op._peer = None, None, None, None
+                got = op(blk).numpy()
+                worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
+        ret[rank] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("proc_sizes", [(1, 2, 2), (2, 1, 2)])
+def test_process_grid_gloo(proc_sizes):
+    """grid.DA on a 2-D process grid (4 ranks): coordinates, line groups, DA_arange, scatter / gather of blocks and
+    PartitionedDerivative along the partitioned directions (the reference runs 2x2x2, code/cuda/test/Makefile:9)."""
+    world = int(np.prod(proc_sizes))
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_grid, args=(world, port, proc_sizes, ret), nprocs=world, join=True)
     for r in range(world):
         assert ret[r] < 1e-13, f"rank {r}: rel L-inf {ret[r]}"
