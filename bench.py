@@ -334,12 +334,25 @@ def run_ours(args):
     f_host = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
     f_host.copy_(f)
     out_host = [torch.empty(f.shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
-    # HostGradient: H2D in z-slabs, fused d/dx + d/dy per slab, D2H overlapping the remaining H2D, then d/dz + D2H
-    # (at N > 1 each rank pipelines its own slab of the 1024^3 field and d/dz is the partitioned operator)
-    hg = C.HostGradient((nz_loc, N, N), (h, h, h), slabs=8, ddz=ddz if world > 1 else None)
+    # "pipelined" = HostGradient: H2D in z-slabs, fused d/dx + d/dy per slab, D2H overlapping the remaining H2D, then
+    # d/dz + D2H (at N > 1 each rank pipelines its own slab and d/dz is the partitioned operator).  "sequential" =
+    # H2D, gradient, D2H one after the other.  Measured: pipelined wins on one GPU (62.7 vs ~78 ms per step); with two
+    # ranks on one host the concurrent H2D + D2H of both slow each other down (412 vs 370 ms) -> sequential at N > 1.
+    e2e_mode = args.e2e if args.e2e != "auto" else ("pipelined" if world == 1 else "sequential")
+    if e2e_mode == "pipelined":
+        hg = C.HostGradient((nz_loc, N, N), (h, h, h), slabs=8, ddz=ddz if world > 1 else None)
 
-    def e2e_step():
-        hg(f_host, out_host)
+        def e2e_step():
+            hg(f_host, out_host)
+    else:
+        f_in = torch.empty_like(f)
+
+        def e2e_step():
+            f_in.copy_(f_host, non_blocking=True)
+            gradient(f_in)
+            for a in range(3):
+                out_host[a].copy_(df[a], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     e2e_step()
     fence()
@@ -395,7 +408,8 @@ def run_ours(args):
             "config": workload_config(world, args.comm, not args.no_overlap),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": f.numel() * 8 * world,
-                    "d2h_bytes_per_step": 3 * f.numel() * 8 * world, "steps": e2e_steps, "verified": e2e_ok},
+                    "d2h_bytes_per_step": 3 * f.numel() * 8 * world, "steps": e2e_steps, "verified": e2e_ok,
+                    "mode": e2e_mode},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -419,6 +433,8 @@ def main():
                     help="exchange of the partitioned d/dz: NVLink peer-memory stores from our kernels, NCCL send/recv per "
                          "z-neighbour, or NCCL all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="do not start the d/dz exchange before d/dx, d/dy")
+    ap.add_argument("--e2e", default="auto", choices=["auto", "pipelined", "sequential"],
+                    help="host-buffer leg: HostGradient slab pipeline, or H2D -> gradient -> D2H in sequence")
     ap.add_argument("--separate", action="store_true", help="d/dx and d/dy as two launches instead of cfd_apply_xy")
     args = ap.parse_args()
     _reserve_stdout()
