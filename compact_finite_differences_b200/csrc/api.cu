@@ -657,6 +657,8 @@ static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *
     return CFD_OK;
 }
 
+static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_t stream);
+
 static int apply_impl(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
                       const double *ab, void *stream)
 {
@@ -667,6 +669,9 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     MapPair mp;
     int rc = get_maps(p->cache, p->g, f, df, mp);
     if (rc) return rc;
+    // Experiment switch (CFD_RING_STAGING=1): whole, unpartitioned lines through the ring-staged kernel of
+    // kernels_xy.cuh with one direction empty -- 32 KiB per warp, 6 warps per SM instead of 40 KiB and 4.
+    if (p->size == 1 && !ab && getenv("CFD_RING_STAGING")) return launch_one_direction_ring(p, mp, (cudaStream_t)stream);
     KParams kp = p->kp;
     kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
     kp.ab = ab; kp.nlines = p->g.nlines;
@@ -755,6 +760,38 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     long blocks = (q.nitems + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
     kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_t stream)
+{
+    static DeviceInfo dinfo;
+    int rc;
+    if (!dinfo.ok) { rc = device_info(dinfo); if (rc) return rc; }
+    constexpr int NSLOT = 4;
+    constexpr int per_warp = NSLOT * SLOT_BYTES + NSLOT * 16;
+    if (p->g.nb > 0x7fffffffL) return fail(CFD_EUNSUPPORTED, "too many bundles");
+    XYParams q;
+    q.nxp = p->g.contig ? (int)p->g.nb : 0;
+    q.nyp = p->g.contig ? 0 : p->g.inner_tiles;
+    q.nitems = p->g.nb;
+    q.order = nullptr;
+    int warps = g_warps ? g_warps : 6;
+    if (warps > 7) warps = 7;
+    const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
+    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    const size_t smem = (size_t)warps * per_warp + 1024;
+    auto kern = stream_kernel_xy<NSLOT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * per_warp + 1024));
+    rc = counter_pair(&q.counter);
+    if (rc) return rc;
+    KParams k = p->kp;
+    k.ab = nullptr;
+    long blocks = (q.nitems + warps - 1) / warps;
+    if (blocks > dinfo.sms) blocks = dinfo.sms;
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mp.tm_in, mp.tm_out, mp.tm_in, mp.tm_out, k, k, q);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
