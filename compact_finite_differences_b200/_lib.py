@@ -20,6 +20,7 @@ SIGNATURES = {
     "cfd_destroy": (None, [_vp]),
     "cfd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_apply_xy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_plan_set_xy_warps": (_i, [_vp, _i]),
     "cfd_compute_rhs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_plan_coeffs": (_i, [_vp, _dp]),
     "cfd_sum_solutions": (_i, [_vp, _vp, _vp, _vp, _vp]),

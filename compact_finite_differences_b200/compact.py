@@ -141,10 +141,14 @@ class CompactFiniteDifferenceSolver:
         planes of f where this block does not own the physical end."""
         return self._apply(self.direction, self.spacing, f, out, halo_lo, halo_hi)
 
-    def dfdxy(self, f, dx, dy, out_x=None, out_y=None):
-        """d/dx and d/dy of f in ONE launch (cfd_apply_xy): the two derivatives share the HBM reads of f through L2."""
+    def dfdxy(self, f, dx, dy, out_x=None, out_y=None, warps=None):
+        """d/dx and d/dy of f in ONE launch (cfd_apply_xy): the two derivatives share the HBM reads of f through L2.
+        warps: warps per SM of the launch (None = library default); 5 leaves room for kernels running beside it."""
         import torch
         px, py = self._plan(0, float(dx)), self._plan(1, float(dy))
+        if warps is not None and getattr(px, "xy_warps", None) != warps:
+            check(lib().cfd_plan_set_xy_warps(px.handle, int(warps)))
+            px.xy_warps = warps
         assert f.is_cuda and f.dtype == torch.float64 and f.is_contiguous() and tuple(f.shape) == self.shape
         out_x = torch.empty_like(f) if out_x is None else out_x
         out_y = torch.empty_like(f) if out_y is None else out_y

@@ -308,6 +308,7 @@ struct cfd_plan {
     std::mutex xy_mu;
     int *d_xy_order = nullptr;
     double xy_active = -1.0;
+    int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
 };
 
 struct nt_plan {
@@ -488,12 +489,12 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
 }
 
 // Default launch shape of stream_kernel_xy and the planes-in-flight figure that goes with it.
-static void xy_shape(const Geometry &gx, int sms, int nslot, int &warps, double &active)
+static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int &warps, double &active)
 {
     const int max_warps = nslot == 3 ? 8 : 7, def_warps = nslot == 3 ? 8 : 6;
     const int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
     const long nitems = (long)gx.nz * (gx.ny / CH + (gx.nx + CH - 1) / CH);
-    warps = g_warps ? g_warps : def_warps;
+    warps = g_warps ? g_warps : (plan_warps ? plan_warps : def_warps);
     if (warps > max_warps) warps = max_warps;
     const long per_sm = (nitems + sms - 1) / sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
@@ -579,7 +580,7 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
         int warps = 0;
         double active = 0.0;
         rc = device_info(di);
-        if (!rc) { xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, warps, active); rc = xy_prepare(p, active); }
+        if (!rc) { xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active); rc = xy_prepare(p, active); }
         if (rc) { cfd_destroy(p); return rc; }
     }
     *out = p;
@@ -656,6 +657,7 @@ static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *
     m.tm_in = c.tm_in; m.tm_out = c.tm_out;
     return CFD_OK;
 }
+
 
 static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_t stream);
 
@@ -739,7 +741,7 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.nitems = nitems;
     int warps = 0;
     double active = 0.0;
-    xy_shape(px->g, dinfo.sms, NSLOT, warps, active);
+    xy_shape(px->g, dinfo.sms, NSLOT, px->xy_warps, warps, active);
     rc = xy_prepare(px, active);        // no-op unless the launch knobs changed since cfd_create
     if (rc) return rc;
     q.order = px->d_xy_order;
@@ -794,6 +796,27 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mp.tm_in, mp.tm_out, mp.tm_in, mp.tm_out, k, k, q);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
+// Warps per SM of the fused x/y launch for this (axis-0) plan.  Callers that run other kernels BESIDE the launch --
+// the exchange chain of a partitioned d/dz -- take 5 instead of the default 6 to leave registers for them
+// (scripts/overlap_timeline.py: 1.108 vs 1.133 ms per step on [128,1024,1024] slabs).  The draw order is rebuilt here,
+// so cfd_apply_xy itself still allocates nothing.
+extern "C" int cfd_plan_set_xy_warps(cfd_plan *p, int warps_per_sm)
+{
+    if (!p || p->g.axis != 0) return fail(CFD_EINVAL, "cfd_plan_set_xy_warps needs an axis-0 plan");
+    if (warps_per_sm < 0 || warps_per_sm > 8) return fail(CFD_EINVAL, "warps per SM must be 0 (default) .. 8");
+    p->xy_warps = warps_per_sm;
+    if (p->size == 1 && xy_eligible(p->g)) {
+        DeviceInfo di;
+        int warps = 0;
+        double active = 0.0;
+        int rc = device_info(di);
+        if (rc) return rc;
+        xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active);
+        return xy_prepare(p, active);
+    }
     return CFD_OK;
 }
 
@@ -889,7 +912,8 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
         int rc = counter_pair(&ep.done);
         if (rc) return rc;
     }
-    const int bs = 128;
+    int bs = 128;
+    if (const char *e = getenv("CFD_EDGE_BS")) { bs = atoi(e); if (bs < 32 || bs > 128 || bs % 32) bs = 128; }
     edge_faces_kernel<<<(unsigned)((ep.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(f, faces, ep);
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -774,6 +774,11 @@ __device__ __forceinline__ void publish_when_grid_done(unsigned long long *done,
     }
 }
 
+// The 67 rows are read once and must not push the tiles other kernels share through L2 out of it (the exchange chain
+// runs beside the fused d/dx + d/dy launch): streaming (evict-first) loads.
+#ifndef EDGE_LD
+#define EDGE_LD __ldcs
+#endif
 __global__ void __launch_bounds__(128)
 edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, const __grid_constant__ EdgeP p)
 {
@@ -786,7 +791,7 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
     if (active && !p.lo_closure) {
         double F[CH + 1], e[CH];
 #pragma unroll
-        for (int j = 0; j <= CH; j++) F[j] = __ldg(fl + (long)j * st);
+        for (int j = 0; j <= CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
         double fm1 = __ldg(p.halo_lo + line), eprev = 0.0;
 #pragma unroll
         for (int j = 0; j < CH; j++) {
@@ -804,7 +809,7 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         const double *ft = fl + (long)(n - CH - 2) * st;       // rows n-34 .. n-1
         double F[CH + 2];
 #pragma unroll
-        for (int j = 0; j < CH + 2; j++) F[j] = __ldg(ft + (long)j * st);
+        for (int j = 0; j < CH + 2; j++) F[j] = EDGE_LD(ft + (long)j * st);
         const double hval = __ldg(p.halo_hi + line);
         double eprev = 0.0;
 #pragma unroll

@@ -68,6 +68,9 @@ int cfd_apply(cfd_plan *plan, const double *f, double *df, const double *halo_lo
  * that every tile of f comes from HBM once and from L2 the second time.  Replaces two dfdx / dfdy calls of the
  * reference (code/ocl/compact.py:26-50).  Falls back to two launches when ny is not a multiple of 32. */
 int cfd_apply_xy(cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy, void *stream);
+/* Warps per SM of that launch for an axis-0 plan (0 = default 6).  5 leaves room on the SMs for kernels that run
+ * beside it on another stream, e.g. the exchange chain of a partitioned d/dz started before it. */
+int cfd_plan_set_xy_warps(cfd_plan *plan_x, int warps_per_sm);
 
 /* The reference's stages one by one, for callers that drive the path the way dfdx does (compact.py:40-44); the
  * fused entry points above never call them.

@@ -199,6 +199,20 @@ def test_fused_xy_launch_shapes(C, warps, slots):
         C.lib().cfd_set_launch(0, 0, 0)
 
 
+def test_fused_xy_per_plan_warps(C):
+    """cfd_plan_set_xy_warps: the per-plan knob a caller uses to leave room for kernels running beside the launch."""
+    shape = (37, 64, 130)
+    rng = np.random.default_rng(3)
+    f = rng.random(shape)
+    s = C.CompactFiniteDifferenceSolver(shape)
+    for warps in (5, 2, 0, 7):
+        gx, gy = s.dfdxy(dev(f), 0.1, 0.2, warps=warps)
+        assert relinf(gx.cpu().numpy(), O.derivative(f, 0, 0.1)) <= TOL
+        assert relinf(gy.cpu().numpy(), O.derivative(f, 1, 0.2)) <= TOL
+    assert C.lib().cfd_plan_set_xy_warps(s._plan(1, 0.2).handle, 5) == -1       # CFD_EINVAL: not an axis-0 plan
+    assert C.lib().cfd_plan_set_xy_warps(s._plan(0, 0.1).handle, 9) == -1
+
+
 def test_gradient_256_cubed(C):
     """BASELINE configs[1] through gradient(): one fused d/dx + d/dy launch and one d/dz launch, full-field parity."""
     n = 256
