@@ -34,6 +34,8 @@ SIGNATURES = {
     "cfd_push_planes": (_i, [_vp, _vp, _vp, _vp, _l, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_edge_faces_p2p": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_wait_flags": (_i, [_vp, _vp, ctypes.c_ulonglong, _vp]),
+    "cfd_edge_faces_push": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
+    "cfd_reduced_unknowns_deferred": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_apply_host": (_i, [_vp, _vp, _vp, _i]),
     "cfd_plane_elems": (_l, [_vp]),
     "cfd_tables_size": (_i, []),

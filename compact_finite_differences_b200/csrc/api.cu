@@ -309,6 +309,7 @@ struct cfd_plan {
     int *d_xy_order = nullptr;
     double xy_active = -1.0;
     int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
+    double w_lo = 0.0, w_hi = 0.0;    // d(lo face)/d f[-1], d(hi face)/d f[n]: cfd_reduced_unknowns_deferred
 };
 
 struct nt_plan {
@@ -564,6 +565,22 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
         int wc = 0;
         while (wc < n && (std::fabs(p->x_uh[wc]) > 1e-19 || std::fabs(p->x_lh[n - 1 - wc]) > 1e-19)) wc++;
         p->wc = wc;
+        // The interface faces depend linearly on the neighbour points of f (edge_faces_kernel): lo face = -x_0 of
+        // the head solve, where f[-1] enters row 0 only (r_0 = sk_0 (f[1] - f[-1])); hi face = -e_{n-1}, where f[n]
+        // enters through sk_last.  Unit responses, for the exchange that folds the halos in afterwards.  They are
+        // applied to the NEIGHBOURS' faces too, so they come from the tables of an interior block (a block end that
+        // has a neighbour is an interior-type end on every rank), not from this rank's own closures.
+        {
+            KParams ki;
+            rc = fill_tables(ki, p->g, pade_block(1, 3), 3.0 / (4.0 * h), true);
+            if (rc) { cfd_destroy(p); return rc == CFD_ESLOWPATH ? CFD_EUNSUPPORTED : rc; }
+            double e[CH], ep = 0.0;
+            for (int j = 0; j < CH; j++) { ep = -ki.head.l[j] * ep + (j == 0 ? -ki.head.sk[0] : 0.0); e[j] = ep; }
+            double x = 0.0;
+            for (int j = CH - 1; j >= 0; j--) x = e[j] - ki.head.g[j] * x;
+            p->w_lo = -x;
+            p->w_hi = -ki.tail.sk[p->g.jl];
+        }
         if (cudaMalloc(&p->d_x_uh, n * sizeof(double)) != cudaSuccess || cudaMalloc(&p->d_x_lh, n * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&p->d_lu, p->lu.size() * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&p->d_lu_nb, p->lu_nb.size() * sizeof(double)) != cudaSuccess) {
@@ -722,7 +739,8 @@ extern "C" int cfd_nb_layout(const cfd_plan *p, int *virtual_ranks, int *own_ind
 
 static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
                      double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
-                     unsigned long long seq, bool p2p, void *stream);
+                     unsigned long long seq, bool p2p, void *stream, bool defer = false, double *push_lo = nullptr,
+                     double *push_hi = nullptr);
 
 template <int NSLOT>
 static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPair &my, long nitems, cudaStream_t stream)
@@ -888,17 +906,45 @@ extern "C" int cfd_wait_flags(const unsigned long long *flag0, const unsigned lo
     return CFD_OK;
 }
 
+extern "C" int cfd_edge_faces_push(cfd_plan *p, const double *f, double *faces, double *peer_face_lo,
+                                   double *peer_face_hi, double *peer_halo_lo, double *peer_halo_hi,
+                                   unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long seq,
+                                   void *stream)
+{
+    return edge_impl(p, f, nullptr, nullptr, faces, peer_face_lo, peer_face_hi, flag_lo, flag_hi, seq, true, stream,
+                     true, peer_halo_lo, peer_halo_hi);
+}
+
+extern "C" int cfd_reduced_unknowns_deferred(cfd_plan *p, const double *faces_nb, const double *halo_lo,
+                                             const double *halo_hi, const double *f, double *ab,
+                                             const unsigned long long *flag0, const unsigned long long *flag1,
+                                             unsigned long long seq, void *stream)
+{
+    if (!p || !faces_nb || !f || !ab) return fail(CFD_EINVAL, "NULL argument");
+    if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no interfaces");
+    if (p->g.n < 2 * CH + 2) return fail(CFD_EUNSUPPORTED, "neighbour-only coupling needs >= %d rows per block", 2 * CH + 2);
+    if ((p->rank > 0) != (halo_lo != nullptr) || (p->rank < p->size - 1) != (halo_hi != nullptr))
+        return fail(CFD_EINVAL, "rank %d of %d: halo_lo / halo_hi must be given exactly where a neighbour exists", p->rank, p->size);
+    const int bs = 256;
+    reduced_planes_deferred_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        faces_nb, p->d_lu_nb, p->g.nlines, p->nb_pv, p->nb_own, ab, halo_lo, halo_hi, f, p->g.inner, p->g.n,
+        p->w_lo, p->w_hi, flag0, flag1, seq);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
 static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi, double *faces,
                      double *peer_lo, double *peer_hi, unsigned long long *flag_lo, unsigned long long *flag_hi,
-                     unsigned long long seq, bool p2p, void *stream)
+                     unsigned long long seq, bool p2p, void *stream, bool defer, double *push_lo, double *push_hi)
 {
     if (!p || !f || !faces) return fail(CFD_EINVAL, "NULL argument");
     if (p->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: no interfaces");
     if (p->g.n < 2 * CH + 2)
         return fail(CFD_EUNSUPPORTED, "cfd_edge_faces needs >= %d rows per block (have %d): use cfd_apply + "
                     "cfd_interface_pack + cfd_reduced_correct", 2 * CH + 2, p->g.n);
-    if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
-    if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
+    if (!defer && !p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
+    if (!defer && !p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
     EdgeP ep;
     memset(&ep, 0, sizeof ep);
     ep.nlines = p->g.nlines; ep.inner = p->g.inner; ep.n = p->g.n; ep.jl = p->g.jl;
@@ -907,6 +953,9 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
     ep.sk_last = p->kp.tail.sk[p->g.jl]; ep.l_last = p->kp.tail.l[p->g.jl];
     ep.halo_lo = halo_lo; ep.halo_hi = halo_hi;
     ep.head = p->kp.head;
+    ep.defer = defer ? 1 : 0;
+    ep.push_lo = p->kp.lo_closure ? nullptr : push_lo;
+    ep.push_hi = p->kp.hi_closure ? nullptr : push_hi;
     if (p2p) {
         ep.peer_lo = peer_lo; ep.peer_hi = peer_hi; ep.flag_lo = flag_lo; ep.flag_hi = flag_hi; ep.seq = seq;
         int rc = counter_pair(&ep.done);

@@ -734,6 +734,47 @@ reduced_planes_kernel(const double *__restrict__ faces, const double *__restrict
     ab[nlines + line] = beta;
 }
 
+// The same for the one-launch exchange (cfd_edge_faces_push + cfd_reduced_unknowns_deferred): the four faces of the
+// neighbour-only system that involve a block boundary were computed without the neighbour point of f; add it here,
+// from planes this rank owns (its own first / last row: the neighbours' missing points) or has received (its halos).
+//   own lo face += w_lo * f[-1]      left neighbour's hi face += w_hi * (our row 0)
+//   own hi face += w_hi * f[n]       right neighbour's lo face += w_lo * (our row n-1)
+__global__ void __launch_bounds__(256)
+reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *__restrict__ lu, long nlines, int pv,
+                               int own, double *__restrict__ ab, const double *__restrict__ halo_lo,
+                               const double *__restrict__ halo_hi, const double *__restrict__ f, long inner, int n,
+                               double w_lo, double w_hi, const unsigned long long *flag0,
+                               const unsigned long long *flag1, unsigned long long seq)
+{
+    if (flag0 || flag1) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+            if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+        }
+        __syncthreads();
+    }
+    const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nlines) return;
+    double v[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) v[i] = (i < 2 * pv) ? faces[(long)i * nlines + line] : 0.0;
+    const long o = line / inner, col = line % inner;
+    const double *fl = f + (o * n) * inner + col;
+    if (halo_lo) {                                       // there is a left neighbour
+        v[2 * own] += w_lo * halo_lo[line];
+        v[2 * own - 1] += w_hi * fl[0];
+    }
+    if (halo_hi) {                                       // there is a right neighbour
+        v[2 * own + 1] += w_hi * halo_hi[line];
+        v[2 * own + 2] += w_lo * fl[(long)(n - 1) * inner];
+    }
+    double alpha, beta;
+    reduced_unknowns(v, lu, 1, 0, pv, own, alpha, beta);
+    ab[line] = alpha;
+    ab[nlines + line] = beta;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Interface planes straight from f, WITHOUT the block solve: faces[0] = -x_R[0], faces[1] = -x_R[n-1]
 // (what negateAndCopyFaces, code/cuda/kernels.cu:76-113, extracts after the reference's full local solve).
@@ -754,6 +795,11 @@ struct EdgeP {
     unsigned long long *flag_lo, *flag_hi;     // arrival flags in the neighbours' memory
     unsigned long long *done;                  // local CTA counter (zero on entry, zero on exit)
     unsigned long long seq;
+    // One-launch exchange (cfd_edge_faces_push): the neighbour points of f are not known yet -- the faces are
+    // computed with f[-1] = f[n] = 0 (they enter LINEARLY, with plan-time weights: the consumer adds w * halo later,
+    // reduced_planes_deferred_kernel) and this rank's own first / last row is stored into the neighbours' halo slots.
+    int defer;
+    double *push_lo, *push_hi;                 // left neighbour's slot for our row 0, right neighbour's for our row n-1
     RowTab head;
 };
 
@@ -792,7 +838,8 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         double F[CH + 1], e[CH];
 #pragma unroll
         for (int j = 0; j <= CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
-        double fm1 = __ldg(p.halo_lo + line), eprev = 0.0;
+        double fm1 = p.defer ? 0.0 : __ldg(p.halo_lo + line), eprev = 0.0;
+        if (p.push_lo) p.push_lo[line] = F[0];            // our first row = the left neighbour's f[n]
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             eprev = fma(-p.head.l[j], eprev, p.head.sk[j] * (F[j + 1] - fm1));
@@ -810,7 +857,8 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         double F[CH + 2];
 #pragma unroll
         for (int j = 0; j < CH + 2; j++) F[j] = EDGE_LD(ft + (long)j * st);
-        const double hval = __ldg(p.halo_hi + line);
+        const double hval = p.defer ? 0.0 : __ldg(p.halo_hi + line);
+        if (p.push_hi) p.push_hi[line] = F[CH + 1];       // our last row = the right neighbour's f[-1]
         double eprev = 0.0;
 #pragma unroll
         for (int j = 1; j <= CH; j++)                           // rows n-33 .. n-2

@@ -152,7 +152,10 @@ class PartitionedDerivative:
              "nvlink"    : the same neighbour-only data flow, but the kernels store halo and interface planes
                            straight into the neighbours' memory over NVLink/NVSwitch (symmetric memory) and
                            synchronise with flags -- no NCCL call on the data path (fused mode, z lines only:
-                           their boundary planes are contiguous; other directions use "pairwise")
+                           their boundary planes are contiguous; other directions use "pairwise").  ONE producer
+                           launch (cfd_edge_faces_push: faces without the neighbour points + own boundary rows into
+                           the neighbours' buffers) and one consumer (cfd_reduced_unknowns_deferred: folds the halo
+                           terms in); "nvlink-2step" keeps the first protocol (halo push, wait, edge faces, reduce)
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
@@ -162,7 +165,10 @@ class PartitionedDerivative:
         self.local_shape = tuple(int(s) for s in local_shape)
         part = (self.rank, self.size) if self._partitioned else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
-        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink")
+        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink", "nvlink-2step")
+        self._two_step = comm == "nvlink-2step"     # halo push + wait before the edge kernel (the first protocol)
+        if self._two_step:
+            comm = "nvlink"
         self._peer = None
         self.mode = mode if self.local_shape[self._dim] >= 66 else "reference"
         self.comm = comm if self.mode == "fused" else "allgather"
@@ -218,6 +224,28 @@ class PartitionedDerivative:
         stream = ctypes.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)
         left, right = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
         L = lib()
+        if not getattr(self, "_two_step", False):
+            halo_lo = px.local_halo(par, 0) if left is not None else None
+            halo_hi = px.local_halo(par, 1) if right is not None else None
+            faces_nb = px.local_faces(par, 2 * pv)
+            own_left = 1 if (left is not None and left > 0) else 0
+            plan = self.solver._plan(self.solver.direction, self.solver.spacing)
+            check(L.cfd_edge_faces_push(
+                plan.handle, f.data_ptr(), faces_nb.data_ptr() + 8 * 2 * own * px.plane,
+                px.faces(left, par, 2 * own_left + 2) if left is not None else None,
+                px.faces(right, par, 1) if right is not None else None,
+                px.halo(left, par, 1) if left is not None else None,
+                px.halo(right, par, 0) if right is not None else None,
+                px.flag(left, 3) if left is not None else None, px.flag(right, 2) if right is not None else None,
+                seq, stream))
+            self._buffers(f)
+            check(L.cfd_reduced_unknowns_deferred(
+                plan.handle, faces_nb.data_ptr(),
+                halo_lo.data_ptr() if halo_lo is not None else None,
+                halo_hi.data_ptr() if halo_hi is not None else None, f.data_ptr(), self._ab.data_ptr(),
+                px.flag(r, 2) if left is not None else None, px.flag(r, 3) if right is not None else None,
+                seq, stream))
+            return halo_lo, halo_hi, self._ab
         check(L.cfd_push_planes(
             f[0].data_ptr() if left is not None else None, px.halo(left, par, 1) if left is not None else None,
             f[-1].data_ptr() if right is not None else None, px.halo(right, par, 0) if right is not None else None,

@@ -141,6 +141,22 @@ int cfd_edge_faces_p2p(cfd_plan *plan, const double *f, const double *halo_lo, c
 int cfd_wait_flags(const unsigned long long *flag0, const unsigned long long *flag1, unsigned long long seq,
                    void *stream);
 
+/* The same exchange in ONE producer launch, with no wait before it: the interface faces depend linearly on the
+ * neighbour points of f, so
+ *   cfd_edge_faces_push            computes them with f[-1] = f[n] = 0, stores them locally (faces[0], faces[1]) and into
+ *                                  the neighbours' interface buffers, stores this block's first / last row into the
+ *                                  neighbours' HALO buffers, and raises the neighbours' flags when all of it has landed;
+ *   cfd_reduced_unknowns_deferred  waits for this rank's flags, adds the missing halo terms (plan-time weights) to the
+ *                                  four faces next to this block, and solves the neighbour-only reduced system.
+ * Replaces halo exchange + negateAndCopyFaces + Gather / Scatter of code/cuda/compact.py:46-51,65-126 by two
+ * launches and one point-to-point synchronisation; cfd_apply_coupled then reads the halo buffers as before. */
+int cfd_edge_faces_push(cfd_plan *plan, const double *f, double *faces, double *peer_face_lo, double *peer_face_hi,
+                        double *peer_halo_lo, double *peer_halo_hi, unsigned long long *flag_lo,
+                        unsigned long long *flag_hi, unsigned long long seq, void *stream);
+int cfd_reduced_unknowns_deferred(cfd_plan *plan, const double *faces_nb, const double *halo_lo, const double *halo_hi,
+                                  const double *f, double *ab, const unsigned long long *flag0,
+                                  const unsigned long long *flag1, unsigned long long seq, void *stream);
+
 /* Synchronous host-buffer form of cfd_apply for part_size == 1 (what the reference's OpenCL flavour
  * offers: ndarray in, ndarray out, code/ocl/compact.py:26-61).  Copies f to the device, runs the kernel,
  * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory. */

@@ -54,7 +54,7 @@ full = (torch.sin(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(
 nl = N // world
 ref = C.CompactFiniteDifferenceSolver((N, N, N), h, 2)(full)[rank * nl:(rank + 1) * nl]
 slab = full[rank * nl:(rank + 1) * nl].contiguous()
-COMMS = os.environ.get("CFD_COMMS", "nvlink,pairwise,allgather").split(",")
+COMMS = os.environ.get("CFD_COMMS", "nvlink,nvlink-2step,pairwise,allgather").split(",")
 for mode, comm in [("fused", c) for c in COMMS] + [("reference", "allgather")]:
     op = C.ZPartitionedDerivative((nl, N, N), h, 2, mode=mode, comm=comm)
     got = op(slab)

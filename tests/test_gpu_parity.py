@@ -474,6 +474,65 @@ def test_peer_memory_protocol_one_device(C, P, shape):
         assert relinf(got, want) <= TOL
 
 
+@pytest.mark.parametrize("P,shape", [(2, (132, 12, 34)), (3, (3 * 66, 8, 32)), (4, (4 * 70, 6, 32))])
+def test_one_launch_exchange_one_device(C, P, shape):
+    """comm="nvlink" as ZPartitionedDerivative drives it now: cfd_edge_faces_push (faces without the neighbour points,
+    own boundary rows pushed into the neighbours' halo slots, one flag per side) and cfd_reduced_unknowns_deferred
+    (halo terms folded in with the plan's weights), all P ranks' buffers on one device, three calls (both parities)."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import check, lib
+    L = lib()
+    rng = np.random.default_rng(10 + P)
+    h = 0.23
+    n = shape[0] // P
+    plane = shape[1] * shape[2]
+    solvers = [C.CompactFiniteDifferenceSolver((n,) + shape[1:], h, 2, part=(r, P)) for r in range(P)]
+    bufs = [torch.zeros(16 * plane + 16, dtype=torch.float64, device="cuda") for _ in range(P)]
+    base = [b.data_ptr() for b in bufs]
+    halo = lambda r, par, s: base[r] + 8 * ((par * 2 + s) * plane)              # noqa: E731
+    faces = lambda r, par, i: base[r] + 8 * (4 * plane + (par * 6 + i) * plane)  # noqa: E731
+    flag = lambda r, k: base[r] + 8 * (16 * plane + k)                          # noqa: E731
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seq in (1, 2, 3):
+        f = rng.random(shape)
+        want = O.derivative(f, 2, h)
+        blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
+        par = seq & 1
+        for r in range(P):                         # producers: no wait, no halo needed
+            lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+            pv, own = solvers[r].nb_layout()
+            own_left = 1 if (lf is not None and lf > 0) else 0
+            check(L.cfd_edge_faces_push(solvers[r]._plan(2, h).handle, blocks[r].data_ptr(), faces(r, par, 2 * own),
+                                        faces(lf, par, 2 * own_left + 2) if lf is not None else None,
+                                        faces(rt, par, 1) if rt is not None else None,
+                                        halo(lf, par, 1) if lf is not None else None,
+                                        halo(rt, par, 0) if rt is not None else None,
+                                        flag(lf, 3) if lf is not None else None, flag(rt, 2) if rt is not None else None,
+                                        seq, st))
+        outs = []
+        ab = torch.empty((2, plane), dtype=torch.float64, device="cuda")
+        for r in range(P):                         # consumers
+            lf, rt = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
+            out = torch.empty_like(blocks[r])
+            plan = solvers[r]._plan(2, h)
+            hl = halo(r, par, 0) if lf is not None else None
+            hh = halo(r, par, 1) if rt is not None else None
+            check(L.cfd_reduced_unknowns_deferred(plan.handle, faces(r, par, 0), hl, hh, blocks[r].data_ptr(),
+                                                  ab.data_ptr(), flag(r, 2) if lf is not None else None,
+                                                  flag(r, 3) if rt is not None else None, seq, st))
+            check(L.cfd_apply_coupled(plan.handle, blocks[r].data_ptr(), out.data_ptr(), hl, hh, ab.data_ptr(), st))
+            outs.append(out)
+        torch.cuda.synchronize()
+        for r in range(1, P):                      # the pushed halos are the neighbours' boundary rows, bit for bit
+            got_lo = bufs[r][(par * 2 + 0) * plane:(par * 2 + 1) * plane].cpu().numpy()
+            assert np.array_equal(got_lo, f[r * n - 1].ravel())
+            got_hi = bufs[r - 1][(par * 2 + 1) * plane:(par * 2 + 2) * plane].cpu().numpy()
+            assert np.array_equal(got_hi, f[r * n].ravel())
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert relinf(got, want) <= TOL
+
+
 def test_host_gradient_pipeline(C):
     """HostGradient (pinned host buffers, slab-pipelined copies) == oracle on every direction."""
     import torch
