@@ -737,8 +737,10 @@ reduced_planes_kernel(const double *__restrict__ faces, const double *__restrict
 // The same for the one-launch exchange (cfd_edge_faces_push + cfd_reduced_unknowns_deferred): the four faces of the
 // neighbour-only system that involve a block boundary were computed without the neighbour point of f; add it here,
 // from planes this rank owns (its own first / last row: the neighbours' missing points) or has received (its halos).
-//   own lo face += w_lo * f[-1]      left neighbour's hi face += w_hi * (our row 0)
-//   own hi face += w_hi * f[n]       right neighbour's lo face += w_lo * (our row n-1)
+// Every face was computed with its missing point guessed as the block's own boundary row, which is exactly the
+// plane the other side holds:
+//   own lo face += w_lo * (halo_lo - our row 0)       left neighbour's hi face  += w_hi * (our row 0 - halo_lo)
+//   own hi face += w_hi * (halo_hi - our row n-1)     right neighbour's lo face += w_lo * (our row n-1 - halo_hi)
 __global__ void __launch_bounds__(256)
 reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *__restrict__ lu, long nlines, int pv,
                                int own, double *__restrict__ ab, const double *__restrict__ halo_lo,
@@ -762,12 +764,14 @@ reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *_
     const long o = line / inner, col = line % inner;
     const double *fl = f + (o * n) * inner + col;
     if (halo_lo) {                                       // there is a left neighbour
-        v[2 * own] += w_lo * halo_lo[line];
-        v[2 * own - 1] += w_hi * fl[0];
+        const double d = halo_lo[line] - fl[0];
+        v[2 * own] += w_lo * d;
+        v[2 * own - 1] -= w_hi * d;
     }
     if (halo_hi) {                                       // there is a right neighbour
-        v[2 * own + 1] += w_hi * halo_hi[line];
-        v[2 * own + 2] += w_lo * fl[(long)(n - 1) * inner];
+        const double d = halo_hi[line] - fl[(long)(n - 1) * inner];
+        v[2 * own + 1] += w_hi * d;
+        v[2 * own + 2] -= w_lo * d;
     }
     double alpha, beta;
     reduced_unknowns(v, lu, 1, 0, pv, own, alpha, beta);
@@ -796,8 +800,10 @@ struct EdgeP {
     unsigned long long *done;                  // local CTA counter (zero on entry, zero on exit)
     unsigned long long seq;
     // One-launch exchange (cfd_edge_faces_push): the neighbour points of f are not known yet -- the faces are
-    // computed with f[-1] = f[n] = 0 (they enter LINEARLY, with plan-time weights: the consumer adds w * halo later,
-    // reduced_planes_deferred_kernel) and this rank's own first / last row is stored into the neighbours' halo slots.
+    // computed with the guesses f[-1] := f[0], f[n] := f[n-1] (they enter LINEARLY, with plan-time weights: the
+    // consumer adds w * (halo - guess) later, reduced_planes_deferred_kernel; a zero guess would make the face the
+    // difference of two numbers 1/h times larger) and this rank's own first / last row is stored into the
+    // neighbours' halo slots.
     int defer;
     double *push_lo, *push_hi;                 // left neighbour's slot for our row 0, right neighbour's for our row n-1
     RowTab head;
@@ -838,7 +844,7 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         double F[CH + 1], e[CH];
 #pragma unroll
         for (int j = 0; j <= CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
-        double fm1 = p.defer ? 0.0 : __ldg(p.halo_lo + line), eprev = 0.0;
+        double fm1 = p.defer ? F[0] : __ldg(p.halo_lo + line), eprev = 0.0;
         if (p.push_lo) p.push_lo[line] = F[0];            // our first row = the left neighbour's f[n]
 #pragma unroll
         for (int j = 0; j < CH; j++) {
@@ -857,7 +863,7 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
         double F[CH + 2];
 #pragma unroll
         for (int j = 0; j < CH + 2; j++) F[j] = EDGE_LD(ft + (long)j * st);
-        const double hval = p.defer ? 0.0 : __ldg(p.halo_hi + line);
+        const double hval = p.defer ? F[CH + 1] : __ldg(p.halo_hi + line);
         if (p.push_hi) p.push_hi[line] = F[CH + 1];       // our last row = the right neighbour's f[-1]
         double eprev = 0.0;
 #pragma unroll

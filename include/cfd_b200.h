@@ -143,10 +143,10 @@ int cfd_wait_flags(const unsigned long long *flag0, const unsigned long long *fl
 
 /* The same exchange in ONE producer launch, with no wait before it: the interface faces depend linearly on the
  * neighbour points of f, so
- *   cfd_edge_faces_push            computes them with f[-1] = f[n] = 0, stores them locally (faces[0], faces[1]) and into
+ *   cfd_edge_faces_push            computes them with f[-1] := f[0], f[n] := f[n-1], stores them locally (faces[0], faces[1]) and into
  *                                  the neighbours' interface buffers, stores this block's first / last row into the
  *                                  neighbours' HALO buffers, and raises the neighbours' flags when all of it has landed;
- *   cfd_reduced_unknowns_deferred  waits for this rank's flags, adds the missing halo terms (plan-time weights) to the
+ *   cfd_reduced_unknowns_deferred  waits for this rank's flags, adds the missing terms w * (halo - guess) (plan-time weights) to the
  *                                  four faces next to this block, and solves the neighbour-only reduced system.
  * Replaces halo exchange + negateAndCopyFaces + Gather / Scatter of code/cuda/compact.py:46-51,65-126 by two
  * launches and one point-to-point synchronisation; cfd_apply_coupled then reads the halo buffers as before. */

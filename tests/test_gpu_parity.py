@@ -494,8 +494,11 @@ def test_one_launch_exchange_one_device(C, P, shape):
     faces = lambda r, par, i: base[r] + 8 * (4 * plane + (par * 6 + i) * plane)  # noqa: E731
     flag = lambda r, k: base[r] + 8 * (16 * plane + k)                          # noqa: E731
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for seq in (1, 2, 3):
-        f = rng.random(shape)
+    zz, yy, xx = smooth(shape)
+    for seq in (1, 2, 3, 4):
+        # three random fields, then a smooth one at large amplitude: the faces must not lose digits to the guessed
+        # neighbour points (a zero guess would: the face would be a difference of numbers 1/h times larger)
+        f = rng.random(shape) if seq < 4 else 1e3 * (np.sin(zz) * np.cos(yy) + xx)
         want = O.derivative(f, 2, h)
         blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
         par = seq & 1
@@ -531,6 +534,9 @@ def test_one_launch_exchange_one_device(C, P, shape):
             assert np.array_equal(got_hi, f[r * n].ravel())
         got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
         assert relinf(got, want) <= TOL
+        if seq == 4:                               # ... and no worse than the one-rank kernel on the whole line
+            whole = C.CompactFiniteDifferenceSolver(shape, h, 2)(dev(f)).cpu().numpy()
+            assert relinf(got, want) <= 4 * relinf(whole, want) + 1e-15
 
 
 def test_host_gradient_pipeline(C):
