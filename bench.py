@@ -269,8 +269,10 @@ def run_ours(args):
     ddz = C.ZPartitionedDerivative((nz_loc, N, N), h, 2, mode="fused", comm=args.comm) if world > 1 else \
         C.CompactFiniteDifferenceSolver((nz_loc, N, N), h, 2)
     pts_local = f.numel()
-    # 5 instead of 6 warps per SM when the d/dz exchange chain runs beside the fused launch (scripts/overlap_timeline.py)
-    xy_warps = 5 if (world > 1 and not args.no_overlap) else None
+    # 5 instead of 6 warps per SM when the d/dz exchange chain runs beside the fused launch on thin slabs
+    # (scripts/overlap_timeline.py; measured: 128-plane slabs 1.123 vs 1.146 ms per step, 256 planes equal, 512 planes
+    # 1.2 % slower with 5)
+    xy_warps = 5 if (world > 1 and not args.no_overlap and nz_loc <= 128) else None
 
     def gradient(src, events=None):
         if world > 1 and not args.no_overlap:
