@@ -231,10 +231,12 @@ def workload_config(n_gpus, comm="nvlink", overlap=True):
     if n_gpus == 1:
         return {"workload": "512^3 fp64 field, derivative along x, y and z on 1 B200 (BASELINE configs[2])",
                 "grid": [512, 512, 512], "derivatives_per_step": 3, "partition": "none",
+                "step": "one fused d/dx + d/dy launch (f read from HBM once) + one d/dz launch",
                 "l2": "inputs (1 GiB field) larger than the 126 MB L2; no flush needed"}
     return {"workload": f"1024^3 fp64 field z-partitioned over {n_gpus} B200, derivative along x, y and z "
-                        "(d/dz: halo send/recv + interface all-gather + correction; BASELINE configs[3])",
+                        "(d/dz: one-plane halo + interface exchange with the z-neighbours + coupled solve; BASELINE configs[3])",
             "grid": [1024, 1024, 1024], "derivatives_per_step": 3, "partition": f"z/{n_gpus}",
+            "step": "per rank: one fused d/dx + d/dy launch on the slab + the partitioned d/dz",
             "ddz": f"fused (edge faces -> {comm} exchange -> coupled kernel)",
             "overlap": "d/dz exchange started before d/dx, d/dy" if overlap else "none",
             "l2": "inputs (slab >= 1 GiB) larger than the 126 MB L2; no flush needed"}

@@ -41,6 +41,8 @@ SIGNATURES = {
     "cfd_tables_size": (_i, []),
     "cfd_plan_tables": (_i, [_vp, _dp]),
     "cfd_debug_tables": (_i, [_i, _dp, _d, _dp]),
+    "cfd_debug_xy_order": (_i, [_i, _i, _i, _d, ctypes.POINTER(_i)]),
+    "cfd_debug_halo_weights": (_i, [_i, _d, _dp, _dp]),
     "cfd_debug_secondary": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp]),
     "cfd_plan_secondary": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "nt_create": (_i, [_pp, _i, _i, _i, _i, _dp]),

@@ -459,6 +459,35 @@ extern "C" int cfd_debug_neighbour(int n, int part_rank, int part_size, int *vir
     return CFD_OK;
 }
 
+// The interface faces depend linearly on the neighbour points of f (edge_faces_kernel): lo face = -x_0 of the head
+// solve, where f[-1] enters row 0 only (r_0 = sk_0 (f[1] - f[-1])); hi face = -e_{n-1}, where f[n] enters through
+// sk_last.  Unit responses, for the exchange that folds the halos in afterwards (cfd_reduced_unknowns_deferred).  They
+// are applied to the NEIGHBOURS' faces too, so they come from the tables of an interior block (a block end that has a
+// neighbour is an interior-type end on every rank), not from this rank's own closures.
+static int halo_weights(const Geometry &g, double h, double &w_lo, double &w_hi)
+{
+    KParams ki;
+    int rc = fill_tables(ki, g, pade_block(1, 3), 3.0 / (4.0 * h), true);
+    if (rc) return rc == CFD_ESLOWPATH ? CFD_EUNSUPPORTED : rc;
+    double e[CH], ep = 0.0;
+    for (int j = 0; j < CH; j++) { ep = -ki.head.l[j] * ep + (j == 0 ? -ki.head.sk[0] : 0.0); e[j] = ep; }
+    double x = 0.0;
+    for (int j = CH - 1; j >= 0; j--) x = e[j] - ki.head.g[j] * x;
+    w_lo = -x;
+    w_hi = -ki.tail.sk[g.jl];
+    return CFD_OK;
+}
+
+// Host-only inspection entries for the CPU tests (no device needed).
+extern "C" int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_hi)
+{
+    if (!w_lo || !w_hi || n < 2 * CH + 2 || !(h > 0.0)) return fail(CFD_EINVAL, "cfd_debug_halo_weights: bad argument");
+    Geometry g;
+    int rc = make_geometry(g, n, 2, 2, 2);
+    if (rc) return rc;
+    return halo_weights(g, h, *w_lo, *w_hi);
+}
+
 // d/dx and d/dy of one field in one launch (kernels_xy.cuh).  A plane of f is a grid of 32 x 32 tiles (j, k):
 // x-bundle j walks tiles (j, 0), (j, 1), ... and y-bundle k walks (0, k), (1, k), ...  When x-bundle j and y-bundle j
 // both start j tile-times after their plane's first bundles, the two readers of EVERY tile (j, k) ask for it at the
@@ -487,6 +516,15 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
         }
     }
     return order;
+}
+
+extern "C" int cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int *out)
+{
+    if (!out || nz < 1 || nxp < 0 || nyp < 0 || nxp + nyp < 1) return fail(CFD_EINVAL, "cfd_debug_xy_order: bad argument");
+    const std::vector<int> order = xy_order(nz, nxp, nyp, active);
+    if ((long)order.size() != (long)nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
+    memcpy(out, order.data(), order.size() * sizeof(int));
+    return CFD_OK;
 }
 
 // Default launch shape of stream_kernel_xy and the planes-in-flight figure that goes with it.
@@ -565,22 +603,8 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
         int wc = 0;
         while (wc < n && (std::fabs(p->x_uh[wc]) > 1e-19 || std::fabs(p->x_lh[n - 1 - wc]) > 1e-19)) wc++;
         p->wc = wc;
-        // The interface faces depend linearly on the neighbour points of f (edge_faces_kernel): lo face = -x_0 of
-        // the head solve, where f[-1] enters row 0 only (r_0 = sk_0 (f[1] - f[-1])); hi face = -e_{n-1}, where f[n]
-        // enters through sk_last.  Unit responses, for the exchange that folds the halos in afterwards.  They are
-        // applied to the NEIGHBOURS' faces too, so they come from the tables of an interior block (a block end that
-        // has a neighbour is an interior-type end on every rank), not from this rank's own closures.
-        {
-            KParams ki;
-            rc = fill_tables(ki, p->g, pade_block(1, 3), 3.0 / (4.0 * h), true);
-            if (rc) { cfd_destroy(p); return rc == CFD_ESLOWPATH ? CFD_EUNSUPPORTED : rc; }
-            double e[CH], ep = 0.0;
-            for (int j = 0; j < CH; j++) { ep = -ki.head.l[j] * ep + (j == 0 ? -ki.head.sk[0] : 0.0); e[j] = ep; }
-            double x = 0.0;
-            for (int j = CH - 1; j >= 0; j--) x = e[j] - ki.head.g[j] * x;
-            p->w_lo = -x;
-            p->w_hi = -ki.tail.sk[p->g.jl];
-        }
+        rc = halo_weights(p->g, h, p->w_lo, p->w_hi);
+        if (rc) { cfd_destroy(p); return rc; }
         if (cudaMalloc(&p->d_x_uh, n * sizeof(double)) != cudaSuccess || cudaMalloc(&p->d_x_lh, n * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&p->d_lu, p->lu.size() * sizeof(double)) != cudaSuccess ||
             cudaMalloc(&p->d_lu_nb, p->lu_nb.size() * sizeof(double)) != cudaSuccess) {

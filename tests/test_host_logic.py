@@ -205,3 +205,80 @@ def test_chunk_schedule_random_property():
         want = O.derivative(F.reshape(1, 2, n), 0, h).reshape(2, n)
         got = stream_lines(F, PADE, h, kseg=kseg or None)
         assert relinf(got, want) < 1e-13, (n, kseg)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cfd_apply_xy: the wavefront draw order (host table)
+# ---------------------------------------------------------------------------------------------------
+def _xy_order(nz, nxp, nyp, active):
+    from compact_finite_differences_b200._lib import check, lib
+    out = np.zeros(nz * (nxp + nyp), dtype=np.int32)
+    check(lib().cfd_debug_xy_order(nz, nxp, nyp, float(active), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))))
+    return out
+
+
+@pytest.mark.parametrize("nz,nxp,nyp,active", [(1, 1, 1, 3.0), (7, 16, 16, 18.5), (40, 8, 8, 37.0), (5, 2, 32, 4.0),
+                                               (9, 32, 1, 1.0), (33, 4, 5, 100.0), (12, 16, 16, 0.0), (3, 0, 4, 2.0)])
+def test_xy_draw_order_is_a_wavefront(nz, nxp, nyp, active):
+    """Every (plane, bundle) item exactly once; inside a plane the x and y bundles come in ascending order (bundle j
+    starts j tile-times after bundle 0, so both readers of tile (j, k) reach it j + k tile-times in); bundle j of the
+    two directions is drawn back to back; planes start in ascending order, `active` of them in flight."""
+    order = _xy_order(nz, nxp, nyp, active)
+    ipp = nxp + nyp
+    assert sorted(order.tolist()) == list(range(nz * ipp))
+    if active == 0.0:
+        assert order.tolist() == list(range(nz * ipp))
+        return
+    pos = np.empty(nz * ipp, dtype=np.int64)
+    pos[order] = np.arange(nz * ipp)
+    first = []
+    for z in range(nz):
+        px, py = pos[z * ipp:z * ipp + nxp], pos[z * ipp + nxp:(z + 1) * ipp]
+        assert np.all(np.diff(px) > 0) and np.all(np.diff(py) > 0)
+        for j in range(min(nxp, nyp)):
+            assert py[j] == px[j] + 1                       # the pair (x_j, y_j) is adjacent in the draw
+        first.append(min(px.min() if nxp else 1 << 60, py.min() if nyp else 1 << 60))
+    assert np.all(np.diff(first) > 0)
+    # planes in flight: between the first and the last draw of a plane, no more than ~active other planes start
+    M = max(nxp, nyp)
+    if nz > 2 * active + 2 and M > 1:
+        z = nz // 2
+        last = pos[z * ipp:(z + 1) * ipp].max()
+        started = sum(1 for zz in range(z + 1, nz) if first[zz] < last)
+        assert started <= int(np.ceil(active)) + 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# one-launch exchange: the faces are linear in the neighbour points of f, with the library's two weights
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,h", [(66, 0.2), (128, 0.013)])
+def test_halo_weights_of_the_deferred_exchange(n, h):
+    """cfd_edge_faces_push computes -x_R[0], -x_R[n-1] with guessed neighbour points and
+    cfd_reduced_unknowns_deferred adds w * (halo - guess): check w_lo, w_hi against block-local solves by the oracle
+    (interior block, and the end blocks' interior-type ends), and that the corrected faces equal the direct ones."""
+    from compact_finite_differences_b200._lib import check, lib
+    w_lo, w_hi = ctypes.c_double(), ctypes.c_double()
+    check(lib().cfd_debug_halo_weights(n, h, ctypes.byref(w_lo), ctypes.byref(w_hi)))
+    w_lo, w_hi = w_lo.value, w_hi.value
+    rng = np.random.default_rng(n)
+    blk = rng.random((4, n))
+    for rank, size in ((1, 3), (0, 2), (1, 2)):
+        co = O.partition_local_coeffs(rank, size)
+        a, b, c = O.banded_abc(n, co)
+
+        def faces(lo, hi):
+            rr = O.rhs(blk.reshape(1, 4, n), 0, h, halo_lo=lo, halo_hi=hi).reshape(4, n)
+            x = O.scipy_solve_banded(a, b, c, rr.T).T
+            return -x[:, 0], -x[:, -1]
+
+        lo_true = rng.random(4) if rank > 0 else None
+        hi_true = rng.random(4) if rank < size - 1 else None
+        guess_lo = blk[:, 0] if rank > 0 else None
+        guess_hi = blk[:, -1] if rank < size - 1 else None
+        f_lo, f_hi = faces(lo_true, hi_true)
+        g_lo, g_hi = faces(guess_lo, guess_hi)
+        scale = max(np.abs(f_lo).max(), np.abs(f_hi).max())
+        if rank > 0:
+            assert np.abs(g_lo + w_lo * (lo_true - guess_lo) - f_lo).max() <= 1e-13 * scale
+        if rank < size - 1:
+            assert np.abs(g_hi + w_hi * (hi_true - guess_hi) - f_hi).max() <= 1e-13 * scale
