@@ -310,3 +310,116 @@ def partition_derivative(f, axis, h, size):
         sh = (n,) + (1,) * len(rest)
         out[r * n:(r + 1) * n] = x_r[r] + sol[2 * r] * x_uh.reshape(sh) + sol[2 * r + 1] * x_lh.reshape(sh)
     return np.ascontiguousarray(np.moveaxis(out, 0, ax))
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's DISTRIBUTED npts solve (lanl-implementation/python/npts.py:172-382; C twin npts.c:275-655),
+# restated in NumPy as a serial emulation of the npx ranks of one x line.  The C version has `product_1 = 0.0`
+# where the Python twin has 1.0 (npts.c:525 vs python/npts.py:365) and gives wrong last elements for npx > 2
+# (lanl-implementation/README.md:3-12), so the restatement follows the Python twin.
+# ------------------------------------------------------------------------------------------------
+def npts_distributed_beta_gam(nx_local, npx):
+    """precompute_beta_gam_dfdx (python/npts.py:172-225): LU pivots handed from rank to rank along the line.
+    Returns beta[npx][nx_local], gam[npx][nx_local]."""
+    beta = np.zeros((npx, nx_local))
+    gam = np.zeros((npx, nx_local))
+    last_beta = 0.0
+    for r in range(npx):
+        if r == 0:
+            beta[r, 0], gam[r, 0] = 1.0, 0.0
+        else:
+            beta[r, 0] = 1. / (1. - (1. / 4) * last_beta * (1. / 4))
+            gam[r, 0] = last_beta * (1. / 4)
+        for i in range(1, nx_local):
+            gam[r, i] = beta[r, i - 1] * (2. if (r == 0 and i == 1) else 1. / 4)
+            if (r == npx - 1 and i == nx_local - 1) or (r == 0 and i == 1):
+                beta[r, i] = 1. / (1. - 2.0 * beta[r, i - 1] * (1. / 4))
+            else:
+                beta[r, i] = 1. / (1. - (1. / 4) * beta[r, i - 1] * (1. / 4))
+        last_beta = beta[r, -1]
+    return beta, gam
+
+
+def npts_distributed_solve(r, npx, c_twin_product_zero=False):
+    """dfdx_parallel (python/npts.py:228-382) for the x lines of r[nz, ny, NX], NX split over npx emulated ranks:
+    L->R sweep of (phi, psi) on every rank at once, all-gather of the last faces, prefix combination u_tilda,
+    u = phi + u_tilda psi; R->L sweep likewise with the first faces; x = phi + x_tilda psi.
+    c_twin_product_zero=True reproduces npts.c:525 (`product_1 = 0.0` in the R->L combination), which drops the
+    contributions of ranks further than one block away."""
+    r = _c(r)
+    nz, ny, NX = r.shape
+    assert NX % npx == 0
+    nx = NX // npx
+    beta, gam = npts_distributed_beta_gam(nx, npx)
+    blocks = [r[:, :, m * nx:(m + 1) * nx] for m in range(npx)]
+    phi = [np.zeros((nz, ny, nx)) for _ in range(npx)]
+    psi = [np.zeros((nz, ny, nx)) for _ in range(npx)]
+    u = [np.zeros((nz, ny, nx)) for _ in range(npx)]
+    x = [np.zeros((nz, ny, nx)) for _ in range(npx)]
+
+    # ---- L-R sweep (python/npts.py:252-272)
+    for m in range(npx):
+        b, rr = beta[m], blocks[m]
+        if m == 0:
+            phi[m][:, :, 0] = 0.0
+            psi[m][:, :, 0] = 1.0
+        else:
+            phi[m][:, :, 0] = b[0] * rr[:, :, 0]
+            psi[m][:, :, 0] = -(1. / 4) * b[0]
+        for i in range(1, nx):
+            phi[m][:, :, i] = b[i] * (rr[:, :, i] - (1. / 4) * phi[m][:, :, i - 1])
+            psi[m][:, :, i] = -(1. / 4) * b[i] * psi[m][:, :, i - 1]
+        if m == npx - 1:
+            i = nx - 1
+            phi[m][:, :, i] = b[i] * (rr[:, :, i] - 2 * phi[m][:, :, i - 1])
+            psi[m][:, :, i] = -2 * b[i] * psi[m][:, :, i - 1]
+    phi_lasts = [p[:, :, -1].copy() for p in phi]            # line_allgather_faces(..., 'last'), :277-281
+    psi_lasts = [p[:, :, -1].copy() for p in psi]
+    u_first = beta[0][0] * blocks[0][:, :, 0]                 # :293-300, broadcast from the line root
+    for m in range(npx):
+        if m == 0:
+            u_tilda = u_first
+        else:                                                 # :302-311
+            u_tilda = np.zeros((nz, ny))
+            product_2 = np.ones((nz, ny))
+            for i in range(m):
+                product_1 = np.ones((nz, ny))
+                for j in range(i + 1, m):
+                    product_1 = product_1 * psi_lasts[j]
+                u_tilda = u_tilda + phi_lasts[i] * product_1
+                product_2 = product_2 * psi_lasts[i]
+            u_tilda = u_tilda + u_first * product_2
+        u[m] = phi[m] + u_tilda[:, :, None] * psi[m]          # :316-317
+
+    # ---- R-L sweep (:325-343)
+    gam_firsts = [gam[m][0] for m in range(npx)]
+    for m in range(npx):
+        g = gam[m]
+        if m == npx - 1:
+            phi[m][:, :, -1] = 0.0
+            psi[m][:, :, -1] = 1.0
+        else:
+            phi[m][:, :, -1] = u[m][:, :, -1]
+            psi[m][:, :, -1] = -gam_firsts[m + 1]
+        for i in range(1, nx):
+            phi[m][:, :, -1 - i] = u[m][:, :, -1 - i] - g[-1 - i + 1] * phi[m][:, :, -1 - i + 1]
+            psi[m][:, :, -1 - i] = -g[-1 - i + 1] * psi[m][:, :, -1 - i + 1]
+    phi_firsts = [p[:, :, 0].copy() for p in phi]             # :349-353
+    psi_firsts = [p[:, :, 0].copy() for p in psi]
+    x_last = u[npx - 1][:, :, -1]                             # :361-368
+    for m in range(npx):
+        if m == npx - 1:
+            x_tilda = x_last
+        else:                                                 # :370-382
+            x_tilda = np.zeros((nz, ny))
+            for i in range(m + 2, npx):
+                product_1 = np.zeros((nz, ny)) if c_twin_product_zero else np.ones((nz, ny))
+                for j in range(m + 1, i):
+                    product_1 = product_1 * psi_firsts[j]
+                x_tilda = x_tilda + phi_firsts[i] * product_1
+            product_2 = np.ones((nz, ny))
+            for i in range(m + 1, npx):
+                product_2 = product_2 * psi_firsts[i]
+            x_tilda = x_tilda + phi_firsts[m + 1] + x_last * product_2
+        x[m] = phi[m] + x_tilda[:, :, None] * psi[m]
+    return np.concatenate(x, axis=2)

@@ -119,3 +119,37 @@ def test_analytic_fields():
     np.testing.assert_almost_equal(O.derivative(np.sin(y), 1, h), np.cos(y), decimal=2)
     np.testing.assert_almost_equal(O.derivative(x * y * z, 1, h), x * z, decimal=2)
     np.testing.assert_almost_equal(O.derivative(x * y * z ** 2, 2, h), 2 * x * y * z, decimal=2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's DISTRIBUTED npts solve (emulated ranks) -- lanl-implementation/python/test_npts.py:13-54
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("npx,shape", [(3, (12, 6, 36)), (1, (2, 3, 32)), (2, (2, 3, 32)), (4, (3, 2, 64)), (8, (1, 2, 64)),
+                                       (6, (2, 2, 24))])
+def test_distributed_npts_restatement(npx, shape):
+    """The reference's own check: random right-hand side, every x line against the banded LU (its 3x3x3-rank case is
+    36 x 18 x 36 with 12 points per rank along the line); here to 1e-14 instead of rtol 1e-7, and against the
+    one-rank npts solve of the port."""
+    rng = np.random.default_rng(npx)
+    r = rng.random(shape)
+    got = O.npts_distributed_solve(r, npx)
+    assert relinf(got, O.scipy_solve_axis(r, O.PADE, 0)) < 1e-14
+    assert relinf(got, O.npts_solve(r, 0)) < 1e-14
+    b1, g1 = O.npts_beta_gam(shape[2])
+    bd, gd = O.npts_distributed_beta_gam(shape[2] // npx, npx)
+    assert np.array_equal(bd.ravel(), b1) and np.array_equal(gd.ravel(), g1)    # the hand-off reproduces the serial pivots
+
+
+def test_distributed_npts_c_twin_defect():
+    """Why the restatement follows python/npts.py and not npts.c: with `product_1 = 0.0` (npts.c:525; 1.0 in
+    python/npts.py:365) the R->L combination loses the ranks more than one block away -- exact for npx <= 2, wrong
+    for short blocks at npx >= 3 (the "high error for the last elements in each block" of lanl-implementation/README.md)."""
+    rng = np.random.default_rng(1)
+    r = rng.random((2, 2, 16))
+    want = O.scipy_solve_axis(r, O.PADE, 0)
+    assert relinf(O.npts_distributed_solve(r, 2, c_twin_product_zero=True), want) < 1e-14
+    bad = O.npts_distributed_solve(r, 4, c_twin_product_zero=True)
+    assert relinf(bad, want) > 1e-6
+    blk = np.abs(bad - want).reshape(2, 2, 4, 4).max(axis=(0, 1))      # [rank, position in block]
+    assert blk[0].argmax() == 3 and blk[1].argmax() == 3               # worst at the last element of a block
+    assert relinf(O.npts_distributed_solve(r, 4), want) < 1e-14
