@@ -5,9 +5,10 @@ distributed-array layer (code/cuda/gpuDA.py): the (npz, npy, npx) decomposition,
 gather / scatter helpers (gpuDA.py:434-488).  One process per GPU, torch.distributed process groups (NCCL on GPUs,
 gloo in the CPU tests) instead of mpi4py communicators.
 
-Not rebuilt: the six-face ghosted `global_to_local` / `local_to_global` copies and stencil widths > 1 -- the
-derivative reads ONE boundary plane per line neighbour, straight from the un-ghosted block
-(partition.PartitionedDerivative), so no ghosted array exists.
+The derivative itself never uses a ghosted array: it reads ONE boundary plane per line neighbour, straight from the
+un-ghosted block (partition.PartitionedDerivative).  `global_to_local` / `local_to_global` (gpuDA.py:61-141, six-face
+halo exchange into a [nz+2sw, ny+2sw, nx+2sw] array) are provided for callers of the reference that use the DA for
+their own stencils; they are torch copies + point-to-point messages, no kernels of this library.
 
     da  = DA(None, (nz, ny, nx), (npz, npy, npx))            # every rank, same arguments (collective)
     x, y, z = DA_arange(da, (0, 2 * pi), (0, 2 * pi), (0, 2 * pi), device="cuda")
@@ -32,14 +33,14 @@ class DA:
         :param local_dims: (nz, ny, nx) of the block every rank owns
         :param proc_sizes: (npz, npy, npx); ranks are laid out row-major like MPI_Cart_create:
                            rank = (mz * npy + my) * npx + mx
-        :param stencil_width: only 1 is meaningful here (one boundary plane per neighbour); kept for the signature
+        :param stencil_width: ghost width of global_to_local (the derivative itself always exchanges one plane)
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.comm = comm
         self.local_dims = tuple(int(s) for s in local_dims)
         self.proc_sizes = tuple(int(s) for s in proc_sizes)
-        self.stencil_width = int(stencil_width)
-        assert self.stencil_width == 1, "the compact derivative exchanges exactly one plane per line neighbour"
+        self.stencil_width = int(stencil_width)          # used by global_to_local only; the derivative exchanges 1 plane
+        assert self.stencil_width >= 1
         self.rank = dist.get_rank(comm)
         self.size = dist.get_world_size(comm)
         self.nz, self.ny, self.nx = self.local_dims
@@ -85,6 +86,56 @@ class DA:
             from .compact import CompactFiniteDifferenceSolver
             return CompactFiniteDifferenceSolver(self.local_dims, spacing, int(direction))
         return PartitionedDerivative(self.local_dims, spacing, int(direction), group=g, mode=mode, comm=comm)
+
+    def create_local_vector(self, device=None):
+        """gpuDA.py:51-59: the ghosted array [nz + 2 sw, ny + 2 sw, nx + 2 sw], zero-filled."""
+        sw = self.stencil_width
+        return torch.zeros((self.nz + 2 * sw, self.ny + 2 * sw, self.nx + 2 * sw), dtype=torch.float64, device=device)
+
+    def _neighbour(self, dim, step):
+        """Rank (in `comm`) of the neighbour one block away along tensor dimension dim (0 = z), or None at the edge."""
+        m = [self.mz, self.my, self.mx]
+        m[dim] += step
+        if m[dim] < 0 or m[dim] >= self.proc_sizes[dim]:
+            return None
+        return (m[0] * self.npy + m[1]) * self.npx + m[2]
+
+    def global_to_local(self, global_array, local_array):
+        """gpuDA.py:61-132: copy the block into the interior of the ghosted array and fill its six ghost faces
+        (width stencil_width) from the face neighbours; ghost cells at physical boundaries, edges and corners are
+        left as they were."""
+        sw = self.stencil_width
+        g, l = global_array, local_array
+        assert tuple(g.shape) == self.local_dims and tuple(l.shape) == tuple(s + 2 * sw for s in self.local_dims)
+        inner = (slice(sw, sw + self.nz), slice(sw, sw + self.ny), slice(sw, sw + self.nx))
+        l[inner] = g
+        ops, recvs = [], []
+        peer = (lambda r: r) if self.comm is None else (lambda r: dist.get_global_rank(self.comm, r))
+        for dim in range(3):
+            n = self.local_dims[dim]
+            for step, send_lo, ghost_lo in ((-1, 0, 0), (+1, n - sw, sw + n)):
+                nb = self._neighbour(dim, step)
+                if nb is None:
+                    continue
+                send = g.narrow(dim, send_lo, sw).contiguous()
+                recv = torch.empty_like(send)
+                ops.append(dist.P2POp(dist.isend, send, peer(nb), self.comm))
+                ops.append(dist.P2POp(dist.irecv, recv, peer(nb), self.comm))
+                idx = list(inner)
+                idx[dim] = slice(ghost_lo, ghost_lo + sw)
+                recvs.append((tuple(idx), recv))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for idx, recv in recvs:
+            l[idx] = recv
+        return l
+
+    def local_to_global(self, local_array, global_array):
+        """gpuDA.py:134-141: strip the ghost cells."""
+        sw = self.stencil_width
+        global_array.copy_(local_array[sw:sw + self.nz, sw:sw + self.ny, sw:sw + self.nx])
+        return global_array
 
     def create_global_vector(self, device=None):
         """gpuDA.py:41-49: this rank's block, zero-filled (the reference's name for the un-ghosted array)."""

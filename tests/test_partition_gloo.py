@@ -296,6 +296,31 @@ def _worker_grid(rank, world, port, proc_sizes, ret):
         else:
             assert back is None
 
+        # global_to_local / local_to_global (code/cuda/test/test_gpuDA/test_3d.py:17-66): fill with the rank, ghosts = neighbours
+        for sw in (1, 2):
+            da_sw = da if sw == 1 else DA(None, local, proc_sizes, stencil_width=2)
+            a = da_sw.create_global_vector()
+            a.fill_(float(rank))
+            b = da_sw.create_local_vector()
+            b.fill_(-1.0)
+            da_sw.global_to_local(a, b)
+            assert torch.all(b[sw:-sw, sw:-sw, sw:-sw] == rank)
+            for dim in range(3):
+                for step, ghost in ((-1, slice(0, sw)), (+1, slice(-sw, None))):
+                    idx = [slice(sw, -sw)] * 3
+                    idx[dim] = ghost
+                    nb = da_sw._neighbour(dim, step)
+                    want_v = -1.0 if nb is None else float(nb)          # physical boundaries stay untouched
+                    assert torch.all(b[tuple(idx)] == want_v), (rank, dim, step)
+                    if nb is not None:
+                        c = list(np.unravel_index(rank, proc_sizes))
+                        c[dim] += step
+                        assert nb == int(np.ravel_multi_index(c, proc_sizes))
+            assert torch.all(b[:sw, :sw, :] == -1.0)                       # edges / corners are not exchanged
+            back_g = torch.empty(local, dtype=torch.float64)
+            da_sw.local_to_global(b, back_g)
+            assert torch.all(back_g == rank)
+
         # derivative along every direction through the line groups, block kernels replaced by the oracle
         worst = 0.0
         for direction in range(3):
