@@ -803,6 +803,14 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     kx.ab = nullptr; ky.ab = nullptr;
     long blocks = (q.nitems + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
+    if (const char *e = getenv("CFD_XY_CTAS")) {      // experiment: "auto" = full last round, or an absolute CTA count
+        if (!strcmp(e, "auto")) {
+            const long rounds = (q.nitems + blocks * warps - 1) / (blocks * warps);
+            const long need = (q.nitems + rounds - 1) / rounds;          // warps that make every round full
+            const long b2 = (need + warps - 1) / warps;
+            if (b2 >= 1 && b2 < blocks) blocks = b2;
+        } else if (atol(e) >= 1 && atol(e) <= blocks) blocks = atol(e);
+    }
     kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
