@@ -787,6 +787,11 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     rc = xy_prepare(px, active);        // no-op unless the launch knobs changed since cfd_create
     if (rc) return rc;
     q.order = px->d_xy_order;
+    q.slot_items = (float)(2.0 * active);
+    // Start-up stagger: pays on long lines only (>= 32 tiles: [128,1024,1024] 0.596 -> 0.577 ms with 1 us per slot;
+    // 512^3, 16 tiles: 0.531 -> 0.534), profiles/r1n_time_xy_startup_stagger.txt.  CFD_XY_TAU overrides (ns).
+    q.tau_ns = (px->g.K + py->g.K >= 64) ? 1000.f : 0.f;
+    if (const char *e = getenv("CFD_XY_TAU")) q.tau_ns = (float)atof(e);
     const size_t smem = (size_t)warps * per_warp + 1024;
     auto kern = stream_kernel_xy<NSLOT>;
     static size_t configured[MAX_DEVICES] = {0};
@@ -830,6 +835,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     q.nyp = p->g.contig ? 0 : p->g.inner_tiles;
     q.nitems = p->g.nb;
     q.order = nullptr;
+    q.tau_ns = 0.f; q.slot_items = 0.f;
     int warps = g_warps ? g_warps : 6;
     if (warps > 7) warps = 7;
     const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;

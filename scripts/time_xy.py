@@ -25,6 +25,7 @@ def timeit(fn, reps=20):
 args = [int(a) for a in sys.argv[1:]] or [512, 512, 512]
 shapes = [tuple(args[i:i + 3]) for i in range(0, len(args), 3)]
 actives = os.environ.get("XY_ACTIVES", "default,0,4,9,14,18.5,24,32,48").split(",")
+taus = os.environ.get("XY_TAUS", "").split(",")                 # start-up stagger per slot in ns ("" = off)
 ctas_list = os.environ.get("XY_CTAS", "").split(",")            # "" = all SMs; "auto" = full last round; or a count
 warps_list = [int(w) for w in os.environ.get("XY_WARPS", "0").split(",")]      # 0 = library default
 slots_list = [int(w) for w in os.environ.get("XY_SLOTS", "0").split(",")]
@@ -37,7 +38,11 @@ for shape in shapes:
     t_sep = timeit(lambda: (op.dfdx(f, 0.1, gx), op.dfdy(f, 0.2, gy)))
     pts = f.numel()
     print(f"{shape}: separate x+y {t_sep:.4f} ms ({32 * pts / t_sep / 1e6:.0f} GB/s algorithmic)", flush=True)
-    for w, ns, ct in [(w, ns, ct) for ns in slots_list for w in warps_list for ct in ctas_list]:
+    for w, ns, ct, tau in [(w, ns, ct, tau) for ns in slots_list for w in warps_list for ct in ctas_list for tau in taus]:
+        if tau:
+            os.environ["CFD_XY_TAU"] = tau
+        else:
+            os.environ.pop("CFD_XY_TAU", None)
         if ct:
             os.environ["CFD_XY_CTAS"] = ct
         else:
@@ -55,9 +60,10 @@ for shape in shapes:
             same = bool(torch.equal(gx, rx) and torch.equal(gy, ry))
             err = max(float((gx - rx).abs().max() / rx.abs().max()), float((gy - ry).abs().max() / ry.abs().max()))
             t = timeit(lambda: op.dfdxy(f, 0.1, 0.2, gx, gy))
-            print(f"  warps={w} slots={ns} ctas={ct or 'all':>4} active={a:>7}: {t:.4f} ms ({32 * pts / t / 1e6:.0f} GB/s algorithmic, "
+            print(f"  warps={w} slots={ns} ctas={ct or 'all':>4} tau={tau or '0':>5} active={a:>7}: {t:.4f} ms ({32 * pts / t / 1e6:.0f} GB/s algorithmic, "
                   f"{t_sep / t:.3f}x) bit-equal={same} rel-diff={err:.1e}", flush=True)
     C.lib().cfd_set_launch(0, 0, 0)
     os.environ.pop("CFD_XY_ACTIVE", None)
     os.environ.pop("CFD_XY_CTAS", None)
+    os.environ.pop("CFD_XY_TAU", None)
     del f, gx, gy, rx, ry
