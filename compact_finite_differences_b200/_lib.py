@@ -41,7 +41,7 @@ SIGNATURES = {
     "cfd_tables_size": (_i, []),
     "cfd_plan_tables": (_i, [_vp, _dp]),
     "cfd_debug_tables": (_i, [_i, _dp, _d, _dp]),
-    "cfd_debug_xy_order": (_i, [_i, _i, _i, _d, ctypes.POINTER(_i)]),
+    "cfd_debug_xy_order": (_l, [_i, _i, _i, _d, _i, ctypes.POINTER(_i), _l]),
     "cfd_debug_halo_weights": (_i, [_i, _d, _dp, _dp]),
     "cfd_debug_secondary": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp]),
     "cfd_plan_secondary": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),

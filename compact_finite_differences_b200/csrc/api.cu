@@ -307,6 +307,8 @@ struct cfd_plan {
     // cfd_apply_xy: draw order of the (plane, bundle) items (axis-0 plans only)
     std::mutex xy_mu;
     int *d_xy_order = nullptr;
+    long xy_entries = 0;              // entries of the table (> items when lines are cut into segments)
+    int xy_kseg = 0, xy_sub = -1;
     double xy_active = -1.0;
     int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
     double w_lo = 0.0, w_hi = 0.0;    // d(lo face)/d f[-1], d(hi face)/d f[n]: cfd_reduced_unknowns_deferred
@@ -495,43 +497,73 @@ extern "C" int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_h
 // produces that wavefront with dynamically scheduled warps: per slot (= one tile-time) every active plane
 // contributes its next (x, y) bundle pair, and `active` planes are in flight so that a slot's worth of items is
 // what all resident warps draw in one tile-time (active = warps / (2 K)).
-static std::vector<int> xy_order(int nz, int nxp, int nyp, double active)
+// Sub-plane wavefronts (sub > 0): on long lines the data in flight between the two readers of a tile outgrows L2
+// (it is proportional to the tiles per line), so a plane is cut into sub x sub-tile squares and the lines into
+// segments of `sub` chunks (one warm-up chunk in front, the look-ahead chunk behind, both served by L2); every square
+// is then a wavefront of its own, as short as a small plane's.  Entries are (item << 3) | segment, segment 0 = whole
+// line.  Returns the effective segment length in `kseg` (0 = nothing was cut).
+static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int sub, int &kseg)
 {
-    const int ipp = nxp + nyp, M = nxp > nyp ? nxp : nyp;
+    const int ipp = nxp + nyp;
+    kseg = 0;
+    if (sub > 0) {
+        const int kmax = nxp > nyp ? nxp : nyp;
+        if (sub * 7 < kmax) sub = (kmax + 6) / 7;             // at most 7 segments fit the 3-bit code
+        if (nxp > sub || nyp > sub) kseg = sub;
+    }
+    const int ngx = (kseg && nyp > kseg) ? (nyp + kseg - 1) / kseg : 1;     // segments of an x line (nyp tiles long)
+    const int ngy = (kseg && nxp > kseg) ? (nxp + kseg - 1) / kseg : 1;     // segments of a y line (nxp tiles long)
+    const int sy = ngy > 1 ? kseg : nxp, sx = ngx > 1 ? kseg : nyp;         // x bundles / y bundles per square
     std::vector<int> order;
-    order.reserve((size_t)nz * ipp);
-    if (active <= 0.0) {                       // plain plane-by-plane order
-        for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)w);
+    order.reserve((size_t)nz * (nxp * ngx + nyp * ngy));
+    if (active <= 0.0) {                       // plain plane-by-plane order (whole lines)
+        kseg = 0;
+        for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)(w << 3));
         return order;
     }
-    const double sigma = (double)M / active;   // slots between the starts of consecutive planes
-    auto start = [&](int z) { return (long)std::floor(z * sigma); };
-    int zlo = 0;
-    for (long s = 0; zlo < nz; s++) {
-        for (int z = zlo; z < nz && start(z) <= s; z++) {
-            const long j = s - start(z);
-            if (j >= M) { if (z == zlo) zlo++; continue; }
-            if (j < nxp) order.push_back(z * ipp + (int)j);
-            if (j < nyp) order.push_back(z * ipp + nxp + (int)j);
+    const long nv = (long)nz * ngy * ngx;      // squares ("virtual planes"), z-major, then y block, then x block
+    const int M = sy > sx ? sy : sx;
+    const double sigma = (double)M / active;   // slots between the starts of consecutive squares
+    auto start = [&](long v) { return (long)std::floor(v * sigma); };
+    long vlo = 0;
+    for (long s = 0; vlo < nv; s++) {
+        for (long v = vlo; v < nv && start(v) <= s; v++) {
+            const long j = s - start(v);
+            if (j >= M) { if (v == vlo) vlo++; continue; }
+            const int z = (int)(v / (ngy * ngx)), a = (int)((v / ngx) % ngy), b = (int)(v % ngx);
+            const long xj = (long)a * sy + j, yk = (long)b * sx + j;
+            if (j < sy && xj < nxp) order.push_back((int)((((long)z * ipp + xj) << 3) | (ngx > 1 ? b + 1 : 0)));
+            if (j < sx && yk < nyp) order.push_back((int)((((long)z * ipp + nxp + yk) << 3) | (ngy > 1 ? a + 1 : 0)));
         }
     }
     return order;
 }
 
-extern "C" int cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int *out)
+extern "C" long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *out, long capacity)
 {
-    if (!out || nz < 1 || nxp < 0 || nyp < 0 || nxp + nyp < 1) return fail(CFD_EINVAL, "cfd_debug_xy_order: bad argument");
-    const std::vector<int> order = xy_order(nz, nxp, nyp, active);
-    if ((long)order.size() != (long)nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
-    memcpy(out, order.data(), order.size() * sizeof(int));
-    return CFD_OK;
+    if (nz < 1 || nxp < 0 || nyp < 0 || nxp + nyp < 1 || sub < 0) return fail(CFD_EINVAL, "cfd_debug_xy_order: bad argument");
+    int kseg = 0;
+    const std::vector<int> order = xy_order(nz, nxp, nyp, active, sub, kseg);
+    if (out) {
+        if ((long)order.size() > capacity) return fail(CFD_EINVAL, "cfd_debug_xy_order: %ld entries, capacity %ld", (long)order.size(), capacity);
+        memcpy(out, order.data(), order.size() * sizeof(int));
+    }
+    return (long)order.size();
 }
 
 // Default launch shape of stream_kernel_xy and the planes-in-flight figure that goes with it.
-static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int &warps, double &active)
+static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int &warps, double &active, int &sub)
 {
     const int max_warps = nslot == 3 ? 8 : 7, def_warps = nslot == 3 ? 8 : 6;
-    const int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
+    int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
+    sub = 0;                                                   // sub-plane wavefronts: experiment switch, off by default
+    if (const char *e = getenv("CFD_XY_SUB")) sub = atoi(e) > 0 ? atoi(e) : 0;
+    if (sub > 0) {                                             // tiles an item walks when its line is cut
+        const int kmax = Kx > Ky ? Kx : Ky;
+        const int ks = sub * 7 < kmax ? (kmax + 6) / 7 : sub;
+        if (Kx > ks) Kx = ks + 2;
+        if (Ky > ks) Ky = ks + 2;
+    }
     const long nitems = (long)gx.nz * (gx.ny / CH + (gx.nx + CH - 1) / CH);
     warps = g_warps ? g_warps : (plan_warps ? plan_warps : def_warps);
     if (warps > max_warps) warps = max_warps;
@@ -544,22 +576,27 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
 
 // (Re)build the draw-order table of an axis-0 plan.  Called from cfd_create with the default launch shape, so that
 // cfd_apply_xy neither allocates nor synchronises; it only runs again if the launch knobs were changed afterwards.
-static int xy_prepare(cfd_plan *px, double active)
+static int xy_prepare(cfd_plan *px, double active, int sub)
 {
     std::lock_guard<std::mutex> lock(px->xy_mu);
-    if (px->d_xy_order && px->xy_active == active) return CFD_OK;
+    if (px->d_xy_order && px->xy_active == active && px->xy_sub == sub) return CFD_OK;
     const int nxp = px->g.ny / CH, nyp = (px->g.nx + CH - 1) / CH;
-    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active);
-    if ((long)order.size() != (long)px->g.nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
+    int kseg = 0;
+    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active, sub, kseg);
+    if ((long)order.size() < (long)px->g.nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
+    if (px->d_xy_order && (long)order.size() > px->xy_entries) { cudaFree(px->d_xy_order); px->d_xy_order = nullptr; }
     if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+    px->xy_entries = (long)order.size();
+    px->xy_kseg = kseg;
     px->xy_active = active;
+    px->xy_sub = sub;
     return CFD_OK;
 }
 
 static bool xy_eligible(const Geometry &g)
 {
-    return g.axis == 0 && g.ny % CH == 0 && (long)g.nz * (g.ny / CH + (g.nx + CH - 1) / CH) <= 0x7fffffffL;
+    return g.axis == 0 && g.ny % CH == 0 && (long)g.nz * (g.ny / CH + (g.nx + CH - 1) / CH) <= 0x0fffffffL;  // id << 3 fits an int
 }
 
 extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size)
@@ -618,10 +655,10 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     }
     if (part_size == 1 && xy_eligible(p->g)) {        // draw order of cfd_apply_xy, default launch shape
         DeviceInfo di;
-        int warps = 0;
+        int warps = 0, sub = 0;
         double active = 0.0;
         rc = device_info(di);
-        if (!rc) { xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active); rc = xy_prepare(p, active); }
+        if (!rc) { xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active, sub); rc = xy_prepare(p, active, sub); }
         if (rc) { cfd_destroy(p); return rc; }
     }
     *out = p;
@@ -781,12 +818,14 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.nxp = px->g.ny / CH;
     q.nyp = py->g.inner_tiles;
     q.nitems = nitems;
-    int warps = 0;
+    int warps = 0, sub = 0;
     double active = 0.0;
-    xy_shape(px->g, dinfo.sms, NSLOT, px->xy_warps, warps, active);
-    rc = xy_prepare(px, active);        // no-op unless the launch knobs changed since cfd_create
+    xy_shape(px->g, dinfo.sms, NSLOT, px->xy_warps, warps, active, sub);
+    rc = xy_prepare(px, active, sub);   // no-op unless the launch knobs changed since cfd_create
     if (rc) return rc;
     q.order = px->d_xy_order;
+    q.nitems = px->xy_entries;
+    q.kseg = px->xy_kseg;
     q.slot_items = (float)(2.0 * active);
     // Start-up stagger: pays on long lines only (>= 32 tiles: [128,1024,1024] 0.596 -> 0.577 ms with 1 us per slot;
     // 512^3, 16 tiles: 0.531 -> 0.534), profiles/r1n_time_xy_startup_stagger.txt.  CFD_XY_TAU overrides (ns).
@@ -835,6 +874,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     q.nyp = p->g.contig ? 0 : p->g.inner_tiles;
     q.nitems = p->g.nb;
     q.order = nullptr;
+    q.kseg = 0;
     q.tau_ns = 0.f; q.slot_items = 0.f;
     int warps = g_warps ? g_warps : 6;
     if (warps > 7) warps = 7;
@@ -866,12 +906,12 @@ extern "C" int cfd_plan_set_xy_warps(cfd_plan *p, int warps_per_sm)
     p->xy_warps = warps_per_sm;
     if (p->size == 1 && xy_eligible(p->g)) {
         DeviceInfo di;
-        int warps = 0;
+        int warps = 0, sub = 0;
         double active = 0.0;
         int rc = device_info(di);
         if (rc) return rc;
-        xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active);
-        return xy_prepare(p, active);
+        xy_shape(p->g, di.sms, g_slots == 3 ? 3 : 4, p->xy_warps, warps, active, sub);
+        return xy_prepare(p, active, sub);
     }
     return CFD_OK;
 }

@@ -16,7 +16,9 @@ struct XYParams {
     long nitems;        // nz * (nxp + nyp)
     int nxp, nyp;       // x-bundles (ny/32) and y-bundles (ceil(nx/32)) per plane
     unsigned long long *counter;
-    const int *order;   // draw position -> item (plane * (nxp + nyp) + index in plane); nullptr = identity
+    const int *order;   // draw position -> (item << 3) | segment, item = plane * (nxp + nyp) + index in plane;
+                        // segment 0 = the whole line, s >= 1 = output chunks [(s-1) kseg, s kseg); nullptr = identity
+    int kseg;           // chunks per line segment (sub-plane wavefronts, see xy_order)
     // Start-up stagger (off when tau_ns == 0): a warp whose FIRST item sits in slot s of the draw order starts it
     // s * tau_ns late, so that the wavefront exists from the first generation of items on instead of all resident
     // warps starting together (worth 3 % on lines of >= 32 tiles, nothing on shorter ones).
@@ -40,19 +42,22 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 template <bool CONTIG, int NS, class Issue>
 __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap *tm_out, long b, int oc0, int oc2,
                                             unsigned char *wbase, uint32_t bar0, int lane, int &slot, uint32_t &phase,
-                                            bool &first_step, Issue &issue)
+                                            bool &first_step, Issue &issue, int kbeg, int kend, int kout, int kstop)
 {
+    // Tiles kbeg .. kend of the line, results for chunks kout .. kstop-1: the whole line (0, K-1, 0, K), or a
+    // segment with one warm-up chunk in front (forward sweep from a zero state, exact to
+    // 0.268^32 like the backward look-ahead) and the look-ahead chunk behind -- the same cut as kernels.cuh makes.
     const int K = p.K;
     double eA[CH], eB[CH], F[CH];
     double eprev = 0.0, fm1 = 0.0, fm2 = 0.0;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (int k = kbeg; k <= kend; ++k) {
         const bool last = (k == K - 1);
         unsigned char *cur = wbase + slot * SLOT_BYTES;
         mbar_wait(bar0 + 8 * slot, phase);
         load_chunk<CONTIG>(cur, lane, F);
         double peek = 0.0;
-        if (!last) {
+        if (k < kend) {                  // the item's next tile is in the ring: peek at its first row
             const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
             const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;
             mbar_wait(bar0 + 8 * s1, ph1);
@@ -91,21 +96,27 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
         };
         double x = 0.0;
         if (last) {
-            if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, cur, lane);
-            else        bwd_chunk<2, true, CONTIG>(p, eB, x, cur, lane);
-            flush(k);
-            if (k > 0) {
+            if (k >= kstop) {                         // the line's last chunk is only this segment's look-ahead
+                bwd_chunk<2, false, CONTIG>(p, eB, x, cur, lane);
+            } else {
+                if (k == 0) bwd_chunk<1, true, CONTIG>(p, eB, x, cur, lane);
+                else        bwd_chunk<2, true, CONTIG>(p, eB, x, cur, lane);
+                flush(k);
+            }
+            if (k > kbeg && k - 1 >= kout) {
                 if (lane == 0) tma_wait_read0();      // the line's last two tiles share the slot
                 __syncwarp();
                 if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, cur, lane);
                 else        bwd_chunk<0, true, CONTIG>(p, eA, x, cur, lane);
                 flush(k - 1);
             }
-        } else if (k > 0) {
+        } else if (k > kbeg) {
             bwd_chunk<0, false, CONTIG>(p, eB, x, cur, lane);
-            if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, cur, lane);
-            else        bwd_chunk<0, true, CONTIG>(p, eA, x, cur, lane);
-            flush(k - 1);
+            if (k - 1 >= kout) {                      // (chunk kbeg of a later segment is warm-up only)
+                if (k == 1) bwd_chunk<1, true, CONTIG>(p, eA, x, cur, lane);
+                else        bwd_chunk<0, true, CONTIG>(p, eA, x, cur, lane);
+                flush(k - 1);
+            }
         }
 #pragma unroll
         for (int j = 0; j < CH; j++) eA[j] = eB[j];
@@ -138,21 +149,33 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
     }
     __syncwarp();
 
-    // item -> (direction, bundle, plane)
-    auto decode = [&](long w, bool &contig, long &b, int &c0, int &c2) {
+    // draw-table entry -> (direction, bundle, plane, tile range)
+    auto decode = [&](long e, bool &contig, long &b, int &c0, int &c2, int &kb, int &ke, int &ko, int &kp) {
+        const int seg = (int)(e & 7);
+        const long w = e >> 3;
         const long z = w / ipp;
         const int r = (int)(w - z * ipp);
         contig = r < q.nxp;
         if (contig) { b = z * q.nxp + r; c0 = 0; c2 = 0; }
         else        { b = z * q.nyp + (r - q.nxp); c0 = (r - q.nxp) * CH; c2 = (int)z; }
+        const int K = contig ? px.K : py.K;
+        if (seg == 0) { kb = 0; ke = K - 1; ko = 0; kp = K; }
+        else {
+            const int s0 = (seg - 1) * q.kseg;
+            const int s1 = (s0 + q.kseg < K) ? s0 + q.kseg : K;
+            ko = s0;
+            kp = s1;
+            kb = s0 > 0 ? s0 - 1 : 0;
+            ke = s1 < K ? s1 : K - 1;
+        }
     };
 
     // ---- producer (lane 0): one call per tile position; after the initial fill it runs NS - 1 positions ahead
     long iw = 0, ib = 0;
-    int ik = 1, iK = 0, ic0 = 0, ic2 = 0, islot = 0;
+    int ik = 1, ikend = 0, iko = 0, ikp = 0, ic0 = 0, ic2 = 0, islot = 0;
     bool icontig = true, dry = false, first_draw = true;
     auto issue = [&]() {
-        if (ik >= iK && !dry) {
+        if (ik > ikend && !dry) {
             iw = (long)atomicAdd(q.counter, 1ULL);
             dry = iw >= q.nitems;
             if (!dry) {
@@ -162,10 +185,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
                     while (global_timer_ns() - t0 < wait) __nanosleep(256);
                 }
                 first_draw = false;
-                if (q.order) iw = q.order[iw];
-                decode(iw, icontig, ib, ic0, ic2);
-                ik = 0;
-                iK = icontig ? px.K : py.K;
+                iw = q.order ? (long)q.order[iw] : (iw << 3);
+                decode(iw, icontig, ib, ic0, ic2, ik, ikend, iko, ikp);
             }
         }
         if (dry) {
@@ -200,10 +221,10 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         if (w < 0) break;
         bool contig;
         long b;
-        int c0, c2;
-        decode(w, contig, b, c0, c2);
-        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue);
-        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue);
+        int c0, c2, kb, ke, ko, kp;
+        decode(w, contig, b, c0, c2, kb, ke, ko, kp);
+        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
+        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
     }
     if (lane == 0) {
         tma_wait_all0();

@@ -176,10 +176,12 @@ int cfd_debug_secondary(int n, int part_rank, int part_size, double *x_uh, doubl
                         double *rc);
 int cfd_debug_neighbour(int n, int part_rank, int part_size, int *virtual_ranks, int *own_index, double *va,
                         double *vb, double *vc);
-/* Host-only: the draw order of cfd_apply_xy for nz planes of nxp x-bundles + nyp y-bundles (out: nz * (nxp + nyp)
- * item ids, plane * (nxp + nyp) + index in plane) with `active` planes in flight (0 = plane by plane); and the two
- * weights d(lo face)/d f[-1], d(hi face)/d f[n] that cfd_reduced_unknowns_deferred applies (blocks of n rows). */
-int cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int *out);
+/* Host-only: the draw order of cfd_apply_xy for nz planes of nxp x-bundles + nyp y-bundles with `active` planes (or
+ * sub x sub-tile squares when sub > 0) in flight; active = 0: plane by plane.  Entries are (item << 3) | segment with
+ * item = plane * (nxp + nyp) + index in plane and segment 0 = whole line, s >= 1 = output chunks [(s-1) sub, s sub).
+ * Returns the number of entries (<0 on error); out may be NULL to query it.  And the two weights d(lo face)/d f[-1],
+ * d(hi face)/d f[n] that cfd_reduced_unknowns_deferred applies (blocks of n rows). */
+long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *out, long capacity);
 int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_hi);
 /* secondary solutions x_UH, x_LH (each n doubles) and the reduced matrix a,b,c (each 2*part_size). */
 int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double *ra, double *rb, double *rc);

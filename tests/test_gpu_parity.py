@@ -199,6 +199,26 @@ def test_fused_xy_launch_shapes(C, warps, slots):
         C.lib().cfd_set_launch(0, 0, 0)
 
 
+@pytest.mark.parametrize("sub", [1, 2, 3, 16])
+@pytest.mark.parametrize("shape", [(5, 160, 192), (3, 96, 258), (2, 64, 1056), (2, 1056, 64)])
+def test_fused_xy_sub_plane_wavefronts(C, sub, shape):
+    """CFD_XY_SUB: lines cut into segments of `sub` chunks (warm-up chunk in front, look-ahead chunk behind), squares
+    of sub x sub tiles as wavefronts of their own.  Every segment length, ragged last chunks, a line whose last
+    segment is a single chunk (33 chunks, sub 16), and the whole-line case (sub >= chunks)."""
+    rng = np.random.default_rng(hash((sub, shape)) % 2 ** 32)
+    f = rng.random(shape)
+    want = O.derivative(f, 0, 0.1), O.derivative(f, 1, 0.2)
+    try:
+        os.environ["CFD_XY_SUB"] = str(sub)
+        s = C.CompactFiniteDifferenceSolver(shape)
+        gx, gy = s.dfdxy(dev(f), 0.1, 0.2)
+        assert relinf(gx.cpu().numpy(), want[0]) <= TOL and relinf(gy.cpu().numpy(), want[1]) <= TOL
+    finally:
+        os.environ.pop("CFD_XY_SUB", None)
+    gx, gy = s.dfdxy(dev(f), 0.1, 0.2)                  # the same plan falls back to whole lines when the knob goes
+    assert relinf(gx.cpu().numpy(), want[0]) <= TOL and relinf(gy.cpu().numpy(), want[1]) <= TOL
+
+
 def test_fused_xy_per_plan_warps(C):
     """cfd_plan_set_xy_warps: the per-plan knob a caller uses to leave room for kernels running beside the launch."""
     shape = (37, 64, 130)

@@ -210,11 +210,13 @@ def test_chunk_schedule_random_property():
 # ---------------------------------------------------------------------------------------------------
 # cfd_apply_xy: the wavefront draw order (host table)
 # ---------------------------------------------------------------------------------------------------
-def _xy_order(nz, nxp, nyp, active):
-    from compact_finite_differences_b200._lib import check, lib
-    out = np.zeros(nz * (nxp + nyp), dtype=np.int32)
-    check(lib().cfd_debug_xy_order(nz, nxp, nyp, float(active), out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))))
-    return out
+def _xy_order(nz, nxp, nyp, active, sub=0):
+    from compact_finite_differences_b200._lib import lib
+    n = lib().cfd_debug_xy_order(nz, nxp, nyp, float(active), sub, None, 0)
+    assert n >= nz * (nxp + nyp)
+    out = np.zeros(n, dtype=np.int32)
+    assert lib().cfd_debug_xy_order(nz, nxp, nyp, float(active), sub, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), n) == n
+    return out >> 3, out & 7
 
 
 @pytest.mark.parametrize("nz,nxp,nyp,active", [(1, 1, 1, 3.0), (7, 16, 16, 18.5), (40, 8, 8, 37.0), (5, 2, 32, 4.0),
@@ -223,9 +225,9 @@ def test_xy_draw_order_is_a_wavefront(nz, nxp, nyp, active):
     """Every (plane, bundle) item exactly once; inside a plane the x and y bundles come in ascending order (bundle j
     starts j tile-times after bundle 0, so both readers of tile (j, k) reach it j + k tile-times in); bundle j of the
     two directions is drawn back to back; planes start in ascending order, `active` of them in flight."""
-    order = _xy_order(nz, nxp, nyp, active)
+    order, seg = _xy_order(nz, nxp, nyp, active)
     ipp = nxp + nyp
-    assert sorted(order.tolist()) == list(range(nz * ipp))
+    assert sorted(order.tolist()) == list(range(nz * ipp)) and not seg.any()
     if active == 0.0:
         assert order.tolist() == list(range(nz * ipp))
         return
@@ -246,6 +248,47 @@ def test_xy_draw_order_is_a_wavefront(nz, nxp, nyp, active):
         last = pos[z * ipp:(z + 1) * ipp].max()
         started = sum(1 for zz in range(z + 1, nz) if first[zz] < last)
         assert started <= int(np.ceil(active)) + 1
+
+
+@pytest.mark.parametrize("nz,nxp,nyp,sub", [(3, 32, 32, 16), (2, 32, 8, 16), (2, 5, 40, 4), (1, 64, 64, 4), (4, 7, 7, 2),
+                                            (2, 16, 16, 16), (2, 33, 17, 16)])
+def test_xy_draw_order_sub_planes(nz, nxp, nyp, sub):
+    """Sub-plane wavefronts: lines longer than `sub` tiles are cut into segments; every line has each of its
+    segments exactly once, the segments tile the line, and an x segment is drawn next to the y segments that share
+    its square of tiles (same plane, x bundle inside the y segment's chunk range and vice versa)."""
+    order, seg = _xy_order(nz, nxp, nyp, 5.0, sub)
+    ipp = nxp + nyp
+    kmax = max(nxp, nyp)
+    ks = sub if sub * 7 >= kmax else (kmax + 6) // 7
+    cut = nxp > ks or nyp > ks
+    ngx = -(-nyp // ks) if (cut and nyp > ks) else 1          # segments of an x line (nyp tiles long)
+    ngy = -(-nxp // ks) if (cut and nxp > ks) else 1
+    assert seg.max() <= 7
+    seen = {}
+    for e, s in zip(order.tolist(), seg.tolist()):
+        seen.setdefault(e, []).append(s)
+    assert sorted(seen) == list(range(nz * ipp))
+    for e, segs in seen.items():
+        is_x = (e % ipp) < nxp
+        ng = ngx if is_x else ngy
+        assert sorted(segs) == ([0] if ng == 1 else list(range(1, ng + 1))), (e, segs)
+    if not cut:
+        return
+    # neighbours in the draw belong to the same square: an (x, y) pair drawn back to back shares tiles
+    sy, sx = (ks if ngy > 1 else nxp), (ks if ngx > 1 else nyp)
+    pairs = 0
+    for i in range(len(order) - 1):
+        e0, e1 = order[i], order[i + 1]
+        if e0 // ipp != e1 // ipp:
+            continue
+        r0, r1 = e0 % ipp, e1 % ipp
+        if r0 < nxp <= r1:                                    # x item followed by a y item of the same plane
+            j, k = r0, r1 - nxp
+            b = seg[i] - 1 if ngx > 1 else 0                  # x segment index = x block of the square
+            a = seg[i + 1] - 1 if ngy > 1 else 0              # y segment index = y block of the square
+            if j // sy == a and k // sx == b:
+                pairs += 1
+    assert pairs >= nz * min(nxp, nyp) // 2
 
 
 # ---------------------------------------------------------------------------------------------------
