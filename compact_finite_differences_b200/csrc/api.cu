@@ -556,7 +556,9 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
 {
     const int max_warps = nslot == 3 ? 8 : 7, def_warps = nslot == 3 ? 8 : 6;
     int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
-    sub = 0;                                                   // sub-plane wavefronts: experiment switch, off by default
+    // Sub-plane wavefronts for lines of >= 32 tiles ([128,1024,1024]: 0.578 -> 0.561 ms with squares of 16 x 16 tiles;
+    // 512^3 with 8 x 8: 0.541 -> 0.582, so shorter lines stay whole).  CFD_XY_SUB overrides (0 = never cut).
+    sub = (Kx >= 32 || Ky >= 32) ? 16 : 0;
     if (const char *e = getenv("CFD_XY_SUB")) sub = atoi(e) > 0 ? atoi(e) : 0;
     if (sub > 0) {                                             // tiles an item walks when its line is cut
         const int kmax = Kx > Ky ? Kx : Ky;
@@ -832,14 +834,15 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.tau_ns = (px->g.K + py->g.K >= 64) ? 1000.f : 0.f;
     if (const char *e = getenv("CFD_XY_TAU")) q.tau_ns = (float)atof(e);
     const size_t smem = (size_t)warps * per_warp + 1024;
-    auto kern = stream_kernel_xy<NSLOT>;
-    static size_t configured[MAX_DEVICES] = {0};
+    const bool seg = q.kseg > 0;          // whole lines only: the variant without segment state
+    auto kern = seg ? stream_kernel_xy<NSLOT, true> : stream_kernel_xy<NSLOT, false>;
+    static size_t configured[2][MAX_DEVICES] = {{0}, {0}};
     int dev = 0;
     rc = current_device(dev);
     if (rc) return rc;
-    if (configured[dev] < smem) {
+    if (configured[seg][dev] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[dev] = smem;
+        configured[seg][dev] = smem;
     }
     rc = counter_pair(&q.counter);
     if (rc) return rc;
@@ -881,7 +884,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     const size_t smem = (size_t)warps * per_warp + 1024;
-    auto kern = stream_kernel_xy<NSLOT>;
+    auto kern = stream_kernel_xy<NSLOT, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * per_warp + 1024));
     rc = counter_pair(&q.counter);
     if (rc) return rc;

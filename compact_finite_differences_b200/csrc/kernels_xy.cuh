@@ -39,15 +39,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // the TMA store has finished reading it.  24 KiB per warp instead of 40 puts 8 warps on an SM (two per scheduler):
 // with one warp per scheduler every fixed-latency dependency of the recurrences is exposed and the pair of
 // derivatives is latency-bound (0.825 / 0.641 / 0.553 ms with 3 / 4 / 5 warps, time x warps = const).
-template <bool CONTIG, int NS, class Issue>
+template <bool CONTIG, int NS, bool SEG, class Issue>
 __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap *tm_out, long b, int oc0, int oc2,
                                             unsigned char *wbase, uint32_t bar0, int lane, int &slot, uint32_t &phase,
-                                            bool &first_step, Issue &issue, int kbeg, int kend, int kout, int kstop)
+                                            bool &first_step, Issue &issue, int kbeg_, int kend_, int kout_, int kstop_)
 {
     // Tiles kbeg .. kend of the line, results for chunks kout .. kstop-1: the whole line (0, K-1, 0, K), or a
     // segment with one warm-up chunk in front (forward sweep from a zero state, exact to
     // 0.268^32 like the backward look-ahead) and the look-ahead chunk behind -- the same cut as kernels.cuh makes.
+    // SEG = false (whole lines only) folds the range to (0, K-1, 0, K) at compile time: the kernel of the common
+    // case carries no segment state in its 255 registers.
     const int K = p.K;
+    const int kbeg = SEG ? kbeg_ : 0, kend = SEG ? kend_ : K - 1, kout = SEG ? kout_ : 0, kstop = SEG ? kstop_ : K;
     double eA[CH], eB[CH], F[CH];
     double eprev = 0.0, fm1 = 0.0, fm2 = 0.0;
 #pragma unroll 1
@@ -124,7 +127,7 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
     }
 }
 
-template <int NS>
+template <int NS, bool SEG>
 __global__ void __launch_bounds__(256, 1)
 stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_constant__ CUtensorMap tmx_out,
                  const __grid_constant__ CUtensorMap tmy_in, const __grid_constant__ CUtensorMap tmy_out,
@@ -159,7 +162,7 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         if (contig) { b = z * q.nxp + r; c0 = 0; c2 = 0; }
         else        { b = z * q.nyp + (r - q.nxp); c0 = (r - q.nxp) * CH; c2 = (int)z; }
         const int K = contig ? px.K : py.K;
-        if (seg == 0) { kb = 0; ke = K - 1; ko = 0; kp = K; }
+        if (!SEG || seg == 0) { kb = 0; ke = K - 1; ko = 0; kp = K; }
         else {
             const int s0 = (seg - 1) * q.kseg;
             const int s1 = (s0 + q.kseg < K) ? s0 + q.kseg : K;
@@ -223,8 +226,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         long b;
         int c0, c2, kb, ke, ko, kp;
         decode(w, contig, b, c0, c2, kb, ke, ko, kp);
-        if (contig) xy_run_item<true, NS>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
-        else        xy_run_item<false, NS>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
+        if (contig) xy_run_item<true, NS, SEG>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
+        else        xy_run_item<false, NS, SEG>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
     }
     if (lane == 0) {
         tma_wait_all0();
