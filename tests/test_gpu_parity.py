@@ -215,7 +215,7 @@ def test_fused_xy_sub_plane_wavefronts(C, sub, shape):
         assert relinf(gx.cpu().numpy(), want[0]) <= TOL and relinf(gy.cpu().numpy(), want[1]) <= TOL
     finally:
         os.environ.pop("CFD_XY_SUB", None)
-    gx, gy = s.dfdxy(dev(f), 0.1, 0.2)                  # the same plan falls back to whole lines when the knob goes
+    gx, gy = s.dfdxy(dev(f), 0.1, 0.2)                  # the same plan returns to its default cut when the knob goes
     assert relinf(gx.cpu().numpy(), want[0]) <= TOL and relinf(gy.cpu().numpy(), want[1]) <= TOL
 
 
