@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import cfd_oracle as O
-from tests.conftest import GOLD
+from tests.conftest import GOLD, convergence_ratios
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -90,6 +90,18 @@ def test_derivative_random(C, shape, axis):
     want = O.derivative(f, axis, h)
     got = C.CompactFiniteDifferenceSolver(shape, h, axis)(dev(f)).cpu().numpy()
     assert relinf(got, want) <= TOL
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_order_of_convergence(C, axis):
+    """code/cuda/test/test_convergence.py:25-52 on the CUDA path: mean error ~16x per doubling (4th-order interior),
+    max error ~8x (3rd-order closures); the same bounds the oracle meets in tests/test_oracle.py."""
+    def derivative(f, ax, h):
+        return C.CompactFiniteDifferenceSolver(f.shape, h, ax)(dev(f)).cpu().numpy()
+    mean_r, max_r = convergence_ratios(derivative, axis)
+    assert 14.0 < mean_r[-1] < 17.5, mean_r
+    assert 6.5 < max_r[-1] < 9.0, max_r
+    assert all(r > 8.0 for r in mean_r)
 
 
 def test_reference_spellings_and_analytic(C):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import cfd_oracle as O
-from tests.conftest import GOLD
+from tests.conftest import GOLD, convergence_ratios
 
 KNOWN = {32: "0.0000293338", 64: "0.0000010363", 128: "0.0000000420", 256: "0.0000000019"}
 
@@ -153,3 +153,14 @@ def test_distributed_npts_c_twin_defect():
     blk = np.abs(bad - want).reshape(2, 2, 4, 4).max(axis=(0, 1))      # [rank, position in block]
     assert blk[0].argmax() == 3 and blk[1].argmax() == 3               # worst at the last element of a block
     assert relinf(O.npts_distributed_solve(r, 4), want) < 1e-14
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_order_of_convergence_oracle(axis):
+    """code/cuda/test/test_convergence.py (prints, no assert): 4th-order interior -> mean error falls ~16x per
+    doubling; 3rd-order closures dominate the max error -> ~8x."""
+    O.port().oracle_set_num_threads(os.cpu_count() or 1)
+    mean_r, max_r = convergence_ratios(O.derivative, axis)
+    assert 14.0 < mean_r[-1] < 17.5, mean_r
+    assert 6.5 < max_r[-1] < 9.0, max_r
+    assert all(r > 8.0 for r in mean_r)
