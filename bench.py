@@ -227,7 +227,7 @@ def run_reference(args):
     print(json.dumps(line), file=RESULT, flush=True)
 
 
-def workload_config(n_gpus, comm="nvlink", overlap=True):
+def workload_config(n_gpus, comm="nvlink", overlap=True, fused_edge=False):
     if n_gpus == 1:
         return {"workload": "512^3 fp64 field, derivative along x, y and z on 1 B200 (BASELINE configs[2])",
                 "grid": [512, 512, 512], "derivatives_per_step": 3, "partition": "none",
@@ -236,11 +236,184 @@ def workload_config(n_gpus, comm="nvlink", overlap=True):
     return {"workload": f"1024^3 fp64 field z-partitioned over {n_gpus} B200, derivative along x, y and z "
                         "(d/dz: one-plane halo + interface exchange with the z-neighbours + coupled solve; BASELINE configs[3])",
             "grid": [1024, 1024, 1024], "derivatives_per_step": 3, "partition": f"z/{n_gpus}",
-            "step": "per rank: one fused d/dx + d/dy launch on the slab + the partitioned d/dz",
+            "step": ("per rank three launches (cfd_zpart_apply_xyz): fused d/dx + d/dy kernel whose first work items are the "
+                     "edge faces of d/dz (pushed to the z-neighbours over NVLink), reduced solve, coupled d/dz kernel")
+            if fused_edge else "per rank: one fused d/dx + d/dy launch on the slab + the partitioned d/dz",
             "ddz": f"fused (edge faces -> {comm} exchange -> coupled kernel)",
-            "overlap": "d/dz exchange started before d/dx, d/dy" if overlap else "none",
+            "overlap": ("exchange inside the x/y launch" if fused_edge else
+                        "d/dz exchange started before d/dx, d/dy" if overlap else "none"),
             "l2": "inputs (slab >= 1 GiB) larger than the 126 MB L2; no flush needed"}
 
+
+
+# ----------------------------------------------------------------------------------------------------
+# in-run correctness checks (outside the timed region) and the extra driver-visible configurations
+# ----------------------------------------------------------------------------------------------------
+def check_derivatives(f, df, h, N, rank, world, nz_loc, dev, dist, nsample=256):
+    """All three derivatives of the timed step against (a) the analytic derivative of the synthetic field, whole
+    field, every rank, and (b) the CPU oracle on `nsample` sampled lines per direction -- z lines gathered across the
+    ranks, so the partitioned d/dz (the only part that communicates) is checked end to end.  The oracle is the checker
+    here, never the thing measured."""
+    import torch
+    from oracle import cfd_oracle as O
+    t1 = torch.arange(N, dtype=torch.float64, device=dev) * h
+    zz = t1[rank * nz_loc:(rank + 1) * nz_loc]
+    sx, cx = torch.sin(t1)[None, None, :], torch.cos(t1)[None, None, :]
+    sy, cy = torch.sin(t1)[None, :, None], torch.cos(t1)[None, :, None]
+    sz, cz = torch.sin(zz)[:, None, None], torch.cos(zz)[:, None, None]
+    errs = []
+    for a, ex in enumerate((lambda: cx * cy * sz, lambda: -sx * sy * sz, lambda: sx * cy * cz)):
+        e = ex()
+        errs.append((df[a] - e).abs().max().item())
+        del e
+    g = torch.Generator().manual_seed(1234)                      # the same sample on every rank
+    iz = torch.randint(0, nz_loc, (nsample,), generator=g)
+    iy = torch.randint(0, N, (nsample,), generator=g)
+    ix = torch.randint(0, N, (nsample,), generator=g)
+    iy[:4] = torch.tensor([0, 0, N - 1, N - 1]); ix[:4] = torch.tensor([0, N - 1, 0, N - 1])   # corner lines too
+    izd, iyd, ixd = iz.to(dev), iy.to(dev), ix.to(dev)
+    rel = []
+    # x lines and y lines live inside the slab
+    for a, (lines_f, lines_d) in enumerate(((f[izd, iyd, :], df[0][izd, iyd, :]),
+                                            (f[izd, :, ixd], df[1][izd, :, ixd]))):
+        want = O.derivative(np.ascontiguousarray(lines_f.cpu().numpy()[None]), 0, h)[0]
+        rel.append(float(np.abs(lines_d.cpu().numpy() - want).max() / np.abs(want).max()))
+    # z lines: every rank contributes its part of the sampled columns
+    part_f, part_d = f[:, iyd, ixd].contiguous(), df[2][:, iyd, ixd].contiguous()          # [nz_loc, nsample]
+    if world > 1:
+        all_f = [torch.empty_like(part_f) for _ in range(world)]
+        all_d = [torch.empty_like(part_d) for _ in range(world)]
+        dist.all_gather(all_f, part_f)
+        dist.all_gather(all_d, part_d)
+        part_f, part_d = torch.cat(all_f, 0), torch.cat(all_d, 0)
+    zl_f = np.ascontiguousarray(part_f.cpu().numpy().T)                                     # [nsample, N]
+    want = O.derivative(zl_f[None], 0, h)[0]
+    rel.append(float(np.abs(part_d.cpu().numpy().T - want).max() / np.abs(want).max()))
+    t = torch.tensor(errs + rel, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    v = t.tolist()
+    out = {"ddx_max_abs_err_vs_analytic": v[0], "ddy_max_abs_err_vs_analytic": v[1], "ddz_max_abs_err_vs_analytic": v[2],
+           "ddx_rel_linf_vs_oracle": v[3], "ddy_rel_linf_vs_oracle": v[4], "ddz_rel_linf_vs_oracle": v[5],
+           "oracle_lines_per_direction": nsample, "ranks_checked": world}
+    assert max(v[:3]) < 1e-6, f"analytic check failed: {out}"
+    assert max(v[3:]) <= 1e-12, f"oracle parity failed: {out}"
+    return out
+
+
+def _time_calls(fn, reps=20, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def extra_configs(C, dev, peak):
+    """BASELINE configs[1] (256^3 along x, y, z), four corners of configs[4] (solver-only sweep) and the 1024^3
+    gradient on ONE GPU (the like-for-like point of the multi-GPU curve), each timed with CUDA events over 20
+    back-to-back calls after 3 warm-ups.  256^3 (128 MiB in + 128 MiB out) is of the order of the 126 MB L2: the
+    rotating set below (4 field pairs, 1 GiB) keeps every call's input out of L2."""
+    import torch
+    out = {}
+    N = 256
+    h = 2 * np.pi / (N - 1)
+    t1 = torch.arange(N, dtype=torch.float64, device=dev) * h
+    fs = [(torch.sin(t1 + 0.1 * i)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(t1)[:, None, None]).contiguous()
+          for i in range(4)]
+    ds = [torch.empty_like(fs[0]) for _ in range(4)]
+    per_axis = {}
+    for a in range(3):
+        op = C.CompactFiniteDifferenceSolver((N, N, N), h, a)
+        k = [0]
+
+        def call():
+            op(fs[k[0] & 3], ds[k[0] & 3])
+            k[0] += 1
+        ms = _time_calls(call)
+        gbs = 16 * N ** 3 / (ms * 1e-3) / 1e9
+        per_axis["xyz"[a]] = {"ms": ms, "GBps": gbs, "frac_of_measured": gbs / peak, "frac_of_8TBps": gbs / 8000.0}
+    g = C.CompactFiniteDifferenceSolver((N, N, N))
+    k = [0]
+
+    def grad():
+        g.gradient(fs[k[0] & 3], (h, h, h), (ds[0], ds[1], ds[2]))
+        k[0] += 1
+    per_axis["gradient_ms"] = _time_calls(grad)
+    out["256^3 (configs[1])"] = per_axis
+    del fs, ds
+    sweep = []
+    for n, batch in ((32, 1 << 10), (32, 1 << 20), (4096, 1 << 10), (4096, 1 << 18)):      # 2^30-unknown cap
+        d = torch.rand((1, batch, n), dtype=torch.float64, device=dev)
+        sol = C.NearToeplitzSolver(d.shape, [1., 2., 0.25, 1., 0.25, 2., 1.])
+        ms = _time_calls(lambda: sol.solve(d))
+        sweep.append({"n": n, "batch": batch, "ms": ms, "GBps": 16 * n * batch / (ms * 1e-3) / 1e9,
+                      "in_L2": bool(8 * n * batch < 100e6)})
+        del d, sol
+    out["solver_sweep_corners (configs[4])"] = sweep
+    N = 1024
+    h = 2 * np.pi / (N - 1)
+    t1 = torch.arange(N, dtype=torch.float64, device=dev) * h
+    f = (torch.sin(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(t1)[:, None, None]).contiguous()
+    df = [torch.empty_like(f) for _ in range(3)]
+    g = C.CompactFiniteDifferenceSolver((N, N, N))
+    ms = _time_calls(lambda: g.gradient(f, (h, h, h), df), reps=10)
+    out["1024^3 gradient on 1 GPU (like-for-like point of the multi-GPU curve)"] = {
+        "ms_per_step": ms, "points_per_s_per_derivative": 3 * N ** 3 / (ms * 1e-3)}
+    del f, df
+    torch.cuda.empty_cache()
+    return out
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, so that the pinned host buffers of the
+    e2e leg are allocated (first touch) in memory local to the GPU's PCIe root.  Returns (node, previous affinity)."""
+    import torch
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node, prev
+    except Exception:
+        pass
+    return None, None
+
+
+def copy_ceiling(f, out_host, f_host, reps=2):
+    """Pinned-copy ceiling of the e2e step on this rank: H2D of the field and D2H of three results, both directions
+    at once, no kernel.  Returns seconds per step."""
+    import torch
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    tmp = torch.empty_like(f)
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            tmp.copy_(f_host, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for o in out_host:
+                o.copy_(f, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
 
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
@@ -271,12 +444,20 @@ def run_ours(args):
     ddz = C.ZPartitionedDerivative((nz_loc, N, N), h, 2, mode="fused", comm=args.comm) if world > 1 else \
         C.CompactFiniteDifferenceSolver((nz_loc, N, N), h, 2)
     pts_local = f.numel()
-    # 5 instead of 6 warps per SM when the d/dz exchange chain runs beside the fused launch on thin slabs
-    # (scripts/overlap_timeline.py; measured: 128-plane slabs 1.123 vs 1.146 ms per step, 256 planes equal, 512 planes
-    # 1.2 % slower with 5)
-    xy_warps = 5 if (world > 1 and not args.no_overlap and nz_loc <= 128) else None
+    # N > 1, default: the whole slab gradient in three launches (cfd_zpart_apply_xyz) -- the edge-face work of d/dz
+    # rides in the fused d/dx + d/dy kernel as its first work items.  --chain = the round-1 step instead: exchange
+    # chain on a side stream beside the x/y launch (5 instead of 6 xy warps on thin slabs to leave it room).
+    fused_edge = world > 1 and args.comm == "nvlink" and not args.chain and not args.separate
+    xy_warps = 5 if (world > 1 and not fused_edge and not args.no_overlap and nz_loc <= 128) else None
 
     def gradient(src, events=None):
+        if fused_edge:
+            if events is not None:
+                events[0][0].record()
+            ddz.gradient(src, h, h, df)
+            if events is not None:
+                events[1][1].record()
+            return
         if world > 1 and not args.no_overlap:
             ddz.begin(src)           # halo + interface exchange of d/dz overlaps the d/dx + d/dy kernel
         if events is not None:
@@ -305,12 +486,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
+    if fused_edge:
+        assert ddz.comm == "nvlink", "CUDA IPC unavailable: the fused step fell back; rerun with --chain --comm pairwise"
 
-    # sanity: the timed kernels produce the derivative (analytic check, cheap, outside the timed region)
-    ex = torch.cos(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(zz)[:, None, None]
-    err = (df[0] - ex).abs().max().item()
-    del ex
-    assert err < 1e-6, f"d/dx check failed: {err}"
+    # in-run correctness of the timed path, all three derivatives, every rank (cheap, outside the timed region)
+    check = check_derivatives(f, df, h, N, rank, world, nz_loc, dev, dist)
 
     launches0 = C.lib().cfd_launch_count()
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
@@ -325,7 +505,26 @@ def run_ours(args):
         fence()
     launches = C.lib().cfd_launch_count() - launches0
     ms = t_beg.elapsed_time(t_end)
-    per_launch = [float(np.mean([ev[s][a][0].elapsed_time(ev[s][a][1]) for s in range(args.steps)])) for a in range(2)]
+    if fused_edge:
+        # the three launches are issued by ONE C call: per-launch durations come from a second, untimed pass through
+        # the same entry points one at a time (begin = edge + reduce, cfd_apply_xy, coupled d/dz) -- they explain the
+        # step, they are not part of `value`
+        span = float(np.mean([ev[s][0][0].elapsed_time(ev[s][1][1]) for s in range(args.steps)]))
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = np.zeros(3)
+        for _ in range(5):
+            fence()
+            e[0].record(); ddz.begin(f); e[1].record(); xy.dfdxy(f, h, h, df[0], df[1]); e[2].record()
+            ddz(f, df[2]); e[3].record()
+            torch.cuda.synchronize()
+            acc += [e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])]
+        acc /= 5
+        per_launch = [span - float(acc[2]), float(acc[2])]      # [fused x/y + edge items (+ reduce), coupled d/dz]
+        pieces = {"edge_plus_reduce_standalone_ms": float(acc[0]), "xy_standalone_ms": float(acc[1]),
+                  "z_coupled_standalone_ms": float(acc[2]), "step_span_ms": span}
+    else:
+        per_launch = [float(np.mean([ev[s][a][0].elapsed_time(ev[s][a][1]) for s in range(args.steps)])) for a in range(2)]
+        pieces = None
     if world > 1:
         t = torch.tensor([ms] + per_launch, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,9 +536,12 @@ def run_ours(args):
 
     # ---- e2e: host buffers in pinned memory through the public host API, copies inside the timed region
     e2e_steps = max(1, min(args.steps, 3))
+    numa_node, prev_aff = bind_to_gpu_numa_node(local) if world > 1 else (None, None)   # NUMA-local pinned buffers
     f_host = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
     f_host.copy_(f)
     out_host = [torch.empty(f.shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+    for o in out_host:
+        o.zero_()                      # first touch here, on the bound cores
     # "pipelined" = HostGradient: H2D in z-slabs, fused d/dx + d/dy per slab, D2H overlapping the remaining H2D, then
     # d/dz + D2H (at N > 1 each rank pipelines its own slab and d/dz is the partitioned operator).  "sequential" =
     # H2D, gradient, D2H one after the other.  Measured: pipelined wins on one GPU (62.7 vs ~78 ms per step); with two
@@ -367,63 +569,91 @@ def run_ours(args):
         e2e_step()
     fence()
     e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-    e2e_value = (N ** 3) * 3 * e2e_steps / e2e_s
     step()                     # refresh df with the device-resident result for the comparison below
     torch.cuda.synchronize()
     e2e_ok = all(float((out_host[a] - df[a].cpu()).abs().max()) == 0.0 for a in range(3))
+    # pinned-copy ceiling of the same step: all ranks copy at once (they share the host's memory system), no kernels
+    fence()
+    ceil_s = copy_ceiling(f, out_host, f_host)
+    if world > 1:
+        t = torch.tensor([e2e_s, ceil_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s, ceil_s = t.tolist()
+    e2e_value = (N ** 3) * 3 * e2e_steps / e2e_s
+    ceil_value = (N ** 3) * 3 / ceil_s
+    if prev_aff:
+        os.sched_setaffinity(0, prev_aff)
+    del f_host, out_host
 
-    # ---- roofline of the dominant kernel, live CUDA-event duration.  The fused d/dx + d/dy launch is the longest
-    # one of the step; the bytes it cannot avoid are f once + two results = 24 B/point (the two derivatives as separate
-    # passes are 2 x 16 B/point -- that credit is reported next to it, not used for `frac`).
+    # ---- roofline, live CUDA-event durations.  The fused d/dx + d/dy launch is the longest one of the step; the bytes
+    # it cannot avoid are f once + two results = 24 B/point (the two derivatives as separate passes are 2 x 16 B/point
+    # -- that credit is reported next to it, not used for `frac`).  At N > 1 the launch also carries the edge-face
+    # items of d/dz (67 of nz_loc planes re-read): they are overhead, not credited.
     peak, peak_src = measured_peak()
     xy_bytes = (2 * BYTES_PER_POINT if args.separate else 24) * pts_local
     z_bytes = BYTES_PER_POINT * pts_local
     gbps = [xy_bytes / (per_launch[0] * 1e-3) / 1e9, z_bytes / (per_launch[1] * 1e-3) / 1e9]
     dom = int(np.argmax(per_launch))
-    names = ["stream_kernel d/dx, d/dy (two launches)" if args.separate else "stream_kernel_xy (d/dx + d/dy, one launch)",
-             "stream_kernel d/dz"]
+    names = ["stream_kernel d/dx, d/dy (two launches)" if args.separate else
+             ("stream_kernel_xy (d/dx + d/dy + edge-face items of d/dz, one launch) + reduced_planes" if fused_edge else
+              "stream_kernel_xy (d/dx + d/dy, one launch)"), "stream_kernel d/dz"]
+    # dram bytes (read + write) per launch from `ncu --set full`, keyed by kernel and slab shape; null when this shape
+    # has not been profiled (profiles/traffic.json names the capture each figure comes from)
+    shape_key = f"{nz_loc}x{N}x{N}"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    tkeys = [("xy_edge@" if fused_edge else "xy@") + shape_key, ("z_coupled@" if world > 1 else "z@") + shape_key]
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": gbps[dom], "peak": peak,
-                "unit": "GB/s", "frac": gbps[dom] / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": gbps[dom] / peak, "traffic": traffic.get(tkeys[dom]), "peak_source": peak_src,
                 "frac_of_8TBps_nominal": gbps[dom] / 8000.0,
-                "per_launch_ms": {"xy": per_launch[0], "z": per_launch[1]},
-                "per_launch_GBps": {"xy": gbps[0], "z": gbps[1]},
+                "launches": {
+                    "xy": {"kernel": names[0], "ms": per_launch[0], "algorithmic_bytes": xy_bytes, "achieved": gbps[0],
+                           "frac": gbps[0] / peak, "traffic": traffic.get(tkeys[0])},
+                    "z": {"kernel": names[1], "ms": per_launch[1], "algorithmic_bytes": z_bytes, "achieved": gbps[1],
+                          "frac": gbps[1] / peak, "traffic": traffic.get(tkeys[1])}},
                 "algorithmic_bytes_per_launch": [xy_bytes, z_bytes][dom],
                 "step_GBps_at_16B_per_point_per_derivative":
                     3 * BYTES_PER_POINT * pts_local * args.steps / (ms * 1e-3) / 1e9}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(["xy", "z"][dom])
-        except Exception:
-            pass
+    if pieces:
+        roofline["pieces"] = pieces
+
+    extra = None
+    if world == 1 and not args.no_extra:
+        del df, f
+        torch.cuda.empty_cache()
+        extra = extra_configs(C, dev, peak)
 
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if not args.no_cpu:
             r, kind, cores, sample = cpu_reference_rate(seconds_budget=12.0, n=N)
             cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, args.comm, not args.no_overlap),
+            "config": workload_config(world, args.comm, not args.no_overlap, fused_edge),
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": f.numel() * 8 * world,
-                    "d2h_bytes_per_step": 3 * f.numel() * 8 * world, "steps": e2e_steps, "verified": e2e_ok,
-                    "mode": e2e_mode},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pts_local * 8 * world,
+                    "d2h_bytes_per_step": 3 * pts_local * 8 * world, "steps": e2e_steps, "verified": e2e_ok,
+                    "mode": e2e_mode, "pinned_copy_ceiling": ceil_value, "frac_of_copy_ceiling": e2e_value / ceil_value,
+                    "numa_node_of_rank0_buffers": numa_node,
+                    "ceiling": "H2D of f + D2H of three results, both directions at once on every rank, no kernels"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "check": {"ddx_max_abs_err_vs_analytic": err},
+            "check": check,
         }
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), file=RESULT, flush=True)
     if world > 1:
         dist.barrier()
+        ddz.close()
         dist.destroy_process_group()
     return line
 
@@ -442,6 +672,10 @@ def main():
     ap.add_argument("--e2e", default="auto", choices=["auto", "pipelined", "sequential"],
                     help="host-buffer leg: HostGradient slab pipeline, or H2D -> gradient -> D2H in sequence")
     ap.add_argument("--separate", action="store_true", help="d/dx and d/dy as two launches instead of cfd_apply_xy")
+    ap.add_argument("--chain", action="store_true",
+                    help="N > 1: the round-1 step (exchange chain on a side stream beside the x/y launch) instead of "
+                         "the three-launch cfd_zpart_apply_xyz step")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the extra configurations (256^3, solver sweep, 1024^3)")
     args = ap.parse_args()
     _reserve_stdout()
     if args.impl == "reference":

@@ -7,7 +7,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfd_b200.so")
 
-CFD_OK, CFD_EINVAL, CFD_ECUDA, CFD_EUNSUPPORTED = 0, -1, -2, -3
+CFD_OK, CFD_EINVAL, CFD_ECUDA, CFD_EUNSUPPORTED, CFD_ETIMEOUT = 0, -1, -2, -3, -4
+CFD_IPC_HANDLE_BYTES = 64
 
 # every symbol include/cfd_b200.h declares: (restype, argtypes)
 _i, _l, _d, _vp = ctypes.c_int, ctypes.c_long, ctypes.c_double, ctypes.c_void_p
@@ -37,6 +38,20 @@ SIGNATURES = {
     "cfd_edge_faces_push": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_reduced_unknowns_deferred": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_ulonglong, _vp]),
     "cfd_apply_host": (_i, [_vp, _vp, _vp, _i]),
+    "cfd_pthomas_create": (_i, [_pp, _dp, _dp, _dp, _i]),
+    "cfd_pthomas_solve": (_i, [_vp, _vp, _l, _vp]),
+    "cfd_pthomas_destroy": (None, [_vp]),
+    "cfd_zpart_create": (_i, [_pp, _vp]),
+    "cfd_zpart_export": (_i, [_vp, _vp]),
+    "cfd_zpart_connect": (_i, [_vp, _vp, _vp]),
+    "cfd_zpart_buffer": (_vp, [_vp]),
+    "cfd_zpart_connect_ptr": (_i, [_vp, _vp, _vp]),
+    "cfd_zpart_begin": (_i, [_vp, _vp, _vp]),
+    "cfd_zpart_apply": (_i, [_vp, _vp, _vp, _vp]),
+    "cfd_zpart_apply_xyz": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_zpart_destroy": (None, [_vp]),
+    "cfd_set_wait_timeout_ms": (_i, [_l]),
+    "cfd_async_status": (_i, []),
     "cfd_plane_elems": (_l, [_vp]),
     "cfd_tables_size": (_i, []),
     "cfd_plan_tables": (_i, [_vp, _dp]),

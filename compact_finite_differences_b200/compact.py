@@ -72,11 +72,13 @@ class CompactFiniteDifferenceSolver:
         :param part: (rank, size) of this block along the derivative line -- the reference's
                      (line_da.rank, line_da.size), code/cuda/compact.py:159-166.  (0, 1) = whole line here.
         """
+        self._group = None
         if hasattr(shape, "nz") and hasattr(shape, "rank"):            # a line_da of the reference
             da = shape
             part = (da.rank, da.size)
             if direction is None:
                 direction = getattr(da, "direction", 0)
+            self._group = getattr(da, "group", None)                   # DA.get_line_DA: the line's process group
             shape = (da.nz, da.ny, da.nx)
         assert len(shape) == 3, "shape is (nz, ny, nx)"
         self.shape = tuple(int(s) for s in shape)
@@ -84,6 +86,8 @@ class CompactFiniteDifferenceSolver:
         self.direction = None if direction is None else int(direction)
         self.spacing = None if spacing is None else float(spacing)
         self._plans = {}
+        self._last_h = None          # spacing of the last call that was given one (the reference passes dx per call)
+        self._line_ops = {}          # (axis, spacing) -> PartitionedDerivative of a multi-rank line
         if self.direction is not None:
             assert self.direction in (0, 1, 2), "direction is 0 (x), 1 (y) or 2 (z)"
             if self.spacing is not None:
@@ -99,7 +103,11 @@ class CompactFiniteDifferenceSolver:
         return p
 
     # -- the hot path --------------------------------------------------------------------------------
-    def _apply(self, axis, spacing, f, out=None, halo_lo=None, halo_hi=None):
+    def _apply(self, axis, spacing, f, out=None, halo_lo=None, halo_hi=None, local=False):
+        if self.part[1] > 1 and not local and axis == self.direction:
+            # The reference's multi-rank call shape (code/cuda/compact.py:29-44): the block of a partitioned line in,
+            # the derivative of the WHOLE line out -- halo exchange, reduced system and correction happen inside.
+            return self._line_op(axis, spacing)(f, out)
         plan = self._plan(axis, spacing)
         if isinstance(f, np.ndarray):
             return self._apply_host(plan, f, out)
@@ -139,7 +147,24 @@ class CompactFiniteDifferenceSolver:
     def apply_local(self, f, out=None, halo_lo=None, halo_hi=None):
         """Block-local solution x_R of a partitioned line (code/cuda/compact.py:46-64): needs the neighbour
         planes of f where this block does not own the physical end."""
-        return self._apply(self.direction, self.spacing, f, out, halo_lo, halo_hi)
+        return self._apply(self.direction, self._h(None, self.direction), f, out, halo_lo, halo_hi, local=True)
+
+    def _line_op(self, axis, spacing):
+        """PartitionedDerivative over this block's line group (the line_da's, or the default group when it has
+        exactly the line's size): the reference's multi-rank dfdx as one object, built on first use."""
+        key = (int(axis), float(spacing))
+        op = self._line_ops.get(key)
+        if op is None:
+            import torch.distributed as dist
+            from .partition import PartitionedDerivative
+            assert dist.is_initialized(), \
+                "a block of a multi-rank line needs torch.distributed (one process per GPU) -- or call apply_local / " \
+                "the stage methods with explicit halo planes"
+            assert dist.get_world_size(self._group) == self.part[1] and dist.get_rank(self._group) == self.part[0], \
+                "the line's process group does not match (rank, size) of the line_da"
+            op = PartitionedDerivative(self.shape, spacing, axis, group=self._group, mode="fused", comm="pairwise")
+            self._line_ops[key] = op
+        return op
 
     def dfdxy(self, f, dx, dy, out_x=None, out_y=None, warps=None):
         """d/dx and d/dy of f in ONE launch (cfd_apply_xy): the two derivatives share the HBM reads of f through L2.
@@ -176,9 +201,19 @@ class CompactFiniteDifferenceSolver:
 
     def _h(self, h, axis):
         if h is not None:
+            self._last_h = float(h)
             return float(h)
-        assert self.spacing is not None and self.direction == axis, f"spacing along {_AXIS_NAMES[axis]} not given"
-        return self.spacing
+        if self.spacing is not None and self.direction == axis:
+            return self.spacing
+        assert self._last_h is not None, f"spacing along {_AXIS_NAMES[axis]} not given"
+        return self._last_h
+
+    def _stage_plan(self):
+        """Plan for the stages that do not depend on the spacing (primary / secondary / reduced systems, sum): the
+        reference constructor takes no spacing (code/cuda/compact.py:18), so neither do they."""
+        axis = self._axis()
+        h = self.spacing if self.spacing is not None else (self._last_h if self._last_h is not None else 1.0)
+        return self._plan(axis, h)
 
     # -- the reference's stage methods (code/cuda/compact.py:46-154), each on its own kernel ------------------
     def compute_RHS(self, f, dx=None, x=None, f_local=None, halo_lo=None, halo_hi=None):
@@ -198,27 +233,54 @@ class CompactFiniteDifferenceSolver:
         """In-place block-local tridiagonal solve of the right-hand sides in x (compact.py:62-64)."""
         from .near_toeplitz import NearToeplitzSolver
         if getattr(self, "_primary", None) is None:
-            plan = self._plan(self._axis(), self._h(None, self._axis()))
             co = (ctypes.c_double * 7)()
-            check(lib().cfd_plan_coeffs(plan.handle, co))
+            check(lib().cfd_plan_coeffs(self._stage_plan().handle, co))
             self._primary = NearToeplitzSolver(self.shape, list(co), axis=self._axis())
         return self._primary.solve(x)
 
     def solve_secondary_systems(self):
         """(x_UH, x_LH): unit responses of the block matrix (compact.py:128-154), as CUDA tensors."""
         import torch
-        plan = self._plan(self._axis(), self._h(None, self._axis()))
         n = self.shape[2 - self._axis()]
         dp = ctypes.POINTER(ctypes.c_double)
         xu, xl = np.zeros(n), np.zeros(n)
-        check(lib().cfd_plan_secondary(plan.handle, xu.ctypes.data_as(dp), xl.ctypes.data_as(dp), None, None, None))
+        check(lib().cfd_plan_secondary(self._stage_plan().handle, xu.ctypes.data_as(dp), xl.ctypes.data_as(dp),
+                                       None, None, None))
         return torch.from_numpy(xu).cuda(), torch.from_numpy(xl).cuda()
 
-    def sum_solutions(self, x_R, alpha, beta):
-        """x_R += alpha * x_UH + beta * x_LH over the whole block (compact.py:52-61); the secondary solutions are
-        the plan's own."""
-        plan = self._plan(self._axis(), self._h(None, self._axis()))
-        check(lib().cfd_sum_solutions(plan.handle, x_R.data_ptr(), alpha.data_ptr(), beta.data_ptr(), _stream_ptr(x_R)))
+    def solve_reduced_system(self, x_UH, x_LH, x_R, group=None):
+        """(alpha, beta) planes of this block from the block-local solution x_R (compact.py:65-126): interface faces
+        (negateAndCopyFaces) -> all ranks of the line (the reference gathers to the line root, solves there and
+        scatters; here every rank receives the 2P planes and solves for its own two unknowns) -> reduced solve.
+        x_UH / x_LH are accepted for the reference's signature; the reduced matrix was built from them at plan
+        creation."""
+        import torch
+        import torch.distributed as dist
+        from .partition import gather_interface_planes
+        plan = self._stage_plan()
+        group = self._group if group is None else group
+        ps = tuple(s for d, s in enumerate(self.shape) if d != 2 - self._axis())
+        faces = torch.empty((2,) + ps, dtype=torch.float64, device=x_R.device)
+        check(lib().cfd_interface_pack(plan.handle, x_R.data_ptr(), faces.data_ptr(), _stream_ptr(x_R)))
+        assert dist.is_initialized() and dist.get_world_size(group) == self.part[1], \
+            "solve_reduced_system gathers over the line's process group"
+        faces_all = gather_interface_planes(faces, self.part[1], group)
+        ab = torch.empty((2,) + ps, dtype=torch.float64, device=x_R.device)
+        check(lib().cfd_reduced_unknowns(plan.handle, faces_all.data_ptr(), 0, ab.data_ptr(), None, None, 0,
+                                         _stream_ptr(x_R)))
+        return ab[0], ab[1]
+
+    def sum_solutions(self, *args):
+        """x_R += alpha * x_UH + beta * x_LH over the whole block (compact.py:52-61).  Reference signature
+        ``sum_solutions(x_UH, x_LH, x_R, alpha, beta)``; the short form ``sum_solutions(x_R, alpha, beta)`` uses the
+        plan's own secondary solutions (which is what the five-argument form receives from solve_secondary_systems)."""
+        if len(args) == 5:
+            _, _, x_R, alpha, beta = args
+        else:
+            x_R, alpha, beta = args
+        alpha, beta = alpha.contiguous(), beta.contiguous()
+        check(lib().cfd_sum_solutions(self._stage_plan().handle, x_R.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                                      _stream_ptr(x_R)))
         return x_R
 
     def _axis(self):
@@ -227,13 +289,13 @@ class CompactFiniteDifferenceSolver:
 
     # -- multi-rank pieces (used by partition.ZPartitionedDerivative) -----------------------------------
     def interface_pack(self, df, faces):
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         check(lib().cfd_interface_pack(plan.handle, df.data_ptr(), faces.data_ptr(), _stream_ptr(df)))
         return faces
 
     def edge_faces(self, f, faces, halo_lo=None, halo_hi=None):
         """Interface planes straight from f (no block solve): cfd_edge_faces."""
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         check(lib().cfd_edge_faces(plan.handle, f.data_ptr(),
                                    halo_lo.data_ptr() if halo_lo is not None else None,
                                    halo_hi.data_ptr() if halo_hi is not None else None,
@@ -242,7 +304,7 @@ class CompactFiniteDifferenceSolver:
 
     def reduced_unknowns(self, faces, ab, neighbours_only=False, flag0=None, flag1=None, seq=0):
         """alpha / beta planes of this rank from the gathered interface planes: cfd_reduced_unknowns."""
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         check(lib().cfd_reduced_unknowns(plan.handle, faces.data_ptr(), 1 if neighbours_only else 0, ab.data_ptr(),
                                          flag0, flag1, int(seq), _stream_ptr(faces)))
         return ab
@@ -250,7 +312,7 @@ class CompactFiniteDifferenceSolver:
     def apply_coupled(self, f, out, halo_lo, halo_hi, ab):
         """Final derivative of the block in one pass, interface unknowns folded in: cfd_apply_coupled."""
         import torch
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         if out is None:
             out = torch.empty_like(f)
         check(lib().cfd_apply_coupled(plan.handle, f.data_ptr(), out.data_ptr(),
@@ -261,12 +323,12 @@ class CompactFiniteDifferenceSolver:
 
     def nb_layout(self):
         """(virtual ranks V, own index) of the neighbour-only interface buffer [2V, plane]: cfd_nb_layout."""
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         pv, own = ctypes.c_int(), ctypes.c_int()
         check(lib().cfd_nb_layout(plan.handle, ctypes.byref(pv), ctypes.byref(own)))
         return pv.value, own.value
 
     def reduced_correct(self, df, faces_all):
-        plan = self._plan(self.direction, self.spacing)
+        plan = self._plan(self.direction, self._h(None, self.direction))
         check(lib().cfd_reduced_correct(plan.handle, df.data_ptr(), faces_all.data_ptr(), _stream_ptr(df)))
         return df

@@ -174,12 +174,19 @@ static int device_info(DeviceInfo &d)
     return CFD_OK;
 }
 
-// Work counters: a ring of {next bundle, finished warps} pairs, one pair per in-flight launch.
-// Each kernel leaves its pair zeroed, so re-use after COUNTER_RING launches needs no memset.
+// Work counters: {next bundle, finished warps} pairs, one per in-flight launch; each kernel leaves its pair zeroed.
+//  * Eager launches draw from a ring of COUNTER_RING pairs per device (allocated by the first plan created on the
+//    device): a pair is re-used 4096 launches later, long after its kernel has finished.
+//  * A launch that is being CAPTURED into a CUDA graph bakes its pair into the graph and may replay at any later time,
+//    concurrently with eager launches or other graphs.  It therefore gets a pair of its own from the owner's PairPool
+//    -- never handed out again while the owner (plan) lives -- plus a memset node in front of the kernel node, so the
+//    pair needs no history.  Pool chunks are allocated on demand under relaxed capture mode
+//    (cudaThreadExchangeStreamCaptureMode), the documented way for a library to call cudaMalloc during a capture.
 constexpr int COUNTER_RING = 4096;
 constexpr int MAX_DEVICES = 64;
 static unsigned long long *g_counters[MAX_DEVICES] = {nullptr};     // one ring per device of this process
 static std::atomic<unsigned long> g_launch_seq{0};
+static std::mutex g_counter_mu;
 
 static int current_device(int &dev)
 {
@@ -188,26 +195,113 @@ static int current_device(int &dev)
     return CFD_OK;
 }
 
-static int counter_pair(unsigned long long **out)
+struct PairPool {
+    static constexpr int CHUNK = 256;                 // pairs per chunk (4 KiB)
+    std::mutex mu;
+    std::vector<unsigned long long *> chunks;
+    int used = CHUNK;                                 // pairs taken from the last chunk
+    int fresh(unsigned long long **out)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (used == CHUNK) {
+            unsigned long long *p = nullptr;
+            cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+            cudaThreadExchangeStreamCaptureMode(&mode);
+            const cudaError_t e = cudaMalloc(&p, sizeof(unsigned long long) * 2 * CHUNK);
+            cudaThreadExchangeStreamCaptureMode(&mode);
+            if (e != cudaSuccess) return fail(CFD_ECUDA, "cudaMalloc of work counters: %s", cudaGetErrorString(e));
+            chunks.push_back(p);
+            used = 0;
+        }
+        *out = chunks.back() + 2 * used++;
+        return CFD_OK;
+    }
+    ~PairPool() { for (auto *p : chunks) cudaFree(p); }
+};
+static PairPool g_planless_pool;                      // captured launches of entry points that take no plan
+
+// Called by every plan constructor (never during a capture): the eager ring of the current device.
+static int ensure_counters()
 {
     int dev = 0;
     int rc = current_device(dev);
     if (rc) return rc;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
+    std::lock_guard<std::mutex> lock(g_counter_mu);
     if (!g_counters[dev]) {
         unsigned long long *p = nullptr;
         CUDA_TRY(cudaMalloc(&p, sizeof(unsigned long long) * 2 * COUNTER_RING));
         CUDA_TRY(cudaMemset(p, 0, sizeof(unsigned long long) * 2 * COUNTER_RING));
         g_counters[dev] = p;
     }
+    return CFD_OK;
+}
+
+static int counter_pair(unsigned long long **out, cudaStream_t stream, PairPool *pool = nullptr)
+{
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs == cudaStreamCaptureStatusActive) {
+        int rc = (pool ? pool : &g_planless_pool)->fresh(out);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(*out, 0, 2 * sizeof(unsigned long long), stream));     // a node of the graph
+        return CFD_OK;
+    }
+    int dev = 0;
+    int rc = current_device(dev);
+    if (rc) return rc;
+    if (!g_counters[dev]) { rc = ensure_counters(); if (rc) return rc; }
     *out = g_counters[dev] + 2 * (g_launch_seq++ % COUNTER_RING);
+    return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU flag waits: time-out and the host-mapped error word (kernels.cuh wait_flag)
+// ------------------------------------------------------------------------------------------------
+static std::atomic<long long> g_wait_timeout_ns{120LL * 1000000000LL};
+static int *g_err_host = nullptr, *g_err_dev = nullptr;
+static std::mutex g_err_mu;
+
+static int ensure_err_word()        // plan constructors of partitioned plans call this (never during a capture)
+{
+    std::lock_guard<std::mutex> lock(g_err_mu);
+    if (g_err_host) return CFD_OK;
+    int *h = nullptr, *d = nullptr;
+    CUDA_TRY(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+    *h = 0;
+    CUDA_TRY(cudaHostGetDevicePointer(&d, h, 0));
+    g_err_host = h;
+    g_err_dev = d;
+    return CFD_OK;
+}
+
+static WaitP wait_params()
+{
+    WaitP w;
+    w.timeout_ns = (unsigned long long)g_wait_timeout_ns.load();
+    w.err = g_err_dev;
+    return w;
+}
+
+extern "C" int cfd_set_wait_timeout_ms(long ms)
+{
+    if (ms < 1) return fail(CFD_EINVAL, "time-out must be >= 1 ms");
+    g_wait_timeout_ns = (long long)ms * 1000000LL;
+    return CFD_OK;
+}
+
+extern "C" int cfd_async_status(void)
+{
+    if (g_err_host && *(volatile int *)g_err_host != 0) {
+        *(volatile int *)g_err_host = 0;
+        return fail(CFD_ETIMEOUT, "a kernel gave up waiting for a neighbour's arrival flag (time-out %lld ms): results "
+                                  "of that call are invalid", g_wait_timeout_ns.load() / 1000000LL);
+    }
     return CFD_OK;
 }
 
 template <bool CONTIG, bool DERIV, int NSLOT>
 static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                            cudaStream_t stream, bool in_place)
+                            cudaStream_t stream, bool in_place, PairPool *pool)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
@@ -258,11 +352,12 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    int rc = counter_pair(&kp.counter);
+    int rc = counter_pair(&kp.counter, stream, pool);
     if (rc) return rc;
     long blocks = (nitems + warps - 1) / warps;
     const long cap = (long)dinfo.sms * ctas;
     if (blocks > cap) blocks = cap;
+    if (const char *e = getenv("CFD_CTAS")) { if (atol(e) >= 1 && atol(e) < blocks) blocks = atol(e); }    // experiment
     kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, kp);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -271,12 +366,12 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
 
 template <bool CONTIG, bool DERIV>
 static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                         cudaStream_t stream, bool in_place = false)
+                         cudaStream_t stream, PairPool *pool, bool in_place = false)
 {
     switch (g_slots ? g_slots : 3) {
-        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream, in_place);
-        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream, in_place);
-        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream, in_place);
+        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream, in_place, pool);
+        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream, in_place, pool);
+        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream, in_place, pool);
         default: return fail(CFD_EINVAL, "ring slots must be 3, 4 or 5");
     }
 }
@@ -295,6 +390,7 @@ struct cfd_plan {
     int rank, size;
     KParams kp;                       // host template (halo/out pointers filled per call)
     MapCache cache;
+    PairPool pool;                    // work counters of this plan's CAPTURED launches (see counter_pair)
     // multi-rank
     std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
     std::vector<double> lu_nb;        // neighbour-only reduced system (ranks r-1, r, r+1)
@@ -303,12 +399,14 @@ struct cfd_plan {
     int wc = 0;
     // host staging
     double *d_f = nullptr, *d_df = nullptr;
-    cudaStream_t hstream = nullptr;
+    cudaStream_t hstream = nullptr, hcopy = nullptr, hback = nullptr;
+    cudaEvent_t hev[8] = {nullptr};
     // cfd_apply_xy: draw order of the (plane, bundle) items (axis-0 plans only)
     std::mutex xy_mu;
     int *d_xy_order = nullptr;
     long xy_entries = 0;              // entries of the table (> items when lines are cut into segments)
     int xy_kseg = 0, xy_sub = -1;
+    long xy_nedge = 0;                // edge entries in front of the table (drawn by cfd_zpart_apply_xyz only)
     double xy_active = -1.0;
     int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
     double w_lo = 0.0, w_hi = 0.0;    // d(lo face)/d f[-1], d(hi face)/d f[n]: cfd_reduced_unknowns_deferred
@@ -318,6 +416,7 @@ struct nt_plan {
     Geometry g;
     KParams kp;
     MapCache cache;
+    PairPool pool;
     bool exact = false;               // two-pass exact solver (matrix refused by the one-pass kernel)
     double *d_tab = nullptr;          // [4][K*32]: forward pc, qc; backward pc, qc
     // Starved shape (long lines, fewer bundles than warps): the lines are cut into segments, which is only safe
@@ -471,10 +570,10 @@ static int halo_weights(const Geometry &g, double h, double &w_lo, double &w_hi)
     KParams ki;
     int rc = fill_tables(ki, g, pade_block(1, 3), 3.0 / (4.0 * h), true);
     if (rc) return rc == CFD_ESLOWPATH ? CFD_EUNSUPPORTED : rc;
-    double e[CH], ep = 0.0;
-    for (int j = 0; j < CH; j++) { ep = -ki.head.l[j] * ep + (j == 0 ? -ki.head.sk[0] : 0.0); e[j] = ep; }
+    double e[CH], ep = 0.0;                 // the same 31 rows as edge_faces_kernel
+    for (int j = 0; j < CH - 1; j++) { ep = -ki.head.l[j] * ep + (j == 0 ? -ki.head.sk[0] : 0.0); e[j] = ep; }
     double x = 0.0;
-    for (int j = CH - 1; j >= 0; j--) x = e[j] - ki.head.g[j] * x;
+    for (int j = CH - 2; j >= 0; j--) x = e[j] - ki.head.g[j] * x;
     w_lo = -x;
     w_hi = -ki.tail.sk[g.jl];
     return CFD_OK;
@@ -502,7 +601,7 @@ extern "C" int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_h
 // segments of `sub` chunks (one warm-up chunk in front, the look-ahead chunk behind, both served by L2); every square
 // is then a wavefront of its own, as short as a small plane's.  Entries are (item << 3) | segment, segment 0 = whole
 // line.  Returns the effective segment length in `kseg` (0 = nothing was cut).
-static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int sub, int &kseg)
+static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int sub, int &kseg, long nedge = 0)
 {
     const int ipp = nxp + nyp;
     kseg = 0;
@@ -515,7 +614,9 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int su
     const int ngy = (kseg && nxp > kseg) ? (nxp + kseg - 1) / kseg : 1;     // segments of a y line (nxp tiles long)
     const int sy = ngy > 1 ? kseg : nxp, sx = ngx > 1 ? kseg : nyp;         // x bundles / y bundles per square
     std::vector<int> order;
-    order.reserve((size_t)nz * (nxp * ngx + nyp * ngy));
+    order.reserve((size_t)nz * (nxp * ngx + nyp * ngy) + (size_t)nedge);
+    // edge items of a z-partitioned d/dz (ids from nz * ipp on) go FIRST: their faces have the whole launch to travel
+    for (long t = 0; t < nedge; t++) order.push_back((int)(((long)nz * ipp + t) << 3));
     if (active <= 0.0) {                       // plain plane-by-plane order (whole lines)
         kseg = 0;
         for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)(w << 3));
@@ -580,12 +681,15 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
 // cfd_apply_xy neither allocates nor synchronises; it only runs again if the launch knobs were changed afterwards.
 static int xy_prepare(cfd_plan *px, double active, int sub)
 {
+    // The table always starts with the edge entries of the plane (one per 32 columns): a plain cfd_apply_xy launch
+    // skips them (order + xy_nedge), the fused zpart launch draws them first -- so neither ever rebuilds the table.
+    const long nedge = ((long)px->g.ny * px->g.nx + CH - 1) / CH;
     std::lock_guard<std::mutex> lock(px->xy_mu);
     if (px->d_xy_order && px->xy_active == active && px->xy_sub == sub) return CFD_OK;
     const int nxp = px->g.ny / CH, nyp = (px->g.nx + CH - 1) / CH;
     int kseg = 0;
-    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active, sub, kseg);
-    if ((long)order.size() < (long)px->g.nz * (nxp + nyp)) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
+    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active, sub, kseg, nedge);
+    if ((long)order.size() < (long)px->g.nz * (nxp + nyp) + nedge) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
     if (px->d_xy_order && (long)order.size() > px->xy_entries) { cudaFree(px->d_xy_order); px->d_xy_order = nullptr; }
     if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -593,12 +697,14 @@ static int xy_prepare(cfd_plan *px, double active, int sub)
     px->xy_kseg = kseg;
     px->xy_active = active;
     px->xy_sub = sub;
+    px->xy_nedge = nedge;
     return CFD_OK;
 }
 
 static bool xy_eligible(const Geometry &g)
-{
-    return g.axis == 0 && g.ny % CH == 0 && (long)g.nz * (g.ny / CH + (g.nx + CH - 1) / CH) <= 0x0fffffffL;  // id << 3 fits an int
+{   // id << 3 must fit an int (edge items of a fused zpart launch included: one per 32 columns of the plane)
+    return g.axis == 0 && g.ny % CH == 0 &&
+           (long)g.nz * (g.ny / CH + (g.nx + CH - 1) / CH) + ((long)g.ny * g.nx + CH - 1) / CH <= 0x0fffffffL;
 }
 
 extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size)
@@ -615,6 +721,8 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
     }
     cfd_plan *p = new cfd_plan();
     int rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (!rc) rc = ensure_counters();
+    if (!rc && part_size > 1) rc = ensure_err_word();
     if (rc) { delete p; return rc; }
     p->h = h; p->rank = part_rank; p->size = part_size;
     const LineCoeffs m = pade_block(part_rank, part_size);
@@ -650,10 +758,14 @@ extern "C" int cfd_create(cfd_plan **out, int nz, int ny, int nx, int axis, doub
             cfd_destroy(p);
             return fail(CFD_ECUDA, "cudaMalloc of plan tables failed");
         }
-        cudaMemcpy(p->d_x_uh, p->x_uh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(p->d_x_lh, p->x_lh.data(), n * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(p->d_lu, p->lu.data(), p->lu.size() * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(p->d_lu_nb, p->lu_nb.data(), p->lu_nb.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (cudaMemcpy(p->d_x_uh, p->x_uh.data(), n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(p->d_x_lh, p->x_lh.data(), n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(p->d_lu, p->lu.data(), p->lu.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(p->d_lu_nb, p->lu_nb.data(), p->lu_nb.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            cfd_destroy(p);
+            return fail(CFD_ECUDA, "upload of plan tables failed: %s", cudaGetErrorString(e));
+        }
     }
     if (part_size == 1 && xy_eligible(p->g)) {        // draw order of cfd_apply_xy, default launch shape
         DeviceInfo di;
@@ -673,6 +785,9 @@ extern "C" void cfd_destroy(cfd_plan *p)
     cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu); cudaFree(p->d_lu_nb);
     cudaFree(p->d_f); cudaFree(p->d_df); cudaFree(p->d_xy_order);
     if (p->hstream) cudaStreamDestroy(p->hstream);
+    if (p->hcopy) cudaStreamDestroy(p->hcopy);
+    if (p->hback) cudaStreamDestroy(p->hback);
+    for (auto e : p->hev) if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -757,8 +872,8 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     KParams kp = p->kp;
     kp.halo_lo = halo_lo; kp.halo_hi = halo_hi;
     kp.ab = ab; kp.nlines = p->g.nlines;
-    if (p->g.contig) return launch_stream<true, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream);
-    return launch_stream<false, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream);
+    if (p->g.contig) return launch_stream<true, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
+    return launch_stream<false, true>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
 }
 
 extern "C" int cfd_apply(cfd_plan *p, const double *f, double *df, const double *halo_lo, const double *halo_hi,
@@ -786,7 +901,7 @@ extern "C" int cfd_reduced_unknowns(cfd_plan *p, const double *faces, int neighb
     const int bs = 256;
     reduced_planes_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
         faces, neighbours_only ? p->d_lu_nb : p->d_lu, p->g.nlines, neighbours_only ? p->nb_pv : p->size,
-        neighbours_only ? p->nb_own : p->rank, ab, flag0, flag1, seq);
+        neighbours_only ? p->nb_own : p->rank, ab, flag0, flag1, seq, wait_params());
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
@@ -806,7 +921,8 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
                      double *push_hi = nullptr);
 
 template <int NSLOT>
-static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPair &my, long nitems, cudaStream_t stream)
+static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPair &my, long nitems, cudaStream_t stream,
+                     const EdgeX *edge = nullptr, const CUtensorMap *tmz = nullptr)
 {
     static DeviceInfo dinfo;
     int rc;
@@ -825,8 +941,10 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     xy_shape(px->g, dinfo.sms, NSLOT, px->xy_warps, warps, active, sub);
     rc = xy_prepare(px, active, sub);   // no-op unless the launch knobs changed since cfd_create
     if (rc) return rc;
-    q.order = px->d_xy_order;
-    q.nitems = px->xy_entries;
+    if (edge && edge->nedge != px->xy_nedge) return fail(CFD_EINVAL, "internal: edge item count does not match the plane");
+    q.order = px->d_xy_order + (edge ? 0 : px->xy_nedge);
+    q.nitems = px->xy_entries - (edge ? 0 : px->xy_nedge);
+    q.nxy = nitems;
     q.kseg = px->xy_kseg;
     q.slot_items = (float)(2.0 * active);
     // Start-up stagger: pays on long lines only (>= 32 tiles: [128,1024,1024] 0.596 -> 0.577 ms with 1 us per slot;
@@ -835,16 +953,21 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     if (const char *e = getenv("CFD_XY_TAU")) q.tau_ns = (float)atof(e);
     const size_t smem = (size_t)warps * per_warp + 1024;
     const bool seg = q.kseg > 0;          // whole lines only: the variant without segment state
-    auto kern = seg ? stream_kernel_xy<NSLOT, true> : stream_kernel_xy<NSLOT, false>;
-    static size_t configured[2][MAX_DEVICES] = {{0}, {0}};
+    auto kern = seg ? stream_kernel_xy<NSLOT, true, false> : stream_kernel_xy<NSLOT, false, false>;
+    if (edge) {
+        if constexpr (NSLOT == 4) kern = seg ? stream_kernel_xy<4, true, true> : stream_kernel_xy<4, false, true>;
+        else return fail(CFD_EUNSUPPORTED, "the fused x/y + edge launch is built for 4 ring slots");
+    }
+    static size_t configured[4][MAX_DEVICES] = {{0}, {0}, {0}, {0}};
+    const int variant = (seg ? 1 : 0) + (edge ? 2 : 0);
     int dev = 0;
     rc = current_device(dev);
     if (rc) return rc;
-    if (configured[seg][dev] < smem) {
+    if (configured[variant][dev] < smem) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[seg][dev] = smem;
+        configured[variant][dev] = smem;
     }
-    rc = counter_pair(&q.counter);
+    rc = counter_pair(&q.counter, stream, &px->pool);
     if (rc) return rc;
     KParams kx = px->kp, ky = py->kp;
     kx.ab = nullptr; ky.ab = nullptr;
@@ -858,7 +981,9 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
             if (b2 >= 1 && b2 < blocks) blocks = b2;
         } else if (atol(e) >= 1 && atol(e) <= blocks) blocks = atol(e);
     }
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q);
+    static const EdgeX no_edge = {};
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q,
+                                                         tmz ? *tmz : mx.tm_in, edge ? *edge : no_edge);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
@@ -876,6 +1001,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     q.nxp = p->g.contig ? (int)p->g.nb : 0;
     q.nyp = p->g.contig ? 0 : p->g.inner_tiles;
     q.nitems = p->g.nb;
+    q.nxy = p->g.nb;
     q.order = nullptr;
     q.kseg = 0;
     q.tau_ns = 0.f; q.slot_items = 0.f;
@@ -884,15 +1010,16 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     const long per_sm = (q.nitems + dinfo.sms - 1) / dinfo.sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     const size_t smem = (size_t)warps * per_warp + 1024;
-    auto kern = stream_kernel_xy<NSLOT, false>;
+    auto kern = stream_kernel_xy<NSLOT, false, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * per_warp + 1024));
-    rc = counter_pair(&q.counter);
+    rc = counter_pair(&q.counter, stream, &p->pool);
     if (rc) return rc;
     KParams k = p->kp;
     k.ab = nullptr;
     long blocks = (q.nitems + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mp.tm_in, mp.tm_out, mp.tm_in, mp.tm_out, k, k, q);
+    static const EdgeX no_edge = {};
+    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mp.tm_in, mp.tm_out, mp.tm_in, mp.tm_out, k, k, q, mp.tm_in, no_edge);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
@@ -965,7 +1092,7 @@ extern "C" int cfd_push_planes(const double *src0, double *dst0, const double *s
     if (n < 2 || (n & 1)) return fail(CFD_EINVAL, "plane size %ld must be even", n);
     if ((dst0 && !src0) || (dst1 && !src1)) return fail(CFD_EINVAL, "destination without source");
     unsigned long long *done = nullptr;
-    int rc = counter_pair(&done);
+    int rc = counter_pair(&done, (cudaStream_t)stream);
     if (rc) return rc;
     const int bs = 256;
     long blocks = (n / 2 + bs - 1) / bs;
@@ -981,7 +1108,7 @@ extern "C" int cfd_wait_flags(const unsigned long long *flag0, const unsigned lo
                               unsigned long long seq, void *stream)
 {
     if (!flag0 && !flag1) return CFD_OK;
-    wait_flags_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag0, flag1, seq);
+    wait_flags_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag0, flag1, seq, wait_params());
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
@@ -1009,7 +1136,7 @@ extern "C" int cfd_reduced_unknowns_deferred(cfd_plan *p, const double *faces_nb
     const int bs = 256;
     reduced_planes_deferred_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
         faces_nb, p->d_lu_nb, p->g.nlines, p->nb_pv, p->nb_own, ab, halo_lo, halo_hi, f, p->g.inner, p->g.n,
-        p->w_lo, p->w_hi, flag0, flag1, seq);
+        p->w_lo, p->w_hi, flag0, flag1, seq, wait_params());
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return CFD_OK;
@@ -1039,7 +1166,7 @@ static int edge_impl(cfd_plan *p, const double *f, const double *halo_lo, const 
     ep.push_hi = p->kp.hi_closure ? nullptr : push_hi;
     if (p2p) {
         ep.peer_lo = peer_lo; ep.peer_hi = peer_hi; ep.flag_lo = flag_lo; ep.flag_hi = flag_hi; ep.seq = seq;
-        int rc = counter_pair(&ep.done);
+        int rc = counter_pair(&ep.done, (cudaStream_t)stream, &p->pool);
         if (rc) return rc;
     }
     int bs = 128;
@@ -1121,22 +1248,69 @@ extern "C" int cfd_reduced_correct(cfd_plan *p, double *df, const double *faces_
     return CFD_OK;
 }
 
+static bool is_page_locked(const void *ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int cfd_apply_host(cfd_plan *p, const double *f_host, double *df_host, int pinned)
 {
-    (void)pinned;
     if (!p || !f_host || !df_host) return fail(CFD_EINVAL, "NULL argument");
     if (p->size != 1) return fail(CFD_EINVAL, "cfd_apply_host serves part_size == 1 only");
+    // pinned != 0 is a promise the asynchronous copies rely on (they would silently fall back to the driver's staged
+    // path otherwise): hold the caller to it
+    if (pinned && !(is_page_locked(f_host) && is_page_locked(df_host)))
+        return fail(CFD_EINVAL, "pinned = %d but the host buffers are not page-locked (cudaHostAlloc / cudaHostRegister)", pinned);
     const size_t bytes = (size_t)p->g.nlines * p->g.n * sizeof(double);
     if (!p->d_f) {
         CUDA_TRY(cudaMalloc(&p->d_f, bytes));
         CUDA_TRY(cudaMalloc(&p->d_df, bytes));
         CUDA_TRY(cudaStreamCreateWithFlags(&p->hstream, cudaStreamNonBlocking));
     }
-    CUDA_TRY(cudaMemcpyAsync(p->d_f, f_host, bytes, cudaMemcpyHostToDevice, p->hstream));
-    int rc = cfd_apply(p, p->d_f, p->d_df, nullptr, nullptr, p->hstream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(df_host, p->d_df, bytes, cudaMemcpyDeviceToHost, p->hstream));
-    CUDA_TRY(cudaStreamSynchronize(p->hstream));
+    // Lines along x or y never leave a z-slab: with page-locked buffers the field moves in slabs, so that slab s+1
+    // travels host -> device while slab s is differentiated and slab s-1 travels back (PCIe is full duplex).  Pageable
+    // buffers (and z lines, which need the whole field) take the plain copy - kernel - copy sequence.
+    const int slabs = (pinned && p->g.axis != 2 && p->g.nz >= 8) ? 4 : 1;
+    if (slabs == 1) {
+        CUDA_TRY(cudaMemcpyAsync(p->d_f, f_host, bytes, cudaMemcpyHostToDevice, p->hstream));
+        int rc = cfd_apply(p, p->d_f, p->d_df, nullptr, nullptr, p->hstream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(df_host, p->d_df, bytes, cudaMemcpyDeviceToHost, p->hstream));
+        CUDA_TRY(cudaStreamSynchronize(p->hstream));
+        return CFD_OK;
+    }
+    if (!p->hcopy) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->hcopy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->hback, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&p->hev[i], cudaEventDisableTiming));
+    }
+    const size_t plane = (size_t)p->g.ny * p->g.nx;
+    for (int s = 0; s < slabs; s++) {
+        const int z0 = (int)((long)p->g.nz * s / slabs), z1 = (int)((long)p->g.nz * (s + 1) / slabs);
+        const size_t off = z0 * plane, cnt = (size_t)(z1 - z0) * plane * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(p->d_f + off, f_host + off, cnt, cudaMemcpyHostToDevice, p->hcopy));
+        CUDA_TRY(cudaEventRecord(p->hev[s], p->hcopy));
+        CUDA_TRY(cudaStreamWaitEvent(p->hstream, p->hev[s], 0));
+        // a slab of a field is a field of fewer planes: same line tables, its own geometry
+        Geometry gs;
+        int rc = make_geometry(gs, z1 - z0, p->g.ny, p->g.nx, p->g.axis);
+        if (rc) return rc;
+        CUtensorMap tin, tout;
+        rc = encode_maps(gs, p->d_f + off, p->d_df + off, &tin, &tout);
+        if (rc) return rc;
+        KParams kp = p->kp;
+        kp.nb = gs.nb; kp.rows = gs.nlines; kp.outer = (int)gs.outer;
+        kp.halo_lo = kp.halo_hi = kp.ab = nullptr; kp.nlines = gs.nlines;
+        rc = gs.contig ? launch_stream<true, true>(gs, kp, tin, tout, p->hstream, &p->pool)
+                       : launch_stream<false, true>(gs, kp, tin, tout, p->hstream, &p->pool);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(p->hev[4 + s], p->hstream));
+        CUDA_TRY(cudaStreamWaitEvent(p->hback, p->hev[4 + s], 0));
+        CUDA_TRY(cudaMemcpyAsync(df_host + off, p->d_df + off, cnt, cudaMemcpyDeviceToHost, p->hback));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->hback));
     return CFD_OK;
 }
 
@@ -1145,7 +1319,7 @@ extern "C" int cfd_apply_host(cfd_plan *p, const double *f_host, double *df_host
 // ------------------------------------------------------------------------------------------------
 template <bool CONTIG, bool REVERSE>
 static int launch_recurrence(const Geometry &g, const double *pc, const double *qc, const CUtensorMap &tm_in,
-                             const CUtensorMap &tm_out, cudaStream_t stream)
+                             const CUtensorMap &tm_out, cudaStream_t stream, PairPool *pool)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
@@ -1164,7 +1338,7 @@ static int launch_recurrence(const Geometry &g, const double *pc, const double *
     }
     RParams rp;
     rp.K = g.K; rp.inner_tiles = g.inner_tiles; rp.nb = g.nb; rp.pc = pc; rp.qc = qc;
-    int rc = counter_pair(&rp.counter);
+    int rc = counter_pair(&rp.counter, stream, pool);
     if (rc) return rc;
     long blocks = (g.nb + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
@@ -1187,6 +1361,7 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
     }
     nt_plan *p = new nt_plan();
     int rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (!rc) rc = ensure_counters();
     if (rc) { delete p; return rc; }
     const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
     rc = fill_tables(p->kp, p->g, m, 1.0, true);
@@ -1204,7 +1379,11 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
             delete p;
             return fail(CFD_ECUDA, "cudaMalloc of solver tables failed");
         }
-        cudaMemcpy(p->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (cudaMemcpy(p->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            nt_destroy(p);
+            return fail(CFD_ECUDA, "upload of solver tables failed: %s", cudaGetErrorString(e));
+        }
         p->exact = true;
         g_err.clear();
         rc = CFD_OK;
@@ -1233,13 +1412,13 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
         const double *t = p->d_tab;
         cudaStream_t st = (cudaStream_t)stream;
         if (p->g.contig) {
-            rc = launch_recurrence<true, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st);
+            rc = launch_recurrence<true, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st, &p->pool);
             if (rc) return rc;
-            return launch_recurrence<true, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st);
+            return launch_recurrence<true, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st, &p->pool);
         }
-        rc = launch_recurrence<false, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st);
+        rc = launch_recurrence<false, false>(p->g, t, t + L, mp.tm_in, mp.tm_out, st, &p->pool);
         if (rc) return rc;
-        return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st);
+        return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st, &p->pool);
     }
     KParams kp = p->kp;
     if (p->d_scratch) {
@@ -1247,16 +1426,16 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
         rc = get_maps(p->scratch_cache, p->g, d, p->d_scratch, ms);
         if (rc) return rc;
         rc = p->g.contig ? launch_stream<true, false>(p->g, kp, ms.tm_in, ms.tm_out,
-                                                      (cudaStream_t)stream, false)
+                                                      (cudaStream_t)stream, &p->pool, false)
                          : launch_stream<false, false>(p->g, kp, ms.tm_in, ms.tm_out,
-                                                       (cudaStream_t)stream, false);
+                                                       (cudaStream_t)stream, &p->pool, false);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d, p->d_scratch, (size_t)p->g.nlines * p->g.n * sizeof(double),
                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         return CFD_OK;
     }
-    if (p->g.contig) return launch_stream<true, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, true);
-    return launch_stream<false, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, true);
+    if (p->g.contig) return launch_stream<true, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool, true);
+    return launch_stream<false, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool, true);
 }
 
 extern "C" void nt_destroy(nt_plan *p)
@@ -1270,26 +1449,331 @@ extern "C" void nt_destroy(nt_plan *p)
 // ------------------------------------------------------------------------------------------------
 // pThomas
 // ------------------------------------------------------------------------------------------------
-extern "C" int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream)
+struct pt_plan { int n = 0; double *d_lu = nullptr; };
+
+extern "C" int cfd_pthomas_create(pt_plan **out, const double *a, const double *b, const double *c, int n)
 {
-    if (!a || !b || !c || !d) return fail(CFD_EINVAL, "NULL argument");
-    if (n < 1 || n > 256 || nsys < 1) return fail(CFD_EINVAL, "n = %d (1..256), nsys = %ld", n, nsys);
+    if (!out || !a || !b || !c) return fail(CFD_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (n < 1 || n > 256) return fail(CFD_EINVAL, "n = %d (1..256)", n);
     std::vector<double> lu(3 * n);
     double piv = b[0];
+    if (piv == 0.0 || !std::isfinite(piv)) return fail(CFD_EINVAL, "zero pivot at row 0");
     lu[0] = 0.0; lu[n] = 1.0 / piv; lu[2 * n] = c[0] / piv;
     for (int i = 1; i < n; i++) {
         piv = b[i] - a[i] * lu[2 * n + i - 1];
         if (piv == 0.0 || !std::isfinite(piv)) return fail(CFD_EINVAL, "zero pivot at row %d", i);
         lu[i] = a[i]; lu[n + i] = 1.0 / piv; lu[2 * n + i] = c[i] / piv;
     }
-    double *d_lu = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_lu, lu.size() * sizeof(double), (cudaStream_t)stream));
-    // lu is pageable host memory: the runtime stages it before cudaMemcpyAsync returns, so it may die with this frame
-    CUDA_TRY(cudaMemcpyAsync(d_lu, lu.data(), lu.size() * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    pt_plan *p = new pt_plan();
+    p->n = n;
+    if (cudaMalloc(&p->d_lu, lu.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(p->d_lu, lu.data(), lu.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        cudaFree(p->d_lu);
+        delete p;
+        return fail(CFD_ECUDA, "pThomas tables: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return CFD_OK;
+}
+
+extern "C" int cfd_pthomas_solve(pt_plan *p, double *d, long nsys, void *stream)
+{
+    if (!p || !d) return fail(CFD_EINVAL, "NULL argument");
+    if (nsys < 1) return fail(CFD_EINVAL, "nsys = %ld", nsys);
     const int bs = 128;
-    pthomas_kernel<<<(unsigned)((nsys + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(d, d_lu, n, nsys);
+    pthomas_kernel<<<(unsigned)((nsys + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(d, p->d_lu, p->n, nsys);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaFreeAsync(d_lu, (cudaStream_t)stream));
+    return CFD_OK;
+}
+
+extern "C" void cfd_pthomas_destroy(pt_plan *p)
+{
+    if (!p) return;
+    cudaFree(p->d_lu);
+    delete p;
+}
+
+// One-shot convenience form (create + solve + destroy): allocates, and synchronises the stream before it frees.
+extern "C" int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream)
+{
+    pt_plan *p = nullptr;
+    int rc = cfd_pthomas_create(&p, a, b, c, n);
+    if (rc) return rc;
+    rc = cfd_pthomas_solve(p, d, nsys, stream);
+    if (!rc && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+        rc = fail(CFD_ECUDA, "cfd_pthomas: %s", cudaGetErrorString(cudaGetLastError()));
+    cfd_pthomas_destroy(p);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Partitioned line over NVLink peer memory, host side in C (SURVEY 8b cfd_mg_*): one cfd_zpart per rank owns the
+// rank's receive buffer, maps the neighbours' (cudaIpc handles between processes, plain pointers inside one), and
+// issues the launches of the fused multi-rank derivative.  Buffer layout, in doubles (plane = lines of the block):
+//     halo  [2 parities][2][plane]   slot 0: last plane of rank-1, slot 1: first plane of rank+1
+//     faces [2 parities][6][plane]   the neighbour-only interface planes (cfd_reduced_unknowns layout)
+//     flags [16] (uint64)            2 / 3: the left / right neighbour's faces + halo of call `seq` have landed
+// The parity is seq & 1 and flags only grow, so nothing is ever reset and no global barrier exists: a neighbour can
+// be at most one call ahead (its call s+1 needs our producer launch of call s+1, which is stream-ordered after our
+// consumer of call s), and then it writes the other parity.
+// ------------------------------------------------------------------------------------------------
+struct cfd_zpart {
+    cfd_plan *plan = nullptr;
+    long plane = 0;
+    double *buf = nullptr;
+    double *peer[2] = {nullptr, nullptr};
+    bool opened[2] = {false, false};
+    double *ab = nullptr;
+    unsigned long long seq = 0;
+    cudaEvent_t ev_begin = nullptr, ev_apply = nullptr;
+    bool applied = false, pending = false;
+    const double *pending_f = nullptr;
+    cudaStream_t pending_stream = nullptr;
+    double *halo(double *base, int par, int slot) const { return base + (long)(par * 2 + slot) * plane; }
+    double *faces(double *base, int par, int i) const { return base + 4 * plane + (long)(par * 6 + i) * plane; }
+    unsigned long long *flag(double *base, int k) const { return reinterpret_cast<unsigned long long *>(base + 16 * plane) + k; }
+};
+
+extern "C" int cfd_zpart_create(cfd_zpart **out, cfd_plan *plan)
+{
+    if (!out || !plan) return fail(CFD_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (plan->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: nothing to exchange");
+    if (plan->g.axis != 2) return fail(CFD_EUNSUPPORTED, "cfd_zpart serves lines along z (contiguous boundary planes)");
+    if (plan->g.n < 2 * CH + 2)
+        return fail(CFD_EUNSUPPORTED, "cfd_zpart needs >= %d planes per slab (have %d)", 2 * CH + 2, plan->g.n);
+    if (plan->g.nlines % 2) return fail(CFD_EINVAL, "plane size must be even");
+    cfd_zpart *z = new cfd_zpart();
+    z->plan = plan;
+    z->plane = plan->g.nlines;
+    const size_t bytes = (size_t)(16 * z->plane + 16) * sizeof(double);
+    if (cudaMalloc(&z->buf, bytes) != cudaSuccess || cudaMemset(z->buf, 0, bytes) != cudaSuccess ||
+        cudaMalloc(&z->ab, (size_t)2 * z->plane * sizeof(double)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&z->ev_begin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&z->ev_apply, cudaEventDisableTiming) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        cfd_zpart_destroy(z);
+        return fail(CFD_ECUDA, "cfd_zpart_create: %s", cudaGetErrorString(e));
+    }
+    *out = z;
+    return CFD_OK;
+}
+
+extern "C" int cfd_zpart_export(cfd_zpart *z, void *handle)
+{
+    if (!z || !handle) return fail(CFD_EINVAL, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CFD_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, z->buf));
+    memcpy(handle, &h, sizeof h);
+    return CFD_OK;
+}
+
+extern "C" void *cfd_zpart_buffer(cfd_zpart *z) { return z ? z->buf : nullptr; }
+
+static int zpart_check_sides(cfd_zpart *z, const void *lo, const void *hi)
+{
+    const bool has_lo = z->plan->rank > 0, has_hi = z->plan->rank < z->plan->size - 1;
+    if (has_lo != (lo != nullptr) || has_hi != (hi != nullptr))
+        return fail(CFD_EINVAL, "rank %d of %d: neighbour buffers must be given exactly where a neighbour exists",
+                    z->plan->rank, z->plan->size);
+    return CFD_OK;
+}
+
+static void zpart_disconnect(cfd_zpart *z)
+{
+    for (int i = 0; i < 2; i++) {
+        if (z->opened[i] && z->peer[i]) cudaIpcCloseMemHandle(z->peer[i]);
+        z->peer[i] = nullptr;
+        z->opened[i] = false;
+    }
+}
+
+extern "C" int cfd_zpart_connect(cfd_zpart *z, const void *handle_lo, const void *handle_hi)
+{
+    if (!z) return fail(CFD_EINVAL, "NULL argument");
+    int rc = zpart_check_sides(z, handle_lo, handle_hi);
+    if (rc) return rc;
+    zpart_disconnect(z);
+    const void *hs[2] = {handle_lo, handle_hi};
+    for (int i = 0; i < 2; i++) {
+        if (!hs[i]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs[i], sizeof h);
+        void *ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            zpart_disconnect(z);
+            return fail(CFD_ECUDA, "cudaIpcOpenMemHandle (%s neighbour): %s", i ? "right" : "left", cudaGetErrorString(e));
+        }
+        z->peer[i] = (double *)ptr;
+        z->opened[i] = true;
+    }
+    return CFD_OK;
+}
+
+extern "C" int cfd_zpart_connect_ptr(cfd_zpart *z, void *buffer_lo, void *buffer_hi)
+{
+    if (!z) return fail(CFD_EINVAL, "NULL argument");
+    int rc = zpart_check_sides(z, buffer_lo, buffer_hi);
+    if (rc) return rc;
+    zpart_disconnect(z);
+    z->peer[0] = (double *)buffer_lo;
+    z->peer[1] = (double *)buffer_hi;
+    return CFD_OK;
+}
+
+extern "C" void cfd_zpart_destroy(cfd_zpart *z)
+{
+    if (!z) return;
+    zpart_disconnect(z);
+    cudaFree(z->buf);
+    cudaFree(z->ab);
+    if (z->ev_begin) cudaEventDestroy(z->ev_begin);
+    if (z->ev_apply) cudaEventDestroy(z->ev_apply);
+    delete z;
+}
+
+// pointers of call `seq` on this rank
+struct ZPtrs {
+    double *faces_nb, *own_faces, *peer_face_lo, *peer_face_hi, *push_lo, *push_hi, *halo_lo, *halo_hi;
+    unsigned long long *flag_lo, *flag_hi, *wait_lo, *wait_hi;
+};
+
+static int zpart_ptrs(cfd_zpart *z, unsigned long long seq, ZPtrs &q)
+{
+    const cfd_plan *p = z->plan;
+    const bool has_lo = p->rank > 0, has_hi = p->rank < p->size - 1;
+    if ((has_lo && !z->peer[0]) || (has_hi && !z->peer[1]))
+        return fail(CFD_EINVAL, "cfd_zpart: neighbours are not connected (cfd_zpart_connect)");
+    const int par = (int)(seq & 1), own = p->nb_own;
+    const int own_left = (has_lo && p->rank - 1 > 0) ? 1 : 0;       // index of the left neighbour among ITS virtual ranks
+    q.faces_nb = z->faces(z->buf, par, 0);
+    q.own_faces = z->faces(z->buf, par, 2 * own);
+    q.peer_face_lo = has_lo ? z->faces(z->peer[0], par, 2 * own_left + 2) : nullptr;   // its "right neighbour's faces[0]"
+    q.peer_face_hi = has_hi ? z->faces(z->peer[1], par, 1) : nullptr;                  // its "left neighbour's faces[1]"
+    q.push_lo = has_lo ? z->halo(z->peer[0], par, 1) : nullptr;
+    q.push_hi = has_hi ? z->halo(z->peer[1], par, 0) : nullptr;
+    q.flag_lo = has_lo ? z->flag(z->peer[0], 3) : nullptr;
+    q.flag_hi = has_hi ? z->flag(z->peer[1], 2) : nullptr;
+    q.halo_lo = has_lo ? z->halo(z->buf, par, 0) : nullptr;
+    q.halo_hi = has_hi ? z->halo(z->buf, par, 1) : nullptr;
+    q.wait_lo = has_lo ? z->flag(z->buf, 2) : nullptr;
+    q.wait_hi = has_hi ? z->flag(z->buf, 3) : nullptr;
+    return CFD_OK;
+}
+
+extern "C" int cfd_zpart_begin(cfd_zpart *z, const double *f, void *stream)
+{
+    if (!z || !f) return fail(CFD_EINVAL, "NULL argument");
+    int rc = cfd_async_status();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the producer of call s+1 overwrites what the consumer of call s-1 read (same parity): order it after the last
+    // coupled launch even when the caller runs begin() on a side stream
+    if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+    ZPtrs q;
+    rc = zpart_ptrs(z, z->seq + 1, q);
+    if (rc) return rc;
+    const unsigned long long seq = ++z->seq;
+    rc = cfd_edge_faces_push(z->plan, f, q.own_faces, q.peer_face_lo, q.peer_face_hi, q.push_lo, q.push_hi, q.flag_lo,
+                             q.flag_hi, seq, stream);
+    if (rc) return rc;
+    rc = cfd_reduced_unknowns_deferred(z->plan, q.faces_nb, q.halo_lo, q.halo_hi, f, z->ab, q.wait_lo, q.wait_hi, seq, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(z->ev_begin, st));
+    z->pending = true;
+    z->pending_f = f;
+    z->pending_stream = st;
+    return CFD_OK;
+}
+
+extern "C" int cfd_zpart_apply(cfd_zpart *z, const double *f, double *df, void *stream)
+{
+    if (!z || !f || !df) return fail(CFD_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(z->pending && z->pending_f == f)) {
+        int rc = cfd_zpart_begin(z, f, stream);
+        if (rc) return rc;
+    }
+    if (z->pending_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_begin, 0));
+    z->pending = false;
+    ZPtrs q;
+    int rc = zpart_ptrs(z, z->seq, q);
+    if (rc) return rc;
+    rc = cfd_apply_coupled(z->plan, f, df, q.halo_lo, q.halo_hi, z->ab, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(z->ev_apply, st));
+    z->applied = true;
+    return CFD_OK;
+}
+
+// All three derivatives of a z-slab in three launches: the fused d/dx + d/dy kernel with the edge-face items of the
+// partitioned d/dz drawn first (faces and halo rows travel over NVLink while x / y are computed), the reduced
+// 2x2 / 6-unknown solve per line, the coupled d/dz kernel.
+extern "C" int cfd_zpart_apply_xyz(cfd_zpart *z, cfd_plan *px, cfd_plan *py, const double *f, double *dfdx, double *dfdy,
+                                   double *dfdz, void *stream)
+{
+    if (!z || !px || !py || !f || !dfdx || !dfdy || !dfdz) return fail(CFD_EINVAL, "NULL argument");
+    cfd_plan *pz = z->plan;
+    if (px->g.axis != 0 || py->g.axis != 1) return fail(CFD_EINVAL, "plans must be for axis 0 (x) and axis 1 (y)");
+    if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "x and y lines of a z-slab are unpartitioned plans");
+    for (const cfd_plan *p : {px, py})
+        if (p->g.nz != pz->g.nz || p->g.ny != pz->g.ny || p->g.nx != pz->g.nx) return fail(CFD_EINVAL, "plans are for different shapes");
+    if (f == dfdx || f == dfdy || f == dfdz || dfdx == dfdy || dfdx == dfdz || dfdy == dfdz)
+        return fail(CFD_EINVAL, "f and the three derivatives must be four different fields");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (!xy_eligible(px->g) || getenv("CFD_NO_XY") || getenv("CFD_NO_XY_EDGE") || (g_slots && g_slots != 4)) {
+        rc = cfd_zpart_begin(z, f, stream);            // separate edge launch, then the x / y launch(es)
+        if (!rc) rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+        if (!rc) rc = cfd_zpart_apply(z, f, dfdz, stream);
+        return rc;
+    }
+    rc = cfd_async_status();
+    if (rc) return rc;
+    if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+    ZPtrs q;
+    rc = zpart_ptrs(z, z->seq + 1, q);
+    if (rc) return rc;
+    MapPair mx, my, mz;
+    rc = get_maps(px->cache, px->g, f, dfdx, mx);
+    if (!rc) rc = get_maps(py->cache, py->g, f, dfdy, my);
+    if (!rc) rc = get_maps(pz->cache, pz->g, f, dfdz, mz);
+    if (rc) return rc;
+    const unsigned long long seq = ++z->seq;
+    EdgeX ex;
+    memset(&ex, 0, sizeof ex);
+    ex.nedge = (pz->g.nlines + CH - 1) / CH;
+    ex.nlines = pz->g.nlines;
+    ex.n = pz->g.n;
+    ex.has_lo = pz->kp.lo_closure ? 0 : 1;
+    ex.has_hi = pz->kp.hi_closure ? 0 : 1;
+    ex.sk_mid = pz->kp.sk_mid; ex.l_mid = pz->kp.l_mid;
+    ex.sk_last = pz->kp.tail.sk[pz->g.jl]; ex.l_last = pz->kp.tail.l[pz->g.jl];
+    ex.f = f;
+    ex.faces = q.own_faces;
+    ex.peer_face_lo = q.peer_face_lo; ex.peer_face_hi = q.peer_face_hi;
+    ex.push_lo = q.push_lo; ex.push_hi = q.push_hi;
+    ex.flag_lo = q.flag_lo; ex.flag_hi = q.flag_hi;
+    ex.seq = seq;
+    ex.head = pz->kp.head;
+    rc = counter_pair(&ex.done, st, &pz->pool);
+    if (rc) return rc;
+    const long nitems = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
+    rc = launch_xy<4>(px, py, mx, my, nitems, st, &ex, &mz.tm_in);
+    if (rc) return rc;
+    rc = cfd_reduced_unknowns_deferred(pz, q.faces_nb, q.halo_lo, q.halo_hi, f, z->ab, q.wait_lo, q.wait_hi, seq, stream);
+    if (rc) return rc;
+    z->pending = false;
+    rc = cfd_apply_coupled(pz, f, dfdz, q.halo_lo, q.halo_hi, z->ab, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(z->ev_apply, st));
+    z->applied = true;
     return CFD_OK;
 }

@@ -134,6 +134,38 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Cross-GPU arrival flags.  A waiter polls with ld.acquire.sys and backs off with __nanosleep (the spinning thread
+// must not starve the SM's other warps); after `timeout_ns` it gives up, records CFD_ETIMEOUT in the host-mapped
+// error word `err` (the host returns it from the next library call, cfd_async_status) and lets the kernel finish
+// on whatever is in the buffers -- a rank that is minutes late (first-call set-up, a debugger, I/O) must not cost
+// the waiting rank its CUDA context, which a __trap() would.
+struct WaitP {
+    unsigned long long timeout_ns;
+    int *err;                        // host-mapped (zero-copy) error word, may be nullptr
+};
+
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long seq, const WaitP &w)
+{
+    if (ld_acquire_sys(flag) >= seq) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned ns = 32;
+    while (ld_acquire_sys(flag) < seq) {
+        __nanosleep(ns);
+        if (ns < 2048) ns <<= 1;
+        if (global_timer_ns() - t0 > w.timeout_ns) {
+            if (w.err) { *(volatile int *)w.err = -4; __threadfence_system(); }
+            return;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reduced (interface) system of one line, solved for this rank's two unknowns only:
 //   alpha = the left neighbour's last point, beta = the right neighbour's first point.
@@ -142,16 +174,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // and closed with a 2x2 solve, so it needs registers only.
 //   lu = [6][2P]: a_i, c_i, 1/p_i, c_i/p_i (top-down pivots p), 1/q_i, a_i/q_i (bottom-up pivots q).
 // ------------------------------------------------------------------------------------------------
+// PEER: the planes are written by the neighbour GPUs while the calling kernel may already be running (it waits for
+// their arrival flags first): they are read with ld.global.cg (L2, never the non-coherent path), see peer_ld().
+__device__ __forceinline__ double peer_ld(const double *p) { return __ldcg(p); }
+
+template <bool PEER>
 __device__ __forceinline__ void reduced_unknowns(const double *faces_all, const double *__restrict__ lu,
                                                  long nlines, long line, int P, int rank, double &alpha, double &beta)
 {
     const int m = 2 * P;
     const double *a = lu, *c = lu + m, *ip = lu + 2 * m, *cp = lu + 3 * m, *iq = lu + 4 * m, *aq = lu + 5 * m;
     const int r0 = 2 * rank, r1 = 2 * rank + 1;
-    double t = faces_all[line] * ip[0];
-    for (int i = 1; i <= r0; i++) t = (faces_all[(long)i * nlines + line] - a[i] * t) * ip[i];
-    double u = faces_all[(long)(m - 1) * nlines + line] * iq[m - 1];
-    for (int i = m - 2; i >= r1; i--) u = (faces_all[(long)i * nlines + line] - c[i] * u) * iq[i];
+    auto face = [&](int i) { return PEER ? peer_ld(faces_all + (long)i * nlines + line) : faces_all[(long)i * nlines + line]; };
+    double t = face(0) * ip[0];
+    for (int i = 1; i <= r0; i++) t = (face(i) - a[i] * t) * ip[i];
+    double u = face(m - 1) * iq[m - 1];
+    for (int i = m - 2; i >= r1; i--) u = (face(i) - c[i] * u) * iq[i];
     // x[r0] = t - cp[r0]*x[r1];  x[r1] = u - aq[r1]*x[r0]
     alpha = (t - cp[r0] * u) / (1.0 - cp[r0] * aq[r1]);
     beta = u - aq[r1] * alpha;
@@ -688,7 +726,7 @@ __global__ void reduced_correct_kernel(double *__restrict__ x, const double *__r
     const int lane = threadIdx.x & 31;
     if (line >= g.nlines) return;
     double alpha, beta;
-    reduced_unknowns(faces_all, lu, g.nlines, line, P, rank, alpha, beta);
+    reduced_unknowns<false>(faces_all, lu, g.nlines, line, P, rank, alpha, beta);
     const long o = line / g.inner, col = line % g.inner;
     double *xl = x + (o * g.n) * g.inner + col;
     const int n = g.n;
@@ -714,22 +752,22 @@ __global__ void reduced_correct_kernel(double *__restrict__ x, const double *__r
 // interface planes (all 2P of them, or the neighbour-only buffer with its own small elimination table).
 // Optionally first waits (bounded spin) until the neighbours' planes of call `seq` have landed.
 __global__ void __launch_bounds__(256)
-reduced_planes_kernel(const double *__restrict__ faces, const double *__restrict__ lu, long nlines, int P, int rank,
-                      double *__restrict__ ab, const unsigned long long *flag0, const unsigned long long *flag1,
-                      unsigned long long seq)
+reduced_planes_kernel(const double *faces, const double *__restrict__ lu, long nlines, int P, int rank,
+                      double *ab, const unsigned long long *flag0, const unsigned long long *flag1,
+                      unsigned long long seq, WaitP wp)
 {
+    // `faces` is peer-written while this kernel runs (no __restrict__, no const-cache loads: peer_ld)
     if (flag0 || flag1) {
         if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
-            if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+            if (flag0) wait_flag(flag0, seq, wp);
+            if (flag1) wait_flag(flag1, seq, wp);
         }
         __syncthreads();
     }
     const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= nlines) return;
     double alpha, beta;
-    reduced_unknowns(faces, lu, nlines, line, P, rank, alpha, beta);
+    reduced_unknowns<true>(faces, lu, nlines, line, P, rank, alpha, beta);
     ab[line] = alpha;
     ab[nlines + line] = beta;
 }
@@ -742,17 +780,17 @@ reduced_planes_kernel(const double *__restrict__ faces, const double *__restrict
 //   own lo face += w_lo * (halo_lo - our row 0)       left neighbour's hi face  += w_hi * (our row 0 - halo_lo)
 //   own hi face += w_hi * (halo_hi - our row n-1)     right neighbour's lo face += w_lo * (our row n-1 - halo_hi)
 __global__ void __launch_bounds__(256)
-reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *__restrict__ lu, long nlines, int pv,
-                               int own, double *__restrict__ ab, const double *__restrict__ halo_lo,
-                               const double *__restrict__ halo_hi, const double *__restrict__ f, long inner, int n,
+reduced_planes_deferred_kernel(const double *faces, const double *__restrict__ lu, long nlines, int pv,
+                               int own, double *ab, const double *halo_lo, const double *halo_hi,
+                               const double *__restrict__ f, long inner, int n,
                                double w_lo, double w_hi, const unsigned long long *flag0,
-                               const unsigned long long *flag1, unsigned long long seq)
+                               const unsigned long long *flag1, unsigned long long seq, WaitP wp)
 {
+    // faces / halo_lo / halo_hi are peer-written while this kernel runs: no __restrict__, loads through peer_ld
     if (flag0 || flag1) {
         if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
-            if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+            if (flag0) wait_flag(flag0, seq, wp);
+            if (flag1) wait_flag(flag1, seq, wp);
         }
         __syncthreads();
     }
@@ -760,21 +798,21 @@ reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *_
     if (line >= nlines) return;
     double v[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) v[i] = (i < 2 * pv) ? faces[(long)i * nlines + line] : 0.0;
+    for (int i = 0; i < 6; i++) v[i] = (i < 2 * pv) ? peer_ld(faces + (long)i * nlines + line) : 0.0;
     const long o = line / inner, col = line % inner;
     const double *fl = f + (o * n) * inner + col;
     if (halo_lo) {                                       // there is a left neighbour
-        const double d = halo_lo[line] - fl[0];
+        const double d = peer_ld(halo_lo + line) - fl[0];
         v[2 * own] += w_lo * d;
         v[2 * own - 1] -= w_hi * d;
     }
     if (halo_hi) {                                       // there is a right neighbour
-        const double d = halo_hi[line] - fl[(long)(n - 1) * inner];
+        const double d = peer_ld(halo_hi + line) - fl[(long)(n - 1) * inner];
         v[2 * own + 1] += w_hi * d;
         v[2 * own + 2] -= w_lo * d;
     }
     double alpha, beta;
-    reduced_unknowns(v, lu, 1, 0, pv, own, alpha, beta);
+    reduced_unknowns<false>(v, lu, 1, 0, pv, own, alpha, beta);
     ab[line] = alpha;
     ab[nlines + line] = beta;
 }
@@ -782,10 +820,11 @@ reduced_planes_deferred_kernel(const double *__restrict__ faces, const double *_
 // ------------------------------------------------------------------------------------------------
 // Interface planes straight from f, WITHOUT the block solve: faces[0] = -x_R[0], faces[1] = -x_R[n-1]
 // (what negateAndCopyFaces, code/cuda/kernels.cu:76-113, extracts after the reference's full local solve).
-// x_R[0] depends on the first rows only and x_R[n-1] on the last rows only, up to 0.268^32 = 5e-19:
-//   head: forward rows 0..31 with the HEAD table, back-substitute from x_31 = e_31 down to x_0;
-//   tail: forward rows n-33..n-1 from a zero state with the MID constants and the last TAIL row; x_{n-1} = e_{n-1}.
-// One thread per line; reads 33 + 34 rows of f (8 B each) instead of the whole block.  Needs n >= 66.
+// x_R[0] depends on the first rows only and x_R[n-1] on the last rows only, up to 0.268^31 = 1.9e-18:
+//   head: forward rows 0..30 with the HEAD table (row 30 reads f[31]), back-substitute from x_30 = e_30 down to x_0;
+//   tail: forward rows n-31..n-1 from a zero state with the MID constants and the last TAIL row; x_{n-1} = e_{n-1}.
+// One thread per line; reads the first 32 and the last 32 rows of f -- exactly one 32-row tile per block end, which is
+// what lets the same work ride in the fused x/y launch as two-tile items (kernels_xy.cuh xy_run_edge).  Needs n >= 66.
 // ------------------------------------------------------------------------------------------------
 struct EdgeP {
     long nlines, inner;
@@ -826,7 +865,7 @@ __device__ __forceinline__ void publish_when_grid_done(unsigned long long *done,
     }
 }
 
-// The 67 rows are read once and must not push the tiles other kernels share through L2 out of it (the exchange chain
+// The 64 rows are read once and must not push the tiles other kernels share through L2 out of it (the exchange chain
 // runs beside the fused d/dx + d/dy launch): streaming (evict-first) loads.
 #ifndef EDGE_LD
 #define EDGE_LD __ldcs
@@ -841,35 +880,35 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
     const long st = p.inner;
     double lo_face = 0.0, hi_face = 0.0;
     if (active && !p.lo_closure) {
-        double F[CH + 1], e[CH];
+        double F[CH], e[CH - 1];
 #pragma unroll
-        for (int j = 0; j <= CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
+        for (int j = 0; j < CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
         double fm1 = p.defer ? F[0] : __ldg(p.halo_lo + line), eprev = 0.0;
         if (p.push_lo) p.push_lo[line] = F[0];            // our first row = the left neighbour's f[n]
 #pragma unroll
-        for (int j = 0; j < CH; j++) {
+        for (int j = 0; j < CH - 1; j++) {
             eprev = fma(-p.head.l[j], eprev, p.head.sk[j] * (F[j + 1] - fm1));
             e[j] = eprev;
             fm1 = F[j];
         }
         double x = 0.0;
 #pragma unroll
-        for (int j = CH - 1; j >= 0; j--) x = fma(-p.head.g[j], x, e[j]);
+        for (int j = CH - 2; j >= 0; j--) x = fma(-p.head.g[j], x, e[j]);
         lo_face = -x;
     }
     if (active && !p.hi_closure) {
         const int n = p.n;
-        const double *ft = fl + (long)(n - CH - 2) * st;       // rows n-34 .. n-1
-        double F[CH + 2];
+        const double *ft = fl + (long)(n - CH) * st;           // rows n-32 .. n-1
+        double F[CH];
 #pragma unroll
-        for (int j = 0; j < CH + 2; j++) F[j] = EDGE_LD(ft + (long)j * st);
-        const double hval = p.defer ? F[CH + 1] : __ldg(p.halo_hi + line);
-        if (p.push_hi) p.push_hi[line] = F[CH + 1];       // our last row = the right neighbour's f[-1]
+        for (int j = 0; j < CH; j++) F[j] = EDGE_LD(ft + (long)j * st);
+        const double hval = p.defer ? F[CH - 1] : __ldg(p.halo_hi + line);
+        if (p.push_hi) p.push_hi[line] = F[CH - 1];       // our last row = the right neighbour's f[-1]
         double eprev = 0.0;
 #pragma unroll
-        for (int j = 1; j <= CH; j++)                           // rows n-33 .. n-2
+        for (int j = 1; j < CH - 1; j++)                        // rows n-31 .. n-2
             eprev = fma(-p.l_mid, eprev, p.sk_mid * (F[j + 1] - F[j - 1]));
-        eprev = fma(-p.l_last, eprev, p.sk_last * (hval - F[CH]));   // row n-1: neighbour point from the halo
+        eprev = fma(-p.l_last, eprev, p.sk_last * (hval - F[CH - 2]));   // row n-1: neighbour point from the halo
         hi_face = -eprev;
     }
     if (active) {
@@ -898,11 +937,10 @@ push_planes_kernel(const double2 *__restrict__ src0, double2 *__restrict__ dst0,
 
 // Stream-ordered wait until the neighbours' data of call `seq` has landed in this rank's memory.
 __global__ void wait_flags_kernel(const unsigned long long *flag0, const unsigned long long *flag1,
-                                  unsigned long long seq)
+                                  unsigned long long seq, WaitP wp)
 {
-    const long long t0 = clock64();
-    if (flag0) while (ld_acquire_sys(flag0) < seq) if (clock64() - t0 > 20000000000LL) __trap();
-    if (flag1) while (ld_acquire_sys(flag1) < seq) if (clock64() - t0 > 20000000000LL) __trap();
+    if (flag0) wait_flag(flag0, seq, wp);
+    if (flag1) wait_flag(flag1, seq, wp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -13,7 +13,8 @@
 namespace cfd {
 
 struct XYParams {
-    long nitems;        // nz * (nxp + nyp)
+    long nitems;        // entries of the draw order
+    long nxy;           // nz * (nxp + nyp): item ids below are x / y bundles, ids from here on are edge items
     int nxp, nyp;       // x-bundles (ny/32) and y-bundles (ceil(nx/32)) per plane
     unsigned long long *counter;
     const int *order;   // draw position -> (item << 3) | segment, item = plane * (nxp + nyp) + index in plane;
@@ -24,13 +25,6 @@ struct XYParams {
     // warps starting together (worth 3 % on lines of >= 32 tiles, nothing on shorter ones).
     float tau_ns, slot_items;
 };
-
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // One item = all chunks of one bundle, x (CONTIG) or y (STRIDED).  Ring state is shared across items.
 //
@@ -127,12 +121,96 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
     }
 }
 
-template <int NS, bool SEG>
+// ------------------------------------------------------------------------------------------------
+// Edge items (EDGE = true, cfd_zpart_apply_xyz): the interface-face pass of a z-partitioned d/dz -- the work of
+// edge_faces_kernel in its one-launch ("defer") form -- as work items of this persistent kernel instead of a launch
+// beside it (a separate launch serialises with a persistent kernel whatever the stream priority: DESIGN.md section 6).
+// Item t = 32 consecutive columns of the flattened [ny*nx] plane: the head tile (planes 0..31) and the tail tile
+// (planes n-32..n-1) arrive through the same TMA ring (z-direction tensor map); nothing else is read.
+// The faces go to the local buffer and straight into the neighbours' (NVLink stores), this slab's first / last plane
+// into the neighbours' halo slots; edge items are drawn FIRST, every warp counts the ones it finished and reports them
+// when it turns to its first x / y item, and the warp that completes the count raises the neighbours' flags.
+// Same arithmetic, in the same order, as edge_faces_kernel: the faces are bit-identical to cfd_edge_faces_push.
+// ------------------------------------------------------------------------------------------------
+struct EdgeX {
+    long nedge;                              // edge items = ceil(ny*nx / 32); 0 = none
+    long nlines;                             // ny * nx
+    int n;                                   // planes of the slab (>= 66)
+    int has_lo, has_hi;                      // a left / right neighbour exists
+    double sk_mid, l_mid, sk_last, l_last;
+    const double *f;
+    double *faces;                           // local [2][plane]: -x_R[first], -x_R[last] (with guessed neighbour points)
+    double *peer_face_lo, *peer_face_hi;     // the neighbours' slots for them
+    double *push_lo, *push_hi;               // the neighbours' halo slots for our first / last plane
+    unsigned long long *flag_lo, *flag_hi;   // the neighbours' arrival flags
+    unsigned long long *done;                // finished edge items (zero on entry, zero on exit)
+    unsigned long long seq;
+    RowTab head;
+};
+
+template <int NS, class Issue>
+__device__ __forceinline__ void xy_run_edge(const EdgeX &ex, long t, unsigned char *wbase, uint32_t bar0, int lane,
+                                            int &slot, uint32_t &phase, bool &first_step, Issue &issue)
+{
+    const long col = t * CH + lane;
+    const bool ok = col < ex.nlines;
+    auto take_tile = [&](double (&F)[CH]) {
+        mbar_wait(bar0 + 8 * slot, phase);
+        load_chunk<false>(wbase + slot * SLOT_BYTES, lane, F);
+        __syncwarp();
+        if (lane == 0 && !first_step) {      // same ring discipline as xy_run_item: refill the previous step's slot
+            tma_wait_read0();
+            issue();
+        }
+        first_step = false;
+        __syncwarp();
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    };
+    double lo_face = 0.0, hi_face = 0.0, row0 = 0.0, rowl = 0.0;
+    if (ex.has_lo) {
+        double F[CH], e[CH - 1];
+        take_tile(F);
+        double fm1 = F[0], eprev = 0.0;      // guess f[-1] := f[0]
+#pragma unroll
+        for (int j = 0; j < CH - 1; j++) {
+            eprev = fma(-ex.head.l[j], eprev, ex.head.sk[j] * (F[j + 1] - fm1));
+            e[j] = eprev;
+            fm1 = F[j];
+        }
+        double x = 0.0;
+#pragma unroll
+        for (int j = CH - 2; j >= 0; j--) x = fma(-ex.head.g[j], x, e[j]);
+        lo_face = -x;
+        row0 = F[0];
+    }
+    if (ex.has_hi) {
+        double F[CH];                        // rows n-32 .. n-1
+        take_tile(F);
+        double eprev = 0.0;
+#pragma unroll
+        for (int j = 1; j < CH - 1; j++)                                    // rows n-31 .. n-2 from a zero state
+            eprev = fma(-ex.l_mid, eprev, ex.sk_mid * (F[j + 1] - F[j - 1]));
+        eprev = fma(-ex.l_last, eprev, ex.sk_last * (F[CH - 1] - F[CH - 2]));   // row n-1, guess f[n] := f[n-1]
+        hi_face = -eprev;
+        rowl = F[CH - 1];
+    }
+    if (ok) {
+        ex.faces[col] = lo_face;
+        ex.faces[ex.nlines + col] = hi_face;
+        if (ex.peer_face_lo) ex.peer_face_lo[col] = lo_face;
+        if (ex.peer_face_hi) ex.peer_face_hi[col] = hi_face;
+        if (ex.push_lo) ex.push_lo[col] = row0;
+        if (ex.push_hi) ex.push_hi[col] = rowl;
+    }
+}
+
+template <int NS, bool SEG, bool EDGE>
 __global__ void __launch_bounds__(256, 1)
 stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_constant__ CUtensorMap tmx_out,
                  const __grid_constant__ CUtensorMap tmy_in, const __grid_constant__ CUtensorMap tmy_out,
                  const __grid_constant__ KParams px, const __grid_constant__ KParams py,
-                 const __grid_constant__ XYParams q)
+                 const __grid_constant__ XYParams q, const __grid_constant__ CUtensorMap tmz_in,
+                 const __grid_constant__ EdgeX ex)
 {
     extern __shared__ unsigned char smem_raw[];
     constexpr int PER_WARP = NS * SLOT_BYTES;
@@ -153,9 +231,18 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
     __syncwarp();
 
     // draw-table entry -> (direction, bundle, plane, tile range)
-    auto decode = [&](long e, bool &contig, long &b, int &c0, int &c2, int &kb, int &ke, int &ko, int &kp) {
+    // (edge items, EDGE only: entries beyond the nz * ipp x / y items; b = edge item, tiles 0 .. ke)
+    const long nxy = q.nxy;
+    auto decode = [&](long e, bool &contig, long &b, int &c0, int &c2, int &kb, int &ke, int &ko, int &kp) -> bool {
         const int seg = (int)(e & 7);
         const long w = e >> 3;
+        if constexpr (EDGE) {
+            if (w >= nxy) {
+                contig = false; b = w - nxy; c0 = 0; c2 = 0; kb = 0; ko = 0;
+                ke = ex.has_lo + ex.has_hi - 1; kp = ke + 1;
+                return true;
+            }
+        }
         const long z = w / ipp;
         const int r = (int)(w - z * ipp);
         contig = r < q.nxp;
@@ -171,25 +258,27 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
             kb = s0 > 0 ? s0 - 1 : 0;
             ke = s1 < K ? s1 : K - 1;
         }
+        return false;
     };
 
     // ---- producer (lane 0): one call per tile position; after the initial fill it runs NS - 1 positions ahead
     long iw = 0, ib = 0;
     int ik = 1, ikend = 0, iko = 0, ikp = 0, ic0 = 0, ic2 = 0, islot = 0;
-    bool icontig = true, dry = false, first_draw = true;
+    bool icontig = true, dry = false, first_draw = true, iedge = false;
     auto issue = [&]() {
         if (ik > ikend && !dry) {
             iw = (long)atomicAdd(q.counter, 1ULL);
             dry = iw >= q.nitems;
             if (!dry) {
-                if (first_draw && q.tau_ns > 0.f && q.slot_items > 0.f) {
+                const long pos = iw - (EDGE ? ex.nedge : 0);      // position among the x / y items (edge items come first)
+                if (first_draw && pos >= 0 && q.tau_ns > 0.f && q.slot_items > 0.f) {
                     const unsigned long long t0 = global_timer_ns();
-                    const unsigned long long wait = (unsigned long long)(floorf((float)iw / q.slot_items) * q.tau_ns);
+                    const unsigned long long wait = (unsigned long long)(floorf((float)pos / q.slot_items) * q.tau_ns);
                     while (global_timer_ns() - t0 < wait) __nanosleep(256);
                 }
-                first_draw = false;
+                if (pos >= 0) first_draw = false;
                 iw = q.order ? (long)q.order[iw] : (iw << 3);
-                decode(iw, icontig, ib, ic0, ic2, ik, ikend, iko, ikp);
+                iedge = decode(iw, icontig, ib, ic0, ic2, ik, ikend, iko, ikp);
             }
         }
         if (dry) {
@@ -199,7 +288,10 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
             const uint32_t bar = bar0 + 8 * islot;
             const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
             mbar_expect_tx(bar, SLOT_BYTES);
-            if (icontig) {
+            if (EDGE && iedge) {             // head tile = planes 0..31, tail tile = planes n-32..n-1
+                const int row = (ex.has_lo && ik == 0) ? 0 : ex.n - CH;
+                tma_load_3d(dst, &tmz_in, bar, (int)(ib * CH), row, 0);
+            } else if (icontig) {
                 tma_load_2d(dst, &tmx_in, bar, ik * CH, (int)(ib * CH));
                 tma_load_2d(dst + 4096, &tmx_in, bar, ik * CH + 16, (int)(ib * CH));
             } else {
@@ -219,15 +311,41 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
     int slot = 0;
     uint32_t phase = 0;
     bool first_step = true;
+    unsigned long long edge_pending = 0;     // EDGE: edge items this warp has finished and not yet reported
+    auto edge_report = [&]() {
+        __threadfence_system();              // every lane: its face / halo stores are visible system-wide
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned long long prev = atomicAdd(ex.done, edge_pending);
+            if (prev + edge_pending == (unsigned long long)ex.nedge) {     // all edge items of the launch are done
+                *ex.done = 0ULL;
+                __threadfence_system();
+                if (ex.flag_lo) st_release_sys(ex.flag_lo, ex.seq);
+                if (ex.flag_hi) st_release_sys(ex.flag_hi, ex.seq);
+            }
+        }
+        edge_pending = 0;
+    };
     for (;;) {
         const long w = tag[slot];
         if (w < 0) break;
         bool contig;
         long b;
         int c0, c2, kb, ke, ko, kp;
-        decode(w, contig, b, c0, c2, kb, ke, ko, kp);
+        const bool edge = decode(w, contig, b, c0, c2, kb, ke, ko, kp);
+        if constexpr (EDGE) {
+            if (edge) {
+                xy_run_edge<NS>(ex, b, wbase, bar0, lane, slot, phase, first_step, issue);
+                ++edge_pending;
+                continue;
+            }
+            if (edge_pending) edge_report();
+        }
         if (contig) xy_run_item<true, NS, SEG>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
         else        xy_run_item<false, NS, SEG>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
+    }
+    if constexpr (EDGE) {
+        if (edge_pending) edge_report();
     }
     if (lane == 0) {
         tma_wait_all0();

@@ -8,7 +8,7 @@ The reference's multi-rank dfdx (code/cuda/compact.py:29-44) is
 Here, for a grid split into P slabs along z:
     d/dx, d/dy : no communication at all (lines never leave the slab);
     d/dz       : (1) send/recv ONE boundary plane of f with each z-neighbour;
-                 (2) interface planes -x_R[first], -x_R[last] from the 33 + 34 planes next to the slab ends
+                 (2) interface planes -x_R[first], -x_R[last] from the first 32 and the last 32 planes of the slab
                      (cfd_edge_faces: they do not depend on planes further away, to 5e-19);
                  (3) ALL-GATHER them (or, comm="pairwise"/"nvlink", one plane from each z-neighbour) -- every
                      rank then solves the reduced system redundantly for its own two unknowns per line
@@ -89,47 +89,55 @@ def exchange_interface_planes(faces_nb, own, pv, rank, size, group=None):
     return faces_nb
 
 
-class PeerExchange:
+class ZPart:
     """
-    NVLink peer-memory buffers of one rank for the d/dz exchange (comm="nvlink"): no NCCL on the data path.
-    One symmetric allocation per rank (torch.distributed._symmetric_memory), laid out in doubles as
-        halo  [2 parities][2][plane]   slot 0: last plane of rank-1, slot 1: first plane of rank+1
-        faces [2 parities][6][plane]   the neighbour-only interface buffer of cfd_apply_coupled_nb
-        flags [16]                     uint64 arrival counters: 0/1 halo from left/right, 2/3 face from left/right
-    Neighbours write into it with plain stores from libcfd_b200's kernels (cfd_push_planes, cfd_edge_faces_p2p)
-    and raise the flags to the call number; consumers wait with cfd_wait_flags.  Two parities + the monotone
-    call number make buffer re-use safe without any global barrier.
+    One rank of a z-partitioned line with the host side in C (`cfd_zpart_*`, include/cfd_b200.h): the rank's receive
+    buffer (halo planes, interface planes, arrival flags) is a plain cudaMalloc allocation of libcfd_b200, the two
+    z-neighbours' buffers are mapped with CUDA IPC handles, and the kernels store into them over NVLink and
+    synchronise with flags -- no NCCL, no torch-internal API on the data path.  torch.distributed only carries the
+    64-byte handles once, at construction (any backend; the reference would use its MPI line communicator).
     """
 
-    def __init__(self, plane, rank, size, group, device):
-        import torch.distributed._symmetric_memory as symm
-        self.plane, self.rank, self.size = int(plane), rank, size
-        total = 4 * self.plane + 12 * self.plane + 16
-        self.buf = symm.empty(total, dtype=torch.float64, device=device)
-        self.buf.zero_()
-        torch.cuda.synchronize(device)
-        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        dist.barrier(group)                      # every rank's flags are zero before anybody pushes
-        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.seq = 0
+    def __init__(self, plan, rank, size, group=None):
+        import ctypes
+        from ._lib import CFD_IPC_HANDLE_BYTES, check, lib
+        self._lib, self._check = lib(), check
+        self.handle = ctypes.c_void_p()
+        check(self._lib.cfd_zpart_create(ctypes.byref(self.handle), plan.handle))
+        self._plan = plan                       # keeps the cfd_plan alive
+        buf = ctypes.create_string_buffer(CFD_IPC_HANDLE_BYTES)
+        check(self._lib.cfd_zpart_export(self.handle, buf))
+        handles = [None] * size
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        lo = ctypes.create_string_buffer(handles[rank - 1], CFD_IPC_HANDLE_BYTES) if rank > 0 else None
+        hi = ctypes.create_string_buffer(handles[rank + 1], CFD_IPC_HANDLE_BYTES) if rank < size - 1 else None
+        check(self._lib.cfd_zpart_connect(self.handle, lo, hi))
+        self.group = group
 
-    # byte addresses inside rank r's buffer
-    def halo(self, r, parity, slot):
-        return self.ptrs[r] + 8 * ((parity * 2 + slot) * self.plane)
+    @staticmethod
+    def _sp(f):
+        import ctypes
+        return ctypes.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)
 
-    def faces(self, r, parity, i):
-        return self.ptrs[r] + 8 * (4 * self.plane + (parity * 6 + i) * self.plane)
+    def begin(self, f):
+        self._check(self._lib.cfd_zpart_begin(self.handle, f.data_ptr(), self._sp(f)))
 
-    def flag(self, r, k):
-        return self.ptrs[r] + 8 * (16 * self.plane + k)
+    def apply(self, f, out):
+        self._check(self._lib.cfd_zpart_apply(self.handle, f.data_ptr(), out.data_ptr(), self._sp(f)))
+        return out
 
-    def local_halo(self, parity, slot):
-        o = (parity * 2 + slot) * self.plane
-        return self.buf[o:o + self.plane]
+    def apply_xyz(self, plan_x, plan_y, f, out_x, out_y, out_z):
+        self._check(self._lib.cfd_zpart_apply_xyz(self.handle, plan_x.handle, plan_y.handle, f.data_ptr(),
+                                                  out_x.data_ptr(), out_y.data_ptr(), out_z.data_ptr(), self._sp(f)))
+        return out_x, out_y, out_z
 
-    def local_faces(self, parity, n):
-        o = 4 * self.plane + parity * 6 * self.plane
-        return self.buf[o:o + n * self.plane]
+    def close(self):
+        """Collective: no neighbour may still be storing into this rank's buffer when it is freed."""
+        if self.handle:
+            torch.cuda.synchronize()
+            dist.barrier(self.group)
+            self._lib.cfd_zpart_destroy(self.handle)
+            self.handle = None
 
 
 class PartitionedDerivative:
@@ -150,12 +158,13 @@ class PartitionedDerivative:
              "pairwise"  : one interface plane from each line neighbour by NCCL send/recv (exact in fp64 for blocks
                            >= 64 rows; fused mode only)
              "nvlink"    : the same neighbour-only data flow, but the kernels store halo and interface planes
-                           straight into the neighbours' memory over NVLink/NVSwitch (symmetric memory) and
-                           synchronise with flags -- no NCCL call on the data path (fused mode, z lines only:
+                           straight into the neighbours' memory over NVLink/NVSwitch (cfd_zpart: CUDA IPC mappings)
+                           and synchronise with flags -- no NCCL call on the data path (fused mode, z lines only:
                            their boundary planes are contiguous; other directions use "pairwise").  ONE producer
                            launch (cfd_edge_faces_push: faces without the neighbour points + own boundary rows into
                            the neighbours' buffers) and one consumer (cfd_reduced_unknowns_deferred: folds the halo
-                           terms in); "nvlink-2step" keeps the first protocol (halo push, wait, edge faces, reduce)
+                           terms in).  (The first, two-step protocol -- halo push, wait, edge faces, reduce -- lives on
+                           as C entry points only: cfd_push_planes / cfd_wait_flags / cfd_edge_faces_p2p.)
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
@@ -165,11 +174,8 @@ class PartitionedDerivative:
         self.local_shape = tuple(int(s) for s in local_shape)
         part = (self.rank, self.size) if self._partitioned else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
-        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink", "nvlink-2step")
-        self._two_step = comm == "nvlink-2step"     # halo push + wait before the edge kernel (the first protocol)
-        if self._two_step:
-            comm = "nvlink"
-        self._peer = None
+        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink")
+        self._zp = None
         self.mode = mode if self.local_shape[self._dim] >= 66 else "reference"
         self.comm = comm if self.mode == "fused" else "allgather"
         if self.comm == "nvlink" and self._dim != 0:
@@ -210,90 +216,32 @@ class PartitionedDerivative:
             self._ab = mk(2, *ps)
         return self._buf
 
-    def _exchange_nvlink(self, f):
-        """Halo push -> edge faces written into the neighbours' buffers -> flags; all stream-ordered kernels."""
-        import ctypes
-        from ._lib import check, lib
-        nz, ny, nx = self.local_shape
-        if self._peer is None:
-            self._peer = PeerExchange(ny * nx, self.rank, self.size, self.group, f.device)
-        px, r, P = self._peer, self.rank, self.size
-        px.seq += 1
-        seq, par = px.seq, px.seq & 1
-        pv, own = self.solver.nb_layout()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(f.device).cuda_stream)
-        left, right = (r - 1 if r > 0 else None), (r + 1 if r < P - 1 else None)
-        L = lib()
-        if not getattr(self, "_two_step", False):
-            halo_lo = px.local_halo(par, 0) if left is not None else None
-            halo_hi = px.local_halo(par, 1) if right is not None else None
-            faces_nb = px.local_faces(par, 2 * pv)
-            own_left = 1 if (left is not None and left > 0) else 0
-            plan = self.solver._plan(self.solver.direction, self.solver.spacing)
-            check(L.cfd_edge_faces_push(
-                plan.handle, f.data_ptr(), faces_nb.data_ptr() + 8 * 2 * own * px.plane,
-                px.faces(left, par, 2 * own_left + 2) if left is not None else None,
-                px.faces(right, par, 1) if right is not None else None,
-                px.halo(left, par, 1) if left is not None else None,
-                px.halo(right, par, 0) if right is not None else None,
-                px.flag(left, 3) if left is not None else None, px.flag(right, 2) if right is not None else None,
-                seq, stream))
-            self._buffers(f)
-            check(L.cfd_reduced_unknowns_deferred(
-                plan.handle, faces_nb.data_ptr(),
-                halo_lo.data_ptr() if halo_lo is not None else None,
-                halo_hi.data_ptr() if halo_hi is not None else None, f.data_ptr(), self._ab.data_ptr(),
-                px.flag(r, 2) if left is not None else None, px.flag(r, 3) if right is not None else None,
-                seq, stream))
-            return halo_lo, halo_hi, self._ab
-        check(L.cfd_push_planes(
-            f[0].data_ptr() if left is not None else None, px.halo(left, par, 1) if left is not None else None,
-            f[-1].data_ptr() if right is not None else None, px.halo(right, par, 0) if right is not None else None,
-            ny * nx, px.flag(left, 1) if left is not None else None, px.flag(right, 0) if right is not None else None,
-            seq, stream))
-        check(L.cfd_wait_flags(px.flag(r, 0) if left is not None else None,
-                               px.flag(r, 1) if right is not None else None, seq, stream))
-        halo_lo = px.local_halo(par, 0) if left is not None else None
-        halo_hi = px.local_halo(par, 1) if right is not None else None
-        faces_nb = px.local_faces(par, 2 * pv)
-        own_left = 1 if (left is not None and left > 0) else 0
-        plan = self.solver._plan(self.solver.direction, self.solver.spacing)
-        check(L.cfd_edge_faces_p2p(
-            plan.handle, f.data_ptr(),
-            halo_lo.data_ptr() if halo_lo is not None else None, halo_hi.data_ptr() if halo_hi is not None else None,
-            faces_nb.data_ptr() + 8 * 2 * own * px.plane,
-            px.faces(left, par, 2 * own_left + 2) if left is not None else None,
-            px.faces(right, par, 1) if right is not None else None,
-            px.flag(left, 3) if left is not None else None, px.flag(right, 2) if right is not None else None,
-            seq, stream))
-        self._buffers(f)
-        # wait for the neighbours' interface planes inside the (tiny) reduced-solve kernel, then alpha / beta
-        check(L.cfd_reduced_unknowns(plan.handle, faces_nb.data_ptr(), 1, self._ab.data_ptr(),
-                                     px.flag(r, 2) if left is not None else None,
-                                     px.flag(r, 3) if right is not None else None, seq, stream))
-        return halo_lo, halo_hi, self._ab
+    def _zpart(self, f):
+        """The C-side exchange object of comm="nvlink", created collectively on first use.  CUDA IPC can be
+        unavailable (containers without a shared PID / IPC namespace): the outcome is agreed by all-reduce and every
+        rank of the line falls back to the NCCL send/recv exchange together."""
+        if self._zp is None and self.comm == "nvlink":
+            ok = 1
+            try:
+                plan = self.solver._plan(self.solver.direction, self.solver.spacing)
+                self._zp = ZPart(plan, self.rank, self.size, self.group)
+            except Exception as e:                                       # pragma: no cover - depends on the box
+                import sys
+                print(f"[cfd_b200] CUDA IPC peer mapping unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
+                      file=sys.stderr)
+                ok = 0
+            on_gpu = dist.get_backend(self.group) == "nccl"
+            flag = torch.tensor([ok], dtype=torch.int32, device=f.device if on_gpu else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if flag.item() == 0:
+                if self._zp is not None:
+                    self._zp.close()
+                self._zp = None
+                self.comm = "pairwise"
+        return self._zp
 
     def _exchange(self, f):
         """Steps (1)-(3) of the fused path; returns (halo_lo, halo_hi, alpha/beta planes) for the coupled kernel."""
-        if self.comm == "nvlink" and self._peer is None:
-            # symmetric memory is a torch-internal API: if it cannot be set up on this system, every rank falls
-            # back (collectively -- the outcome is agreed by all-reduce) to the NCCL send/recv exchange
-            nz, ny, nx = self.local_shape
-            ok = 1
-            try:
-                self._peer = PeerExchange(ny * nx, self.rank, self.size, self.group, f.device)
-            except Exception as e:                                   # pragma: no cover - depends on the box
-                import sys
-                print(f"[cfd_b200] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL send/recv",
-                      file=sys.stderr)
-                ok = 0
-            flag = torch.tensor([ok], dtype=torch.int32, device=f.device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if flag.item() == 0:
-                self._peer = None
-                self.comm = "pairwise"
-        if self.comm == "nvlink":
-            return self._exchange_nvlink(f)
         lo_buf, hi_buf, faces, faces_all, faces_nb, pv, own = self._buffers(f)
         first, last = self._ends(f)
         halo_lo, halo_hi = exchange_halo_planes(first, last, self.rank, self.size, self.group, lo_buf, hi_buf)
@@ -313,6 +261,13 @@ class PartitionedDerivative:
         next __call__ with the same f picks the result up.  No-op where there is nothing to exchange."""
         if not self._partitioned or self.size == 1 or self.mode != "fused":
             return
+        if self._zpart(f) is not None:          # comm "nvlink": cfd_zpart orders the two streams with its own events
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=f.device)
+            self._side.wait_stream(torch.cuda.current_stream(f.device))     # f is ready on the caller's stream
+            with torch.cuda.stream(self._side):
+                self._zp.begin(f)
+            return
         if self._side is None:
             self._side = torch.cuda.Stream(device=f.device)
         cur = torch.cuda.current_stream(f.device)
@@ -326,6 +281,10 @@ class PartitionedDerivative:
     def __call__(self, f, out=None):
         if not self._partitioned or self.size == 1:
             return self.solver(f, out)
+        if self.mode == "fused" and self._zpart(f) is not None:
+            if out is None:
+                out = torch.empty_like(f)
+            return self._zp.apply(f, out)
         if self.mode == "fused":
             if self._pending is not None and self._pending[0] == f.data_ptr():
                 _, (halo_lo, halo_hi, planes), ev = self._pending
@@ -348,3 +307,26 @@ class ZPartitionedDerivative(PartitionedDerivative):
     """Derivative of a z-partitioned field; `local_shape` is this rank's slab [nz/P, ny, nx].  d/dx and d/dy
     (direction 0, 1) never leave the slab; d/dz is the partitioned line."""
     _part_axis = 2
+
+    def gradient(self, f, dx, dy, out=None):
+        """(df/dx, df/dy, df/dz) of the slab.  With direction = 2 and comm = "nvlink": three launches
+        (cfd_zpart_apply_xyz) -- the fused d/dx + d/dy kernel with the edge-face work of d/dz as its first work
+        items (faces and halo planes cross NVLink while x / y are computed), the reduced solve, the coupled d/dz
+        kernel.  Otherwise the exchange is started on a side stream and the same results come from separate calls."""
+        assert self.direction == 2, "gradient() belongs to the d/dz operator of the slab"
+        out = [torch.empty_like(f) if o is None else o for o in (out if out is not None else (None, None, None))]
+        if getattr(self, "_xy", None) is None:
+            self._xy = CompactFiniteDifferenceSolver(self.local_shape)
+        if self.size > 1 and self.mode == "fused" and self._zpart(f) is not None:
+            px, py = self._xy._plan(0, float(dx)), self._xy._plan(1, float(dy))
+            self._zp.apply_xyz(px, py, f, out[0], out[1], out[2])
+            return tuple(out)
+        self.begin(f)
+        self._xy.dfdxy(f, dx, dy, out[0], out[1])
+        self(f, out[2])
+        return tuple(out)
+
+    def close(self):
+        if self._zp is not None:
+            self._zp.close()
+            self._zp = None

@@ -16,6 +16,31 @@ from ._lib import check, lib
 class ReducedSolver:
     def __init__(self, shape):
         self.nz, self.ny, self.nx = (int(s) for s in shape)
+        self._plans = {}            # (a, b, c) bytes -> pt_plan: the matrix is eliminated once, not per call
+
+    def _plan(self, host):
+        key = b"".join(v.tobytes() for v in host)
+        h = self._plans.get(key)
+        if h is None:
+            if len(self._plans) >= 16:
+                self.close()
+            dp = ctypes.POINTER(ctypes.c_double)
+            h = ctypes.c_void_p()
+            check(lib().cfd_pthomas_create(ctypes.byref(h), host[0].ctypes.data_as(dp), host[1].ctypes.data_as(dp),
+                                           host[2].ctypes.data_as(dp), self.nz))
+            self._plans[key] = h
+        return h
+
+    def close(self):
+        for h in self._plans.values():
+            lib().cfd_pthomas_destroy(h)
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def solve(self, a, b, c, c2, x_d):
         """a, b, c: length-n diagonals (NumPy or tensors; a[0], c[-1] ignored).  c2 is the reference's scratch
@@ -31,8 +56,6 @@ class ReducedSolver:
             host.append(v)
         assert x_d.is_cuda and x_d.dtype == torch.float64 and x_d.is_contiguous()
         assert x_d.numel() == n * self.ny * self.nx
-        dp = ctypes.POINTER(ctypes.c_double)
         stream = ctypes.c_void_p(torch.cuda.current_stream(x_d.device).cuda_stream)
-        check(lib().cfd_pthomas(host[0].ctypes.data_as(dp), host[1].ctypes.data_as(dp), host[2].ctypes.data_as(dp),
-                                x_d.data_ptr(), n, self.ny * self.nx, stream))
+        check(lib().cfd_pthomas_solve(self._plan(host), x_d.data_ptr(), self.ny * self.nx, stream))
         return x_d

@@ -13,8 +13,9 @@
  *     small coefficient tables (code/cuda/solvers/templated/near_toeplitz.py:62-69);
  *   - the tridiagonal solve is in place (near_toeplitz.py:78); the derivative is out of place (f -> df);
  *   - calls are asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL = default
- *     stream), never allocate, never synchronise -- except the *_host convenience calls, which are
- *     synchronous and own their staging buffers;
+ *     stream), never allocate, never synchronise -- except the *_host convenience calls and the one-shot
+ *     cfd_pthomas, which are synchronous and own their staging buffers -- and may be captured into CUDA graphs
+ *     (a captured launch gets work counters of its own, so replays never collide with eager launches);
  *   - every function returns 0 on success or a negative CFD_E* code; cfd_last_error() gives the text.
  *     Nothing throws, nothing exits.  There is no CPU fallback: without a CUDA device create() fails
  *     with CFD_ECUDA.
@@ -29,15 +30,18 @@
 extern "C" {
 #endif
 
-#define CFD_B200_VERSION 100
+#define CFD_B200_VERSION 200
 
 #define CFD_OK            0
 #define CFD_EINVAL       (-1)   /* bad shape / axis / pointer / coefficient                    */
 #define CFD_ECUDA        (-2)   /* CUDA runtime or driver error (text in cfd_last_error)        */
 #define CFD_EUNSUPPORTED (-3)   /* valid request this build cannot serve                        */
+#define CFD_ETIMEOUT     (-4)   /* a kernel gave up waiting for a neighbour rank (cfd_async_status) */
 
 typedef struct cfd_plan cfd_plan;   /* derivative operator for one (shape, axis, spacing, rank position) */
 typedef struct nt_plan nt_plan;     /* batched near-Toeplitz tridiagonal solver                          */
+typedef struct pt_plan pt_plan;     /* thread-parallel Thomas for one general tridiagonal matrix         */
+typedef struct cfd_zpart cfd_zpart; /* one rank of a z-partitioned line: peer buffers + launch sequence  */
 
 int cfd_version(void);
 const char *cfd_last_error(void);   /* thread-local text of the last failure */
@@ -99,8 +103,8 @@ int cfd_reduced_correct(cfd_plan *plan, double *df, const double *faces_all, voi
 
 /* Fused multi-rank path (no correction pass).
  *   cfd_edge_faces       the same interface planes as cfd_apply + cfd_interface_pack, but directly from f and from
- *                        the 33 + 34 rows next to the block ends only (x_R[first] / x_R[last] do not depend on rows
- *                        further away, to 0.268^32 = 5e-19).
+ *                        the first 32 and the last 32 rows of the block only (x_R[first] / x_R[last] do not depend on rows
+ *                        further away, to 0.268^31 = 2e-18).
  *   cfd_reduced_unknowns solves the reduced system of every line for THIS rank's two unknowns (rows of
  *                        code/cuda/compact.py:96-111, elimination of reducedSolverKernel kernels.cu:115-145):
  *                        ab[0] = alpha plane (the left neighbour's last point), ab[1] = beta plane (the right
@@ -159,7 +163,9 @@ int cfd_reduced_unknowns_deferred(cfd_plan *plan, const double *faces_nb, const 
 
 /* Synchronous host-buffer form of cfd_apply for part_size == 1 (what the reference's OpenCL flavour
  * offers: ndarray in, ndarray out, code/ocl/compact.py:26-61).  Copies f to the device, runs the kernel,
- * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory. */
+ * copies df back; staging buffers belong to the plan.  pinned != 0 promises page-locked host memory: the
+ * promise is checked (CFD_EINVAL otherwise) and used -- x / y derivatives then move in z-slabs, copies in both
+ * directions overlapping the kernels; pinned == 0 takes the plain copy - kernel - copy sequence. */
 int cfd_apply_host(cfd_plan *plan, const double *f_host, double *df_host, int pinned);
 
 /* plane = number of lines of the block (elements of one halo / interface plane). */
@@ -203,11 +209,54 @@ void nt_destroy(nt_plan *plan);
 
 /* ---------------------------------------------------------------------------------------------------
  * Thread-parallel Thomas for `nsys` interleaved systems sharing one general tridiagonal matrix.
- * Replaces ReducedSolver.solve / reducedSolverKernel (code/cuda/reduced.py:5-18,
- * code/cuda/kernels.cu:115-145).  a, b, c: HOST arrays of length n (a[0], c[n-1] ignored);
- * d: DEVICE array [n][nsys], solved in place.  n <= 256.
+ * Replaces ReducedSolver / reducedSolverKernel (code/cuda/reduced.py:5-18, code/cuda/kernels.cu:115-145).
+ * a, b, c: HOST arrays of length n (a[0], c[n-1] ignored); d: DEVICE array [n][nsys], solved in place; n <= 256.
+ * cfd_pthomas_create eliminates the matrix once (the reference redoes it in every thread of every call,
+ * kernels.cu:127-133) and keeps the pivots on the device; cfd_pthomas_solve is then one asynchronous launch that
+ * allocates nothing.  cfd_pthomas = create + solve + stream synchronise + destroy, for one-off calls.
  * ------------------------------------------------------------------------------------------------- */
+int cfd_pthomas_create(pt_plan **plan, const double *a, const double *b, const double *c, int n);
+int cfd_pthomas_solve(pt_plan *plan, double *d, long nsys, void *stream);
+void cfd_pthomas_destroy(pt_plan *plan);
 int cfd_pthomas(const double *a, const double *b, const double *c, double *d, int n, long nsys, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * The partitioned d/dz with the host side in C: what a caller of the reference's multi-rank dfdx
+ * (code/cuda/compact.py:29-44 -- halo exchange gpuDA.py:86-113, Gather / Scatter compact.py:93-94,121-122) binds
+ * when it has no torch: one cfd_zpart per rank (= per process and GPU) owns that rank's receive buffer, maps its
+ * two z-neighbours' buffers and issues the launches.  Set-up, once:
+ *     cfd_zpart_create(&zp, plan_z)              plan_z: axis 2, part_size > 1, >= 66 planes per slab
+ *     cfd_zpart_export(zp, handle)               CFD_IPC_HANDLE_BYTES bytes to hand to both neighbours (MPI / any channel)
+ *     cfd_zpart_connect(zp, handle_lo, handle_hi)  the neighbours' handles (NULL at a physical end); cudaIpc underneath
+ *   (ranks living in ONE process -- tests, one process driving several devices with peer access enabled -- pass
+ *    cfd_zpart_buffer() of the neighbours to cfd_zpart_connect_ptr instead).
+ * Per call:
+ *     cfd_zpart_apply(zp, f, dfdz, stream)       = cfd_edge_faces_push -> cfd_reduced_unknowns_deferred ->
+ *                                                  cfd_apply_coupled: three launches, one point-to-point
+ *                                                  synchronisation, no collective, no host synchronisation;
+ *     cfd_zpart_begin(zp, f, side_stream)        optional: the first two launches early, on another stream, so that
+ *                                                  the exchange overlaps other work; the next cfd_zpart_apply on the
+ *                                                  same f picks them up (events order the streams both ways);
+ *     cfd_zpart_apply_xyz(zp, px, py, f, ...)    the whole gradient of the slab in three launches: the fused
+ *                                                  d/dx + d/dy kernel (cfd_apply_xy) with the edge-face work of d/dz
+ *                                                  as its first work items, the reduced solve, the coupled d/dz.
+ * A rank that never arrives makes the neighbours' reduced kernel give up after cfd_set_wait_timeout_ms (default
+ * 120 s; it polls with back-off and never traps): the next cfd_zpart_* call, or cfd_async_status(), returns
+ * CFD_ETIMEOUT and the results of that call are invalid.
+ * ------------------------------------------------------------------------------------------------- */
+#define CFD_IPC_HANDLE_BYTES 64
+int cfd_zpart_create(cfd_zpart **zp, cfd_plan *plan_z);
+int cfd_zpart_export(cfd_zpart *zp, void *handle);
+int cfd_zpart_connect(cfd_zpart *zp, const void *handle_lo, const void *handle_hi);
+void *cfd_zpart_buffer(cfd_zpart *zp);
+int cfd_zpart_connect_ptr(cfd_zpart *zp, void *buffer_lo, void *buffer_hi);
+int cfd_zpart_begin(cfd_zpart *zp, const double *f, void *stream);
+int cfd_zpart_apply(cfd_zpart *zp, const double *f, double *dfdz, void *stream);
+int cfd_zpart_apply_xyz(cfd_zpart *zp, cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy,
+                        double *dfdz, void *stream);
+void cfd_zpart_destroy(cfd_zpart *zp);
+int cfd_set_wait_timeout_ms(long milliseconds);
+int cfd_async_status(void);
 
 /* Tuning knobs for experiments (0 = built-in default).  Not part of the reference surface. */
 int cfd_set_launch(int warps_per_cta, int ctas_per_sm, int ring_slots);

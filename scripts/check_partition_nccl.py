@@ -54,7 +54,7 @@ full = (torch.sin(t1)[None, None, :] * torch.cos(t1)[None, :, None] * torch.sin(
 nl = N // world
 ref = C.CompactFiniteDifferenceSolver((N, N, N), h, 2)(full)[rank * nl:(rank + 1) * nl]
 slab = full[rank * nl:(rank + 1) * nl].contiguous()
-COMMS = os.environ.get("CFD_COMMS", "nvlink,nvlink-2step,pairwise,allgather").split(",")
+COMMS = os.environ.get("CFD_COMMS", "nvlink,pairwise,allgather").split(",")
 for mode, comm in [("fused", c) for c in COMMS] + [("reference", "allgather")]:
     op = C.ZPartitionedDerivative((nl, N, N), h, 2, mode=mode, comm=comm)
     got = op(slab)
@@ -101,6 +101,30 @@ for overlap in (False, True):
     if rank == 0:
         print(f"gradient step (x, y, z) {N}^3 on {world} GPUs, overlap={overlap}: {ms.item():.3f} ms -> "
               f"{3 * N ** 3 / ms.item() * 1e3:.3e} pts/s per derivative", flush=True)
+
+# the whole gradient of the slab in three launches (cfd_zpart_apply_xyz: edge-face items inside the fused x/y kernel)
+refx = C.CompactFiniteDifferenceSolver((N, N, N), h, 0)(full)[rank * nl:(rank + 1) * nl]
+refy = C.CompactFiniteDifferenceSolver((N, N, N), h, 1)(full)[rank * nl:(rank + 1) * nl]
+opg = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm="nvlink")
+for it in range(3):
+    g3 = opg.gradient(slab, h, h, o3)
+torch.cuda.synchronize()
+report(f"fused gradient (zpart_apply_xyz, comm={opg.comm}) d/dx vs single-GPU", ((g3[0] - refx).abs().max() / refx.abs().max()).item())
+report(f"fused gradient (zpart_apply_xyz, comm={opg.comm}) d/dy vs single-GPU", ((g3[1] - refy).abs().max() / refy.abs().max()).item())
+report(f"fused gradient (zpart_apply_xyz, comm={opg.comm}) d/dz vs single-GPU", ((g3[2] - ref).abs().max() / ref.abs().max()).item())
+torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    opg.gradient(slab, h, h, o3)
+e1.record()
+torch.cuda.synchronize()
+ms = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(f"fused gradient step {N}^3 on {world} GPUs (three launches): {ms.item():.3f} ms -> "
+          f"{3 * N ** 3 / ms.item() * 1e3:.3e} pts/s per derivative", flush=True)
+del refx, refy, full
 
 # (c) Cartesian process grids (grid.DA): x-, y- and z-partitioned lines through PartitionedDerivative, field
 #     generated per block on the device with DA_arange, result gathered with DA_gather_blocks and checked on rank 0

@@ -131,7 +131,7 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
 
 
 def edge_faces(F, coeffs, h, lo_closure, hi_closure, halo_lo, halo_hi):
-    """Emulation of edge_faces_kernel: interface values from the 33 + 34 rows next to the block ends."""
+    """Emulation of edge_faces_kernel: interface values from the first 32 and the last 32 rows of the block."""
     F = np.asarray(F, dtype=np.float64)
     nl, n = F.shape
     assert n >= 2 * CH + 2
@@ -140,21 +140,21 @@ def edge_faces(F, coeffs, h, lo_closure, hi_closure, halo_lo, halo_hi):
     if not lo_closure:
         fm1 = np.asarray(halo_lo, dtype=np.float64)
         eprev = np.zeros(nl)
-        e = np.zeros((nl, CH))
-        for j in range(CH):
+        e = np.zeros((nl, CH - 1))
+        for j in range(CH - 1):
             eprev = -T["head"]["l"][j] * eprev + T["head"]["sk"][j] * (F[:, j + 1] - fm1)
             e[:, j] = eprev
             fm1 = F[:, j]
         x = np.zeros(nl)
-        for j in range(CH - 1, -1, -1):
+        for j in range(CH - 2, -1, -1):
             x = -T["head"]["g"][j] * x + e[:, j]
         lo_face = -x
     if not hi_closure:
-        Ft = F[:, n - CH - 2:]
+        Ft = F[:, n - CH:]
         eprev = np.zeros(nl)
-        for j in range(1, CH + 1):
+        for j in range(1, CH - 1):
             eprev = -T["l_mid"] * eprev + T["sk_mid"] * (Ft[:, j + 1] - Ft[:, j - 1])
         jl = T["jl"]
-        eprev = -T["tail"]["l"][jl] * eprev + T["tail"]["sk"][jl] * (np.asarray(halo_hi) - Ft[:, CH])
+        eprev = -T["tail"]["l"][jl] * eprev + T["tail"]["sk"][jl] * (np.asarray(halo_hi) - Ft[:, CH - 2])
         hi_face = -eprev
     return lo_face, hi_face

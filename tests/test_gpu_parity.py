@@ -571,6 +571,181 @@ def test_one_launch_exchange_one_device(C, P, shape):
             assert relinf(got, want) <= 4 * relinf(whole, want) + 1e-15
 
 
+@pytest.mark.parametrize("P,shape", [(2, (132, 64, 96)), (3, (3 * 66, 32, 40)), (4, (4 * 70, 32, 64)), (2, (140, 12, 34))])
+def test_zpart_c_abi_one_process(C, P, shape):
+    """cfd_zpart_* (the C-side driver of the partitioned d/dz) with all P ranks in ONE process on one device: buffers
+    wired with cfd_zpart_connect_ptr, one stream per rank (a rank's consumer spins until its neighbours' producers,
+    enqueued later on other streams, have run).  cfd_zpart_apply (separate edge launch) and cfd_zpart_apply_xyz (edge
+    items inside the fused x/y kernel) against the oracle, and bit-equal to each other / to cfd_apply_xy."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import check, lib
+    L = lib()
+    rng = np.random.default_rng(40 + P)
+    hs = (0.19, 0.07, 0.23)
+    n = shape[0] // P
+    lshape = (n,) + tuple(shape[1:])
+    zsol = [C.CompactFiniteDifferenceSolver(lshape, hs[2], 2, part=(r, P)) for r in range(P)]
+    xy = C.CompactFiniteDifferenceSolver(lshape)
+    px, py = xy._plan(0, hs[0]), xy._plan(1, hs[1])
+    zps = []
+    for r in range(P):
+        h = ctypes.c_void_p()
+        check(L.cfd_zpart_create(ctypes.byref(h), zsol[r]._plan(2, hs[2]).handle))
+        zps.append(h)
+    bufs = [L.cfd_zpart_buffer(z) for z in zps]
+    for r in range(P):
+        check(L.cfd_zpart_connect_ptr(zps[r], bufs[r - 1] if r > 0 else None, bufs[r + 1] if r < P - 1 else None))
+    assert L.cfd_zpart_connect_ptr(zps[0], bufs[1], bufs[1]) != 0        # rank 0 has no left neighbour
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    zz, yy, xx = smooth(shape)
+    try:
+        for it in range(5):
+            f = rng.random(shape) if it < 4 else 1e3 * (np.sin(zz) * np.cos(yy) + xx)
+            want = [O.derivative(f, a, hs[a]) for a in range(3)]
+            blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
+            outs = [[torch.empty_like(b) for _ in range(3)] for b in blocks]
+            torch.cuda.synchronize()
+            for r in range(P):
+                sp = ctypes.c_void_p(streams[r].cuda_stream)
+                if it % 2 == 0:
+                    if it == 2:                  # exchange begun early (on the rank's stream), then picked up
+                        check(L.cfd_zpart_begin(zps[r], blocks[r].data_ptr(), sp))
+                    check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs[r][2].data_ptr(), sp))
+                else:
+                    check(L.cfd_zpart_apply_xyz(zps[r], px.handle, py.handle, blocks[r].data_ptr(), outs[r][0].data_ptr(),
+                                                outs[r][1].data_ptr(), outs[r][2].data_ptr(), sp))
+            torch.cuda.synchronize()
+            assert L.cfd_async_status() == 0
+            gz = np.concatenate([o[2].cpu().numpy() for o in outs], axis=0)
+            assert relinf(gz, want[2]) <= TOL
+            if it % 2 == 1:
+                for a in (0, 1):
+                    ga = np.concatenate([o[a].cpu().numpy() for o in outs], axis=0)
+                    assert relinf(ga, want[a]) <= TOL
+                # same field again through the separate-launch path: bit-identical d/dz, and x / y == cfd_apply_xy
+                outs2 = [torch.empty_like(b) for b in blocks]
+                for r in range(P):
+                    sp = ctypes.c_void_p(streams[r].cuda_stream)
+                    check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs2[r].data_ptr(), sp))
+                torch.cuda.synchronize()
+                for r in range(P):
+                    assert torch.equal(outs2[r], outs[r][2])
+                    ex, ey = xy.dfdxy(blocks[r], hs[0], hs[1])
+                    assert torch.equal(ex, outs[r][0]) and torch.equal(ey, outs[r][1])
+    finally:
+        torch.cuda.synchronize()
+        for z in zps:
+            L.cfd_zpart_destroy(z)
+
+
+def test_zpart_rejects_bad_arguments(C):
+    import ctypes
+    from compact_finite_differences_b200._lib import CFD_EINVAL, CFD_EUNSUPPORTED, lib
+    L = lib()
+    h = ctypes.c_void_p()
+    whole = C.CompactFiniteDifferenceSolver((70, 8, 8), 0.1, 2)
+    assert L.cfd_zpart_create(ctypes.byref(h), whole._plan(2, 0.1).handle) == CFD_EINVAL          # part_size 1
+    thin = C.CompactFiniteDifferenceSolver((40, 8, 8), 0.1, 2, part=(0, 2))
+    assert L.cfd_zpart_create(ctypes.byref(h), thin._plan(2, 0.1).handle) == CFD_EUNSUPPORTED     # < 66 planes
+    xline = C.CompactFiniteDifferenceSolver((8, 8, 128), 0.1, 0, part=(0, 2))
+    assert L.cfd_zpart_create(ctypes.byref(h), xline._plan(0, 0.1).handle) == CFD_EUNSUPPORTED    # not a z line
+    ok = C.CompactFiniteDifferenceSolver((70, 8, 8), 0.1, 2, part=(0, 2))
+    assert L.cfd_zpart_create(ctypes.byref(h), ok._plan(2, 0.1).handle) == 0
+    f = dev(np.zeros((70, 8, 8)))
+    assert L.cfd_zpart_apply(h, f.data_ptr(), f.data_ptr() + 8, None) == CFD_EINVAL                # not connected
+    L.cfd_zpart_destroy(h)
+
+
+def test_flag_wait_times_out_instead_of_trapping(C):
+    """A rank that never arrives: the waiting kernel gives up after the configured time-out, the context survives and
+    the next status query reports CFD_ETIMEOUT (the round-1 kernels trapped after ~10 s)."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import CFD_ETIMEOUT, lib
+    L = lib()
+    C.CompactFiniteDifferenceSolver((70, 8, 8), 0.1, 2, part=(0, 2))._plan(2, 0.1)     # a partitioned plan: error word exists
+    flag = torch.zeros(2, dtype=torch.int64, device="cuda")
+    assert L.cfd_set_wait_timeout_ms(50) == 0
+    try:
+        assert L.cfd_wait_flags(flag.data_ptr(), None, 7, None) == 0
+        torch.cuda.synchronize()                     # returns: no trap, no hang
+        assert L.cfd_async_status() == CFD_ETIMEOUT
+        assert L.cfd_async_status() == 0             # reported once
+        flag[0] = 7
+        assert L.cfd_wait_flags(flag.data_ptr(), None, 7, None) == 0
+        torch.cuda.synchronize()
+        assert L.cfd_async_status() == 0
+    finally:
+        L.cfd_set_wait_timeout_ms(120000)
+
+
+def test_pinned_host_path(C):
+    """cfd_apply_host honours `pinned`: page-locked buffers take the slab-pipelined path (x, y) and give the same
+    numbers; a false promise is refused."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import CFD_EINVAL, lib
+    L = lib()
+    rng = np.random.default_rng(5)
+    shape = (21, 40, 64)
+    f = rng.random(shape)
+    fp = torch.from_numpy(f).pin_memory()
+    for axis in range(3):
+        op = C.CompactFiniteDifferenceSolver(shape, 0.1, axis)
+        plan = op._plan(axis, 0.1)
+        out = torch.empty(shape, dtype=torch.float64).pin_memory()
+        assert L.cfd_apply_host(plan.handle, fp.data_ptr(), out.data_ptr(), 1) == 0
+        assert relinf(out.numpy(), O.derivative(f, axis, 0.1)) <= TOL
+        plain = np.empty(shape)
+        assert L.cfd_apply_host(plan.handle, f.ctypes.data, plain.ctypes.data, 0) == 0
+        assert np.array_equal(plain, out.numpy())
+        assert L.cfd_apply_host(plan.handle, f.ctypes.data, plain.ctypes.data, 1) == CFD_EINVAL
+
+
+def test_graph_replay_beside_eager_launches(C):
+    """A captured launch owns its work counters: replaying the graph on one stream while thousands of eager launches
+    of the same plan run on another (enough to wrap the eager counter ring) never shares a counter pair."""
+    import torch
+    rng = np.random.default_rng(8)
+    shape = (24, 64, 96)
+    f = dev(rng.random(shape))
+    op = C.CompactFiniteDifferenceSolver(shape, 0.1, 1)
+    want = O.derivative(f.cpu().numpy(), 1, 0.1)
+    g_out, e_out = torch.empty_like(f), torch.empty_like(f)
+    op(f, g_out)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s1):
+        for _ in range(4):
+            op(f, g_out)
+    for _ in range(40):
+        with torch.cuda.stream(s1):
+            graph.replay()
+        with torch.cuda.stream(s2):
+            for _ in range(120):                 # 40 x 120 > 4096 eager launches: the ring wraps
+                op(f, e_out)
+    torch.cuda.synchronize()
+    assert relinf(g_out.cpu().numpy(), want) <= TOL and relinf(e_out.cpu().numpy(), want) <= TOL
+
+
+def test_pthomas_plan_is_reused(C):
+    import torch
+    rng = np.random.default_rng(2)
+    n = 12
+    a, b, c = rng.random(n), rng.random(n) + 2.0, rng.random(n)
+    rs = C.ReducedSolver((n, 3, 5))
+    for _ in range(3):
+        d = rng.random((n, 3, 5))
+        t = dev(d)
+        rs.solve(a, b, c, None, t)
+        np.testing.assert_allclose(t.cpu().numpy(), O.pthomas(a, b, c, d), rtol=1e-12)
+    assert len(rs._plans) == 1
+    rs.solve(a, b + 1.0, c, None, dev(rng.random((n, 3, 5))))
+    assert len(rs._plans) == 2
+
+
 def test_host_gradient_pipeline(C):
     """HostGradient (pinned host buffers, slab-pipelined copies) == oracle on every direction."""
     import torch

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/cfd_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert _lib.lib().cfd_version() == 100
+    assert _lib.lib().cfd_version() == 200
 
 
 def test_no_cpu_fallback():

@@ -225,7 +225,7 @@ def _worker_class(rank, world, port, ret):
             op.local_shape = (n, ny, nx)
             op.solver = _OracleBlockSolver(op.local_shape, h, rank, world)
             op.mode, op.comm = mode, comm
-            op._buf, op._side, op._pending, op._peer = None, None, None, None
+            op._buf, op._side, op._pending, op._zp = None, None, None, None
             got = op(slab).numpy()
             worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
         ret[rank] = worst
@@ -335,7 +335,7 @@ def _worker_grid(rank, world, port, proc_sizes, ret):
                 op.local_shape = local
                 op.solver = _OracleBlockSolver(local, h, r, sz, direction)
                 op.mode, op.comm = mode, comm
-                op._buf, op._side, op._pending, op._peer = None, None, None, None
+                op._buf, op._side, op._pending, op._zp = None, None, None, None
                 got = op(blk).numpy()
                 worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
         ret[rank] = worst
