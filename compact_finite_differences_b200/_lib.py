@@ -19,6 +19,8 @@ SIGNATURES = {
     "cfd_last_error": (ctypes.c_char_p, []),
     "cfd_create": (_i, [_pp, _i, _i, _i, _i, _d, _i, _i]),
     "cfd_destroy": (None, [_vp]),
+    "cfd_create_scheme": (_i, [_pp, _i, _i, _i, _i, _d, _i]),
+    "cfd_plan_lookahead": (_i, [_vp]),
     "cfd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_apply_xy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_plan_set_xy_warps": (_i, [_vp, _i]),
@@ -58,12 +60,15 @@ SIGNATURES = {
     "cfd_debug_tables": (_i, [_i, _dp, _d, _dp]),
     "cfd_debug_xy_order": (_l, [_i, _i, _i, _d, _i, ctypes.POINTER(_i), _l]),
     "cfd_debug_halo_weights": (_i, [_i, _d, _dp, _dp]),
+    "cfd_debug_lookahead": (_i, [_i, _dp]),
+    "cfd_debug_scheme": (_i, [_i, _i, _d, _dp]),
     "cfd_debug_secondary": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp, _dp]),
     "cfd_plan_secondary": (_i, [_vp, _dp, _dp, _dp, _dp, _dp]),
     "nt_create": (_i, [_pp, _i, _i, _i, _i, _dp]),
     "nt_solve": (_i, [_vp, _vp, _vp]),
     "nt_destroy": (None, [_vp]),
     "nt_is_exact_two_pass": (_i, [_vp]),
+    "nt_lookahead": (_i, [_vp]),
     "cfd_pthomas": (_i, [_dp, _dp, _dp, _vp, _i, _l, _vp]),
     "cfd_set_launch": (_i, [_i, _i, _i]),
     "cfd_set_segments": (_i, [_i]),

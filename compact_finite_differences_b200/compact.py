@@ -19,6 +19,9 @@ import numpy as np
 from ._lib import check, lib
 
 _AXIS_NAMES = {0: "x", 1: "y", 2: "z"}
+#: compact schemes of cfd_create_scheme (include/cfd_b200.h): the reference's 4th-order Pade first derivative, the
+#: 6th-order tridiagonal first derivative (two chunks of look-ahead), the 4th-order Pade SECOND derivative
+SCHEMES = {"pade4": 0, "compact6": 1, "pade4-d2": 2}
 
 
 def _stream_ptr(t):
@@ -29,11 +32,17 @@ def _stream_ptr(t):
 class _Plan:
     """Owns one cfd_plan (cfd_create / cfd_destroy)."""
 
-    def __init__(self, shape, axis, spacing, part_rank=0, part_size=1):
+    def __init__(self, shape, axis, spacing, part_rank=0, part_size=1, scheme="pade4"):
         nz, ny, nx = (int(s) for s in shape)
         self.handle = ctypes.c_void_p()
-        check(lib().cfd_create(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
-                               int(part_rank), int(part_size)))
+        if scheme == "pade4":
+            check(lib().cfd_create(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
+                                   int(part_rank), int(part_size)))
+        else:
+            assert int(part_size) == 1, "schemes other than 'pade4' serve unpartitioned lines"
+            check(lib().cfd_create_scheme(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
+                                          SCHEMES[scheme]))
+        self.scheme = scheme
         self.shape, self.axis, self.spacing = (nz, ny, nx), int(axis), float(spacing)
         self.part = (int(part_rank), int(part_size))
         self.plane_elems = lib().cfd_plane_elems(self.handle)
@@ -60,7 +69,7 @@ class LineDA:
 
 
 class CompactFiniteDifferenceSolver:
-    def __init__(self, shape, spacing=None, direction=None, part=(0, 1), solver=None):
+    def __init__(self, shape, spacing=None, direction=None, part=(0, 1), solver=None, scheme="pade4"):
         """
         Reference spelling: ``CompactFiniteDifferenceSolver(line_da, solver='templated')`` (code/cuda/compact.py:18)
         with any object carrying ``nz, ny, nx, rank, size`` (e.g. :class:`LineDA`); `solver` is accepted and
@@ -71,7 +80,11 @@ class CompactFiniteDifferenceSolver:
         :param direction: 0 = x, 1 = y, 2 = z (numbering of code/cuda/gpuDA.py:162)
         :param part: (rank, size) of this block along the derivative line -- the reference's
                      (line_da.rank, line_da.size), code/cuda/compact.py:159-166.  (0, 1) = whole line here.
+        :param scheme: "pade4" (the reference's scheme, default), "compact6" (6th-order first derivative) or
+                       "pade4-d2" (4th-order SECOND derivative: dfdx / dfdy / dfdz then return d2f/dx2 ...), see SCHEMES
         """
+        assert scheme in SCHEMES, f"scheme is one of {sorted(SCHEMES)}"
+        self.scheme = scheme
         self._group = None
         if hasattr(shape, "nz") and hasattr(shape, "rank"):            # a line_da of the reference
             da = shape
@@ -98,7 +111,7 @@ class CompactFiniteDifferenceSolver:
         key = (int(axis), float(spacing))
         p = self._plans.get(key)
         if p is None:
-            p = _Plan(self.shape, axis, spacing, *self.part)
+            p = _Plan(self.shape, axis, spacing, *self.part, scheme=self.scheme)
             self._plans[key] = p
         return p
 

@@ -14,9 +14,14 @@
 #include <string>
 #include <vector>
 
+#ifndef CFD_PDL_DEFAULT
+#define CFD_PDL_DEFAULT 0
+#endif
+#include <utility>
 #include "../../include/cfd_b200.h"
 #include "kernels.cuh"
 #include "kernels_xy.cuh"
+#include "kernels_general.cuh"
 
 using namespace cfd;
 
@@ -63,6 +68,36 @@ extern "C" int cfd_set_segments(int chunks_per_segment)
     if (chunks_per_segment < 0) return fail(CFD_EINVAL, "chunks_per_segment must be >= 0 (0 = automatic)");
     g_kseg = chunks_per_segment;
     return CFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel launch, optionally as a programmatic dependent launch (kernels.cuh pdl_wait): the streaming kernels, the
+// reduced-system kernels and the fused x/y kernel all park at pdl_wait() before their first global access, so a
+// launch may be scheduled while the previous kernel of the stream drains.  CFD_PDL=0 turns it off.
+// ------------------------------------------------------------------------------------------------
+static bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CFD_PDL"); v = e ? (atoi(e) != 0) : CFD_PDL_DEFAULT; }
+    return v != 0;
+}
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (pdl_enabled()) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -358,9 +393,8 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
     const long cap = (long)dinfo.sms * ctas;
     if (blocks > cap) blocks = cap;
     if (const char *e = getenv("CFD_CTAS")) { if (atol(e) >= 1 && atol(e) < blocks) blocks = atol(e); }    // experiment
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, kp);
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, kp));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return CFD_OK;
 }
 
@@ -391,6 +425,9 @@ struct cfd_plan {
     KParams kp;                       // host template (halo/out pointers filled per call)
     MapCache cache;
     PairPool pool;                    // work counters of this plan's CAPTURED launches (see counter_pair)
+    int scheme = 0;                   // CFD_SCHEME_*; schemes other than PADE4 run the general kernel
+    int la = 1;                       // look-ahead chunks of the general kernel
+    GParams gp;
     // multi-rank
     std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
     std::vector<double> lu_nb;        // neighbour-only reduced system (ranks r-1, r, r+1)
@@ -417,7 +454,9 @@ struct nt_plan {
     KParams kp;
     MapCache cache;
     PairPool pool;
-    bool exact = false;               // two-pass exact solver (matrix refused by the one-pass kernel)
+    bool exact = false;               // two-pass exact solver (matrix refused by the one-pass kernels)
+    int la = 0;                       // > 0: the general one-pass kernel with this many look-ahead chunks
+    GParams gp;
     double *d_tab = nullptr;          // [4][K*32]: forward pc, qc; backward pc, qc
     // Starved shape (long lines, fewer bundles than warps): the lines are cut into segments, which is only safe
     // out of place -- solve into this scratch field, then copy it back over d (both tiny by definition).
@@ -841,6 +880,185 @@ extern "C" int cfd_debug_tables(int n, const double coeffs[7], double scale, dou
     return CFD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// General one-pass kernel (kernels_general.cuh): look-ahead derived from the coefficients, compact schemes beyond Pade-4
+// ------------------------------------------------------------------------------------------------
+// Chunks of backward look-ahead a matrix needs so that the neglected coupling |g|^(32 LA) stays below fp64 round-off;
+// 0 = not served one-pass (pivots that do not converge by row 32, or a coupling weaker than 0.563 per row).
+static int lookahead_chunks(const Pivots &pv, int K)
+{
+    if (K <= 2) return 1;                                   // at most two chunks: every sweep starts at the true end
+    if (!pv.converged) return 0;
+    if (std::pow(pv.decay, CH) <= 1.2e-16) return 1;
+    if (std::pow(pv.decay, 2 * CH) <= 1.2e-16) return 2;
+    return 0;
+}
+
+static void fill_general(GParams &gp, const Geometry &g, const Pivots &pv, double scale)
+{
+    memset(&gp, 0, sizeof gp);
+    gp.n = g.n; gp.K = g.K; gp.jl = g.jl;
+    gp.inner = (int)g.inner; gp.inner_tiles = g.inner_tiles;
+    gp.nb = g.nb; gp.rows = g.nlines;
+    gp.head = chunk_table(pv, g.n, 0, scale);
+    gp.tail = chunk_table(pv, g.n, g.K - 1, scale);
+    gp.tail2 = chunk_table(pv, g.n, g.K >= 2 ? g.K - 2 : 0, scale);
+    if (g.K > 3) { gp.sk_mid = pv.beta[CH] * scale; gp.l_mid = pv.l[CH]; gp.g_mid = pv.g[CH]; }
+    gp.nspecial = 0;
+}
+
+template <bool CONTIG, bool STENCIL, int LA>
+static int launch_general_la(const Geometry &g, GParams gp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                             cudaStream_t stream, PairPool *pool)
+{
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
+    constexpr int per_warp = (3 + LA + 1) * SLOT_BYTES + 3 * 16;
+    int warps = g_warps ? g_warps : 4;
+    const int max_warps = (LA == 1) ? 5 : 4;
+    if (warps > max_warps) warps = max_warps;
+    const long per_sm = (g.nb + dinfo.sms - 1) / dinfo.sms;
+    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    const size_t smem = (size_t)warps * per_warp + 1024;
+    auto kern = stream_kernel_g<CONTIG, STENCIL, LA>;
+    static size_t configured[MAX_DEVICES] = {0};
+    int dev = 0;
+    { int rc = current_device(dev); if (rc) return rc; }
+    if (configured[dev] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_warps * per_warp + 1024));
+        configured[dev] = max_warps * per_warp + 1024;
+    }
+    int rc = counter_pair(&gp.counter, stream, pool);
+    if (rc) return rc;
+    long blocks = (g.nb + warps - 1) / warps;
+    if (blocks > dinfo.sms) blocks = dinfo.sms;
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, gp));
+    g_launches++;
+    return CFD_OK;
+}
+
+template <bool STENCIL>
+static int launch_general(const Geometry &g, const GParams &gp, int la, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                          cudaStream_t stream, PairPool *pool)
+{
+    if (g.contig) return la == 2 ? launch_general_la<true, STENCIL, 2>(g, gp, tm_in, tm_out, stream, pool)
+                                 : launch_general_la<true, STENCIL, 1>(g, gp, tm_in, tm_out, stream, pool);
+    return la == 2 ? launch_general_la<false, STENCIL, 2>(g, gp, tm_in, tm_out, stream, pool)
+                   : launch_general_la<false, STENCIL, 1>(g, gp, tm_in, tm_out, stream, pool);
+}
+
+// Compact schemes beyond the reference's (Lele, "Compact finite difference schemes with spectral-like resolution",
+// J. Comput. Phys. 103, 1992): matrix rows, interior stencil, closure rows.
+struct SchemeDef {
+    LineMatrix m;
+    double c0, c1, c2, sgn;
+    int nspecial, min_n;
+    double q[2][4], p[2][4];
+};
+
+static int make_scheme(int scheme, double h, SchemeDef &d)
+{
+    memset(&d, 0, sizeof d);
+    if (scheme == CFD_SCHEME_COMPACT6) {
+        // interior (eq. 2.1, alpha = 1/3): f'_{i-1}/3 + f'_i + f'_{i+1}/3 = 14/9 (f_{i+1} - f_{i-1}) / 2h + 1/9 (f_{i+2} - f_{i-2}) / 4h
+        // row 1 / n-2: the 4th-order Pade row  f'_{i-1}/4 + f'_i + f'_{i+1}/4 = 3/4 (f_{i+1} - f_{i-1}) / h
+        // row 0 / n-1: the 3rd-order closure  f'_0 + 2 f'_1 = (-5/2 f_0 + 2 f_1 + 1/2 f_2) / h   (eq. 4.1.4; the reference's closure)
+        d.m = {1.0, 2.0, 1.0 / 3, 1.0, 1.0 / 3, 2.0, 1.0, true, 0.25, 1.0, 0.25, 0.25, 1.0, 0.25};
+        d.c0 = 0.0; d.c1 = 14.0 / 9 / (2 * h); d.c2 = 1.0 / 9 / (4 * h); d.sgn = -1.0;
+        d.nspecial = 2; d.min_n = 6;
+        const double q0[4] = {-2.5 / h, 2.0 / h, 0.5 / h, 0.0}, q1[4] = {-0.75 / h, 0.0, 0.75 / h, 0.0};
+        for (int k = 0; k < 4; k++) { d.q[0][k] = q0[k]; d.q[1][k] = q1[k]; d.p[0][k] = -q0[k]; }
+        d.p[1][0] = 0.75 / h; d.p[1][1] = 0.0; d.p[1][2] = -0.75 / h; d.p[1][3] = 0.0;     // 3/4 (f_{n-1} - f_{n-3}) / h
+        return CFD_OK;
+    }
+    if (scheme == CFD_SCHEME_PADE4_D2) {
+        // interior (eq. 2.2, alpha = 1/10): f''_{i-1}/10 + f''_i + f''_{i+1}/10 = 6/5 (f_{i+1} - 2 f_i + f_{i-1}) / h^2
+        // row 0 / n-1 (eq. 4.3.4, 3rd order): f''_0 + 11 f''_1 = (13 f_0 - 27 f_1 + 15 f_2 - f_3) / h^2
+        const double ih2 = 1.0 / (h * h);
+        d.m = {1.0, 11.0, 0.1, 1.0, 0.1, 11.0, 1.0, false, 0, 0, 0, 0, 0, 0};
+        d.c0 = -2.4 * ih2; d.c1 = 1.2 * ih2; d.c2 = 0.0; d.sgn = 1.0;
+        d.nspecial = 1; d.min_n = 5;
+        const double q0[4] = {13.0 * ih2, -27.0 * ih2, 15.0 * ih2, -1.0 * ih2};
+        for (int k = 0; k < 4; k++) { d.q[0][k] = q0[k]; d.p[0][k] = q0[k]; }
+        return CFD_OK;
+    }
+    return fail(CFD_EINVAL, "unknown scheme %d", scheme);
+}
+
+extern "C" int cfd_create_scheme(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int scheme)
+{
+    if (scheme == CFD_SCHEME_PADE4) return cfd_create(out, nz, ny, nx, axis, h, 0, 1);
+    if (!out) return fail(CFD_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    if (!(h > 0.0) || !std::isfinite(h)) return fail(CFD_EINVAL, "spacing h = %g must be positive", h);
+    SchemeDef d;
+    int rc = make_scheme(scheme, h, d);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CFD_ECUDA, "no CUDA device: libcfd_b200 has no CPU path");
+    }
+    cfd_plan *p = new cfd_plan();
+    rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (!rc && p->g.n < d.min_n) rc = fail(CFD_EINVAL, "extent along axis %d is %d; scheme %d needs >= %d", axis, p->g.n, scheme, d.min_n);
+    if (!rc) rc = ensure_counters();
+    if (rc) { delete p; return rc; }
+    p->h = h; p->rank = 0; p->size = 1; p->scheme = scheme;
+    const Pivots pv = build_pivots(p->g.n, d.m);
+    if (!pv.finite) { delete p; return fail(CFD_EINVAL, "internal: zero pivot in scheme %d", scheme); }
+    p->la = lookahead_chunks(pv, p->g.K);
+    if (p->la == 0) { delete p; return fail(CFD_EUNSUPPORTED, "internal: scheme %d is not diagonally dominant enough", scheme); }
+    fill_general(p->gp, p->g, pv, 1.0);
+    p->gp.c0 = d.c0; p->gp.c1 = d.c1; p->gp.c2 = d.c2; p->gp.sgn = d.sgn; p->gp.nspecial = d.nspecial;
+    memcpy(p->gp.q, d.q, sizeof d.q);
+    memcpy(p->gp.p, d.p, sizeof d.p);
+    memset(&p->kp, 0, sizeof p->kp);
+    p->kp.lo_closure = p->kp.hi_closure = 1;
+    *out = p;
+    return CFD_OK;
+}
+
+extern "C" int cfd_plan_lookahead(const cfd_plan *p) { return p ? p->la : 0; }
+
+// Host-only inspection (no device): look-ahead chunks for a line of n rows of the matrix coeffs, and the definition
+// of a scheme: out[0..6] = b1,c1,ai,bi,ci,an,bn; [7] = two special rows per end; [8..13] = a2,b2,c2,am,bm,cm;
+// [14..18] = c0,c1,c2,sgn,closure rows per end; [19..26] = q[2][4]; [27..34] = p[2][4]; [35] = look-ahead chunks for n
+// rows; [36] = interior coupling per row.
+extern "C" int cfd_debug_lookahead(int n, const double coeffs[7])
+{
+    if (n < 3 || !coeffs) return fail(CFD_EINVAL, "bad argument");
+    const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
+    const Pivots pv = build_pivots(n, as_matrix(m));
+    if (!pv.finite) return fail(CFD_EINVAL, "zero pivot");
+    return lookahead_chunks(pv, (n + CH - 1) / CH);
+}
+
+extern "C" int cfd_debug_scheme(int scheme, int n, double h, double *out)
+{
+    if (!out || n < 6 || !(h > 0.0)) return fail(CFD_EINVAL, "bad argument");
+    SchemeDef d;
+    if (scheme == CFD_SCHEME_PADE4) {
+        memset(&d, 0, sizeof d);
+        d.m = as_matrix(pade_block(0, 1));
+        d.c1 = 3.0 / (4.0 * h); d.sgn = -1.0; d.nspecial = 1;
+        const double q0[4] = {-2.5 / h, 2.0 / h, 0.5 / h, 0.0};
+        for (int k = 0; k < 4; k++) { d.q[0][k] = q0[k]; d.p[0][k] = -q0[k]; }
+    } else {
+        int rc = make_scheme(scheme, h, d);
+        if (rc) return rc;
+    }
+    const double v[19] = {d.m.b1, d.m.c1, d.m.ai, d.m.bi, d.m.ci, d.m.an, d.m.bn, d.m.two ? 1.0 : 0.0, d.m.a2, d.m.b2, d.m.c2,
+                          d.m.am, d.m.bm, d.m.cm, d.c0, d.c1, d.c2, d.sgn, (double)d.nspecial};
+    memcpy(out, v, sizeof v);
+    memcpy(out + 19, d.q, sizeof d.q);
+    memcpy(out + 27, d.p, sizeof d.p);
+    const Pivots pv = build_pivots(n, d.m);
+    out[35] = lookahead_chunks(pv, (n + CH - 1) / CH);
+    out[36] = pv.decay;
+    return CFD_OK;
+}
+
 static int get_maps(MapCache &c, const Geometry &g, const void *in, const void *out, MapPair &m)
 {
     std::lock_guard<std::mutex> lock(c.mu);
@@ -866,6 +1084,8 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     MapPair mp;
     int rc = get_maps(p->cache, p->g, f, df, mp);
     if (rc) return rc;
+    if (p->scheme != CFD_SCHEME_PADE4)
+        return launch_general<true>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
     // Experiment switch (CFD_RING_STAGING=1): whole, unpartitioned lines through the ring-staged kernel of
     // kernels_xy.cuh with one direction empty -- 32 KiB per warp, 6 warps per SM instead of 40 KiB and 4.
     if (p->size == 1 && !ab && getenv("CFD_RING_STAGING")) return launch_one_direction_ring(p, mp, (cudaStream_t)stream);
@@ -899,11 +1119,11 @@ extern "C" int cfd_reduced_unknowns(cfd_plan *p, const double *faces, int neighb
     if (neighbours_only && p->g.n < 2 * CH)
         return fail(CFD_EUNSUPPORTED, "neighbour-only coupling needs >= %d rows per block", 2 * CH);
     const int bs = 256;
-    reduced_planes_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
-        faces, neighbours_only ? p->d_lu_nb : p->d_lu, p->g.nlines, neighbours_only ? p->nb_pv : p->size,
-        neighbours_only ? p->nb_own : p->rank, ab, flag0, flag1, seq, wait_params());
+    CUDA_TRY(launch_k(reduced_planes_kernel, (unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream,
+                      faces, (const double *)(neighbours_only ? p->d_lu_nb : p->d_lu), p->g.nlines,
+                      neighbours_only ? p->nb_pv : p->size, neighbours_only ? p->nb_own : p->rank, ab, flag0, flag1, seq,
+                      wait_params()));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return CFD_OK;
 }
 
@@ -982,10 +1202,9 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
         } else if (atol(e) >= 1 && atol(e) <= blocks) blocks = atol(e);
     }
     static const EdgeX no_edge = {};
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q,
-                                                         tmz ? *tmz : mx.tm_in, edge ? *edge : no_edge);
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, mx.tm_in, mx.tm_out, my.tm_in, my.tm_out, kx, ky, q,
+                      tmz ? *tmz : mx.tm_in, edge ? *edge : no_edge));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return CFD_OK;
 }
 
@@ -1053,6 +1272,10 @@ extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double 
     if (px->g.nz != py->g.nz || px->g.ny != py->g.ny || px->g.nx != py->g.nx)
         return fail(CFD_EINVAL, "plans are for different shapes");
     if (px->size != 1 || py->size != 1) return fail(CFD_EINVAL, "cfd_apply_xy serves unpartitioned x / y lines");
+    if (px->scheme != CFD_SCHEME_PADE4 || py->scheme != CFD_SCHEME_PADE4) {     // other schemes: one launch each
+        int rc2 = cfd_apply(px, f, dfdx, nullptr, nullptr, stream);
+        return rc2 ? rc2 : cfd_apply(py, f, dfdy, nullptr, nullptr, stream);
+    }
     if (f == dfdx || f == dfdy || dfdx == dfdy) return fail(CFD_EINVAL, "f, dfdx, dfdy must be three different fields");
     const long nitems = (long)px->g.nz * (px->g.ny / CH + py->g.inner_tiles);
     if (!xy_eligible(px->g) || getenv("CFD_NO_XY")) {
@@ -1134,11 +1357,10 @@ extern "C" int cfd_reduced_unknowns_deferred(cfd_plan *p, const double *faces_nb
     if ((p->rank > 0) != (halo_lo != nullptr) || (p->rank < p->size - 1) != (halo_hi != nullptr))
         return fail(CFD_EINVAL, "rank %d of %d: halo_lo / halo_hi must be given exactly where a neighbour exists", p->rank, p->size);
     const int bs = 256;
-    reduced_planes_deferred_kernel<<<(unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
-        faces_nb, p->d_lu_nb, p->g.nlines, p->nb_pv, p->nb_own, ab, halo_lo, halo_hi, f, p->g.inner, p->g.n,
-        p->w_lo, p->w_hi, flag0, flag1, seq, wait_params());
+    CUDA_TRY(launch_k(reduced_planes_deferred_kernel, (unsigned)((p->g.nlines + bs - 1) / bs), bs, 0, (cudaStream_t)stream,
+                      faces_nb, (const double *)p->d_lu_nb, p->g.nlines, p->nb_pv, p->nb_own, ab, halo_lo, halo_hi, f,
+                      p->g.inner, p->g.n, p->w_lo, p->w_hi, flag0, flag1, seq, wait_params()));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return CFD_OK;
 }
 
@@ -1181,6 +1403,7 @@ extern "C" int cfd_compute_rhs(cfd_plan *p, const double *f, double *rhs, const 
                                void *stream)
 {
     if (!p || !f || !rhs) return fail(CFD_EINVAL, "NULL argument");
+    if (p->scheme != CFD_SCHEME_PADE4) return fail(CFD_EUNSUPPORTED, "the stage entry points serve the reference's Pade-4 scheme");
     if (f == rhs) return fail(CFD_EINVAL, "the right-hand side is computed out of place");
     if (!p->kp.lo_closure && !halo_lo) return fail(CFD_EINVAL, "rank %d of %d needs halo_lo", p->rank, p->size);
     if (!p->kp.hi_closure && !halo_hi) return fail(CFD_EINVAL, "rank %d of %d needs halo_hi", p->rank, p->size);
@@ -1211,6 +1434,7 @@ extern "C" int cfd_sum_solutions(cfd_plan *p, double *x, const double *alpha, co
 extern "C" int cfd_plan_coeffs(const cfd_plan *p, double coeffs[7])
 {
     if (!p || !coeffs) return fail(CFD_EINVAL, "NULL argument");
+    if (p->scheme != CFD_SCHEME_PADE4) return fail(CFD_EUNSUPPORTED, "the stage entry points serve the reference's Pade-4 scheme");
     const LineCoeffs m = pade_block(p->rank, p->size);
     coeffs[0] = m.b1; coeffs[1] = m.c1; coeffs[2] = m.ai; coeffs[3] = m.bi; coeffs[4] = m.ci; coeffs[5] = m.an;
     coeffs[6] = m.bn;
@@ -1272,7 +1496,7 @@ extern "C" int cfd_apply_host(cfd_plan *p, const double *f_host, double *df_host
     // Lines along x or y never leave a z-slab: with page-locked buffers the field moves in slabs, so that slab s+1
     // travels host -> device while slab s is differentiated and slab s-1 travels back (PCIe is full duplex).  Pageable
     // buffers (and z lines, which need the whole field) take the plain copy - kernel - copy sequence.
-    const int slabs = (pinned && p->g.axis != 2 && p->g.nz >= 8) ? 4 : 1;
+    const int slabs = (pinned && p->g.axis != 2 && p->g.nz >= 8 && p->scheme == CFD_SCHEME_PADE4) ? 4 : 1;
     if (slabs == 1) {
         CUDA_TRY(cudaMemcpyAsync(p->d_f, f_host, bytes, cudaMemcpyHostToDevice, p->hstream));
         int rc = cfd_apply(p, p->d_f, p->d_df, nullptr, nullptr, p->hstream);
@@ -1342,9 +1566,8 @@ static int launch_recurrence(const Geometry &g, const double *pc, const double *
     if (rc) return rc;
     long blocks = (g.nb + warps - 1) / warps;
     if (blocks > dinfo.sms) blocks = dinfo.sms;
-    kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_in, tm_out, rp);
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, rp));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return CFD_OK;
 }
 
@@ -1365,6 +1588,20 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
     if (rc) { delete p; return rc; }
     const LineCoeffs m = {coeffs[0], coeffs[1], coeffs[2], coeffs[3], coeffs[4], coeffs[5], coeffs[6]};
     rc = fill_tables(p->kp, p->g, m, 1.0, true);
+    if (rc == CFD_ESLOWPATH) {
+        // Coupling too weak for one chunk of look-ahead.  Two chunks (|g|^64 below round-off: e.g. the 6th-order
+        // scheme, alpha = 1/3) keep the solve one-pass in the general kernel; anything weaker takes the exact two-pass LU.
+        const Pivots pg = build_pivots(p->g.n, as_matrix(m));
+        const int la = pg.finite ? lookahead_chunks(pg, p->g.K) : 0;
+        if (la == 2 && !getenv("CFD_NO_LA2")) {
+            fill_general(p->gp, p->g, pg, 1.0);
+            p->la = 2;
+            g_err.clear();
+            p->kp.lo_closure = 1; p->kp.hi_closure = 1;
+            *out = p;
+            return CFD_OK;
+        }
+    }
     if (rc == CFD_ESLOWPATH) {
         // exact two-pass LU: per-row tables on the device
         Pivots pv = build_pivots(p->g.n, m);
@@ -1400,6 +1637,7 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
 }
 
 extern "C" int nt_is_exact_two_pass(const nt_plan *p) { return p ? (p->exact ? 1 : 0) : 0; }
+extern "C" int nt_lookahead(const nt_plan *p) { return p ? (p->exact ? 0 : (p->la > 0 ? p->la : 1)) : 0; }
 
 extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
 {
@@ -1407,6 +1645,7 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
     MapPair mp;
     int rc = get_maps(p->cache, p->g, d, d, mp);
     if (rc) return rc;
+    if (p->la > 0) return launch_general<false>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
     if (p->exact) {
         const long L = (long)p->g.K * CH;
         const double *t = p->d_tab;

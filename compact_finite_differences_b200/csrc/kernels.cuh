@@ -134,6 +134,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still draining; it must not touch global memory before pdl_wait()
+// (everything in front of it -- shared-memory carve-up, mbarrier init -- overlaps the predecessor's tail and the launch
+// latency).  Both instructions are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -345,6 +352,8 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
         fence_mbar_init();
     }
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();
 
     // A work item is (bundle, segment): output chunks [c0, c1) of the bundle's lines.  Its tile sequence runs
     // from chunk max(c0-1, 0) -- a 32-row forward warm-up from a zero state, exact to 0.268^32 like the backward
@@ -591,6 +600,8 @@ recurrence_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         fence_mbar_init();
     }
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();
 
     long ib = 0;
     int ik = 0, islot = 0;
@@ -757,6 +768,8 @@ reduced_planes_kernel(const double *faces, const double *__restrict__ lu, long n
                       unsigned long long seq, WaitP wp)
 {
     // `faces` is peer-written while this kernel runs (no __restrict__, no const-cache loads: peer_ld)
+    pdl_launch_dependents();
+    pdl_wait();
     if (flag0 || flag1) {
         if (threadIdx.x == 0) {
             if (flag0) wait_flag(flag0, seq, wp);
@@ -787,6 +800,8 @@ reduced_planes_deferred_kernel(const double *faces, const double *__restrict__ l
                                const unsigned long long *flag1, unsigned long long seq, WaitP wp)
 {
     // faces / halo_lo / halo_hi are peer-written while this kernel runs: no __restrict__, loads through peer_ld
+    pdl_launch_dependents();
+    pdl_wait();
     if (flag0 || flag1) {
         if (threadIdx.x == 0) {
             if (flag0) wait_flag(flag0, seq, wp);

@@ -1,0 +1,277 @@
+// kernels_general.cuh -- the one-pass streaming solve for everything the Pade-4 fast path (kernels.cuh) does not cover:
+//
+//   * WIDER LOOK-AHEAD.  The backward sweep of a chunk is started LA chunks to the right; the neglected coupling is
+//     |g|^(32 LA).  LA = 1 needs |g| <= 0.316 (the reference's Pade matrix: 0.268); LA = 2 serves |g| <= 0.563, e.g. the
+//     6th-order tridiagonal scheme (alpha = 1/3, |g| = 0.382: 0.382^64 = 2e-27) -- still read-once / write-once, where
+//     round 1 fell back to the exact two-pass kernel (32 B / unknown).  The look-ahead width is derived from the
+//     coefficients on the host (api.cu lookahead_chunks).
+//   * GENERAL RIGHT-HAND SIDES.  r_i = c0 f_i + c1 (f_{i+1} + s f_{i-1}) + c2 (f_{i+2} + s f_{i-2}) in the interior
+//     (s = -1: first derivatives, s = +1: second derivatives), up to two closure rows per end with 4-point one-sided
+//     stencils, and a matrix whose first two and last two rows may differ from the Toeplitz interior.  Serves the
+//     6th-order first derivative and the 4th-order second derivative; the reference solver's general
+//     [b1, c1, ai, bi, ci, an, bn] matrices are the STENCIL = false case (right-hand side = the tile itself).
+//
+// Same warp-autonomous TMA ring, dynamic bundle draw and TMA stores as stream_kernel.  What differs: the forward
+// values e of the LA chunks that wait for their backward sweep live in SHARED memory (LA + 1 slots per warp, in the
+// tile layout), not in registers -- two chunks of look-ahead would need 96 doubles per lane -- and the result of a chunk
+// is written over its e values in place and leaves by TMA from that slot.  Whole lines only (no segmentation).
+#pragma once
+#include "kernels.cuh"
+
+namespace cfd {
+
+struct GParams {
+    int n, K, jl;
+    int inner, inner_tiles;
+    long nb, rows;
+    unsigned long long *counter;
+    // matrix: per-row tables for the first chunk and the last TWO chunks (a special row n-2 can fall into chunk K-2),
+    // constants in between.  sk multiplies the right-hand side (beta_i, times the caller's scale for STENCIL = false).
+    double sk_mid, l_mid, g_mid;
+    RowTab head, tail2, tail;
+    // right-hand side stencil (STENCIL = true)
+    double c0, c1, c2, sgn;
+    int nspecial;                 // closure rows per end: 1 or 2
+    double q[2][4];               // row 0, row 1:     r = sum_k q[.][k] f[k]
+    double p[2][4];               // row n-1, row n-2: r = sum_k p[.][k] f[n-1-k]
+};
+
+template <bool CONTIG>
+__device__ __forceinline__ void store_chunk(unsigned char *slot, int lane, const double (&E)[CH])
+{
+    if constexpr (CONTIG) {
+        unsigned char *row = slot + lane * 128;
+        const int sw = (lane & 7) << 4;
+#pragma unroll
+        for (int m = 0; m < 16; m++)
+            *reinterpret_cast<double2 *>(row + (m >> 3) * 4096 + (((m & 7) << 4) ^ sw)) = make_double2(E[2 * m], E[2 * m + 1]);
+    } else {
+        double *col = reinterpret_cast<double *>(slot) + lane;
+#pragma unroll
+        for (int j = 0; j < CH; j++) col[j * CH] = E[j];
+    }
+}
+
+template <bool CONTIG>
+__device__ __forceinline__ double load_row(const unsigned char *slot, int lane, int r)   // r = 0 or 1
+{
+    if constexpr (CONTIG) return *reinterpret_cast<const double *>(slot + lane * 128 + ((lane & 7) << 4) + 8 * r);
+    else return reinterpret_cast<const double *>(slot)[r * CH + lane];
+}
+
+// Forward elimination of chunk k.  TAB: 0 = constants, 1 = table chunk (head / tail2 / tail; rows located at run time).
+// History: h1, h2, h3 = f[i-1], f[i-2], f[i-3] on entry; pk0, pk1 = first two rows of the next tile (0 past the end).
+template <bool STENCIL, int TAB>
+__device__ __forceinline__ void gfwd_chunk(const GParams &p, const RowTab *T, int k, const double (&F)[CH], double pk0,
+                                           double pk1, double (&e)[CH], double &eprev, double &h1, double &h2, double &h3)
+{
+    const int n = p.n;
+    const int row0 = k * CH;
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        double r;
+        if constexpr (STENCIL) {
+            const double a1 = (j >= 1) ? F[j - 1] : h1, a2 = (j >= 2) ? F[j - 2] : (j == 1 ? h1 : h2);
+            const double b1 = (j < CH - 1) ? F[j + 1] : pk0, b2 = (j < CH - 2) ? F[j + 2] : (j == CH - 2 ? pk0 : pk1);
+            r = fma(p.c2, fma(p.sgn, a2, b2), fma(p.c1, fma(p.sgn, a1, b1), p.c0 * F[j]));
+            if constexpr (TAB == 1) {
+                const int row = row0 + j;
+                if (k == 0 && j < 2 && j < p.nspecial) {          // closure rows 0 (, 1): forward one-sided, inside chunk 0
+                    r = fma(p.q[j][3], F[3], fma(p.q[j][2], F[2], fma(p.q[j][1], F[1], p.q[j][0] * F[0])));
+                }
+                const int back = n - 1 - row;                     // 0: row n-1, 1: row n-2
+                if (back >= 0 && back < p.nspecial) {
+                    // f[n-1], f[n-2], f[n-3], f[n-4] relative to this row
+                    const double a3 = (j >= 3) ? F[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+                    if (back == 0) r = fma(p.p[0][3], a3, fma(p.p[0][2], a2, fma(p.p[0][1], a1, p.p[0][0] * F[j])));
+                    else           r = fma(p.p[1][3], a2, fma(p.p[1][2], a1, fma(p.p[1][1], F[j], p.p[1][0] * b1)));
+                }
+            }
+        } else {
+            r = F[j];
+        }
+        if constexpr (TAB == 1) eprev = fma(-T->l[j], eprev, T->sk[j] * r);
+        else                    eprev = fma(-p.l_mid, eprev, p.sk_mid * r);
+        e[j] = eprev;
+    }
+    if constexpr (STENCIL) { h3 = F[CH - 3]; h2 = F[CH - 2]; h1 = F[CH - 1]; }
+}
+
+// Backward sweep over one chunk held in registers; OUT writes x over the values of `slot` (tile layout).
+template <bool CONTIG, int TAB, bool OUT>
+__device__ __forceinline__ void gbwd_chunk(const GParams &p, const RowTab *T, const double (&e)[CH], double &x,
+                                           unsigned char *slot, int lane)
+{
+    double X[CH];
+#pragma unroll
+    for (int j = CH - 1; j >= 0; j--) {
+        const double ng = (TAB == 1) ? -T->g[j] : -p.g_mid;
+        x = fma(ng, x, e[j]);
+        X[j] = x;
+    }
+    if constexpr (OUT) store_chunk<CONTIG>(slot, lane, X);
+}
+
+template <bool CONTIG, bool STENCIL, int LA>
+__global__ void __launch_bounds__(160, 1)
+stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                const __grid_constant__ GParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int NS = 3, NE = LA + 1;
+    constexpr int PER_WARP = (NS + NE) * SLOT_BYTES;
+    constexpr int CTRL = NS * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *wbase = base + warp * PER_WARP;
+    unsigned char *ebase = wbase + NS * SLOT_BYTES;
+    unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
+    const uint32_t bar0 = smem_u32(ctrl);
+    volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
+    const int K = p.K;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();
+
+    long ib = 0;
+    int ik = 0, islot = 0;
+    bool dry = false;
+    auto issue = [&]() {
+        if (ik == 0 && !dry) {
+            ib = (long)atomicAdd(p.counter, 1ULL);
+            dry = ib >= p.nb;
+        }
+        if (dry) {
+            tag[islot] = -1;
+        } else {
+            tag[islot] = ib;
+            const uint32_t bar = bar0 + 8 * islot;
+            const uint32_t dst = smem_u32(wbase + islot * SLOT_BYTES);
+            mbar_expect_tx(bar, SLOT_BYTES);
+            if constexpr (CONTIG) {
+                tma_load_2d(dst, &tm_in, bar, ik * CH, (int)(ib * CH));
+                tma_load_2d(dst + 4096, &tm_in, bar, ik * CH + 16, (int)(ib * CH));
+            } else {
+                tma_load_3d(dst, &tm_in, bar, (int)(ib % p.inner_tiles) * CH, ik * CH, (int)(ib / p.inner_tiles));
+            }
+            if (++ik == K) ik = 0;
+        }
+        if (++islot == NS) islot = 0;
+    };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NS; s++) issue();
+    }
+    __syncwarp();
+
+    auto table_of = [&](int c) -> const RowTab * {            // nullptr = constants
+        if (c == 0) return &p.head;
+        if (c == K - 1) return &p.tail;
+        if (c == K - 2) return &p.tail2;
+        return nullptr;
+    };
+    auto ship = [&](int c, long b, unsigned char *slot) {     // TMA store of result chunk c from its slot
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            if constexpr (CONTIG) {
+                tma_store_2d(&tm_out, smem_u32(slot), c * CH, (int)(b * CH));
+                tma_store_2d(&tm_out, smem_u32(slot) + 4096, c * CH + 16, (int)(b * CH));
+            } else {
+                tma_store_3d(&tm_out, smem_u32(slot), (int)(b % p.inner_tiles) * CH, c * CH, (int)(b / p.inner_tiles));
+            }
+            tma_commit();
+        }
+    };
+    // sweep x through the e values of chunk c held in its shared-memory slot; OUT: results over them, then shipped
+    auto sweep_slot = [&](int c, long b, double &x, bool out) {
+        unsigned char *slot = ebase + (c % NE) * SLOT_BYTES;
+        double E[CH];
+        load_chunk<CONTIG>(slot, lane, E);
+        const RowTab *T = table_of(c);
+        if (out) {
+            if (T) gbwd_chunk<CONTIG, 1, true>(p, T, E, x, slot, lane);
+            else   gbwd_chunk<CONTIG, 0, true>(p, T, E, x, slot, lane);
+            ship(c, b, slot);
+        } else {
+            if (T) gbwd_chunk<CONTIG, 1, false>(p, T, E, x, slot, lane);
+            else   gbwd_chunk<CONTIG, 0, false>(p, T, E, x, slot, lane);
+        }
+    };
+
+    double F[CH], e[CH];
+    double eprev = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+    long b = 0;
+    int k = 0, slot = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        if (k == 0) {
+            b = tag[slot];
+            if (b < 0) break;
+            eprev = 0.0; h1 = 0.0; h2 = 0.0; h3 = 0.0;
+        }
+        const bool last = (k == K - 1);
+        mbar_wait(bar0 + 8 * slot, phase);
+        load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
+        double pk0 = 0.0, pk1 = 0.0;
+        if constexpr (STENCIL) {
+            if (!last) {
+                const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
+                const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;
+                mbar_wait(bar0 + 8 * s1, ph1);
+                pk0 = load_row<CONTIG>(wbase + s1 * SLOT_BYTES, lane, 0);
+                pk1 = load_row<CONTIG>(wbase + s1 * SLOT_BYTES, lane, 1);
+            }
+        }
+        const RowTab *T = table_of(k);
+        if (T) gfwd_chunk<STENCIL, 1>(p, T, k, F, pk0, pk1, e, eprev, h1, h2, h3);
+        else   gfwd_chunk<STENCIL, 0>(p, T, k, F, pk0, pk1, e, eprev, h1, h2, h3);
+        __syncwarp();
+        if (lane == 0) issue();
+        __syncwarp();
+
+        // the slot e(k) goes to was shipped LA + 1 steps ago: its TMA store must have finished reading it
+        if (lane == 0) tma_wait_read0();
+        __syncwarp();
+        unsigned char *eslot = ebase + (k % NE) * SLOT_BYTES;
+        double x = 0.0;
+        if (last) {                                   // exact sweep from the true end of the line
+            if (T) gbwd_chunk<CONTIG, 1, true>(p, T, e, x, eslot, lane);
+            else   gbwd_chunk<CONTIG, 0, true>(p, T, e, x, eslot, lane);
+            ship(k, b, eslot);
+#pragma unroll 1
+            for (int c = k - 1; c >= 0 && c >= k - LA; c--) sweep_slot(c, b, x, true);
+        } else {
+            if (k >= LA) {                            // a result chunk follows: warm the sweep up through chunk k
+                if (T) gbwd_chunk<CONTIG, 1, false>(p, T, e, x, eslot, lane);
+                else   gbwd_chunk<CONTIG, 0, false>(p, T, e, x, eslot, lane);
+            }
+            store_chunk<CONTIG>(eslot, lane, e);
+            __syncwarp();
+            if (k >= LA) {
+                if constexpr (LA == 2) sweep_slot(k - 1, b, x, false);          // ... and through chunk k-1
+                sweep_slot(k - LA, b, x, true);
+            }
+        }
+        if (++k == K) k = 0;
+        if (++slot == NS) { slot = 0; phase ^= 1u; }
+    }
+    if (lane == 0) {
+        tma_wait_all0();
+        __threadfence();
+        const unsigned long long total = (unsigned long long)gridDim.x * nwarps;
+        if (atomicAdd(p.counter + 1, 1ULL) == total - 1) {
+            p.counter[0] = 0ULL;
+            p.counter[1] = 0ULL;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace cfd

@@ -229,6 +229,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         fence_mbar_init();
     }
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();
 
     // draw-table entry -> (direction, bundle, plane, tile range)
     // (edge items, EDGE only: entries beyond the nz * ipp x / y items; b = edge item, tiles 0 .. ke)

@@ -29,6 +29,24 @@ struct RowTab {          // 768 B
 
 struct LineCoeffs { double b1, c1, ai, bi, ci, an, bn; };
 
+// Near-Toeplitz matrix whose first TWO and last TWO rows may differ from the interior (higher-order compact schemes
+// drop to a lower-order scheme next to the closure rows):
+//   row 0: (b1, c1)   row 1: (a2, b2, c2)   interior: (ai, bi, ci)   row n-2: (am, bm, cm)   row n-1: (an, bn)
+struct LineMatrix {
+    double b1, c1, ai, bi, ci, an, bn;
+    bool two;
+    double a2, b2, c2, am, bm, cm;
+    double a(int i, int n) const { return i == 0 ? 0.0 : i == n - 1 ? an : (two && i == 1) ? a2 : (two && i == n - 2) ? am : ai; }
+    double b(int i, int n) const { return i == 0 ? b1 : i == n - 1 ? bn : (two && i == 1) ? b2 : (two && i == n - 2) ? bm : bi; }
+    double c(int i, int n) const { return i == 0 ? c1 : i == n - 1 ? 0.0 : (two && i == 1) ? c2 : (two && i == n - 2) ? cm : ci; }
+};
+
+inline LineMatrix as_matrix(const LineCoeffs &m)
+{
+    LineMatrix g = {m.b1, m.c1, m.ai, m.bi, m.ci, m.an, m.bn, false, 0, 0, 0, 0, 0, 0};
+    return g;
+}
+
 struct Pivots {
     std::vector<double> beta, l, g;
     double decay = 0;        // |g| in the converged region: backward coupling per row
@@ -61,6 +79,34 @@ inline Pivots build_pivots(int n, const LineCoeffs &m)
         for (int i = CH; i < n - 1; i++)
             if (std::fabs(p.beta[i] - ref) > 4e-16 * std::fabs(ref)) { p.converged = false; break; }
         p.decay = std::fabs(p.g[CH]);
+    }
+    return p;
+}
+
+// The same elimination for a LineMatrix.  `decay` / `converged` look at rows [CH, n-2): the rows the kernels serve with
+// constants (rows n-2 and n-1 always come from a per-row table).
+inline Pivots build_pivots(int n, const LineMatrix &m)
+{
+    Pivots p;
+    p.beta.resize(n); p.l.resize(n); p.g.resize(n);
+    p.beta[0] = 1.0 / m.b(0, n);
+    p.l[0] = 0.0;
+    for (int i = 1; i < n; i++) {
+        const double gam = p.beta[i - 1] * m.c(i - 1, n);
+        p.beta[i] = 1.0 / (m.b(i, n) - m.a(i, n) * gam);
+        p.l[i] = m.a(i, n) * p.beta[i];
+        p.g[i - 1] = gam;
+    }
+    p.g[n - 1] = 0.0;
+    for (int i = 0; i < n; i++)
+        if (!std::isfinite(p.beta[i])) p.finite = false;
+    p.converged = true;
+    if (n > 2 * CH) {
+        const double ref = p.beta[CH];
+        for (int i = CH; i < n - 2; i++)
+            if (std::fabs(p.beta[i] - ref) > 4e-16 * std::fabs(ref)) { p.converged = false; break; }
+        p.decay = std::fabs(p.g[CH]);
+        if (std::fabs(p.l[CH]) > p.decay) p.decay = std::fabs(p.l[CH]);
     }
     return p;
 }

@@ -57,6 +57,22 @@ const char *cfd_last_error(void);   /* thread-local text of the last failure */
 int cfd_create(cfd_plan **plan, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size);
 void cfd_destroy(cfd_plan *plan);
 
+/* Other compact schemes through the same one-pass streaming solve (the reference's solver takes any
+ * [b1,c1,ai,bi,ci,an,bn], code/cuda/solvers/templated/near_toeplitz.py:49-50, its derivative operator only Pade-4):
+ *   CFD_SCHEME_PADE4     the reference's scheme (= cfd_create with part (0, 1));
+ *   CFD_SCHEME_COMPACT6  6th-order tridiagonal first derivative (Lele 1992 eq. 2.1, alpha = 1/3), 4th-order Pade rows
+ *                        next to the reference's 3rd-order closure rows; interior coupling 0.382 per row, so the
+ *                        backward sweep looks TWO chunks ahead (0.382^64 = 2e-27) -- still one pass, 16 B / point;
+ *   CFD_SCHEME_PADE4_D2  4th-order SECOND derivative (eq. 2.2, alpha = 1/10) with the 3rd-order closure
+ *                        f''_0 + 11 f''_1 = (13 f_0 - 27 f_1 + 15 f_2 - f_3) / h^2.
+ * Plans of these schemes serve cfd_apply (and cfd_apply_host) on unpartitioned lines; cfd_plan_lookahead() = chunks of
+ * look-ahead the plan's matrix needs (1 or 2), derived from its coefficients. */
+#define CFD_SCHEME_PADE4    0
+#define CFD_SCHEME_COMPACT6 1
+#define CFD_SCHEME_PADE4_D2 2
+int cfd_create_scheme(cfd_plan **plan, int nz, int ny, int nx, int axis, double h, int scheme);
+int cfd_plan_lookahead(const cfd_plan *plan);
+
 /* df = local solution x_R of the block: Pade RHS (code/cuda/kernels.cu:4-47 computeRHS) fused with the
  * block's tridiagonal solve (NearToeplitzSolver.solve, templated/near_toeplitz.py:78-107) -- one kernel,
  * f read once, df written once.  halo_lo / halo_hi: the neighbour's boundary plane of f (what
@@ -189,6 +205,12 @@ int cfd_debug_neighbour(int n, int part_rank, int part_size, int *virtual_ranks,
  * d(hi face)/d f[n] that cfd_reduced_unknowns_deferred applies (blocks of n rows). */
 long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *out, long capacity);
 int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_hi);
+/* Host-only: chunks of look-ahead (1, 2; 0 = two-pass) the one-pass solve needs for n rows of coeffs[7], and the
+ * definition of a scheme -- out[37]: b1,c1,ai,bi,ci,an,bn | two special rows per end | a2,b2,c2 (row 1), am,bm,cm
+ * (row n-2) | c0,c1,c2,sgn (interior r_i = c0 f_i + c1 (f_{i+1} + sgn f_{i-1}) + c2 (f_{i+2} + sgn f_{i-2})) | closure
+ * rows per end | q[2][4] (rows 0, 1: sum_k q f[k]) | p[2][4] (rows n-1, n-2: sum_k p f[n-1-k]) | look-ahead | coupling. */
+int cfd_debug_lookahead(int n, const double coeffs[7]);
+int cfd_debug_scheme(int scheme, int n, double h, double *out);
 /* secondary solutions x_UH, x_LH (each n doubles) and the reduced matrix a,b,c (each 2*part_size). */
 int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double *ra, double *rb, double *rc);
 
@@ -203,8 +225,11 @@ int cfd_plan_secondary(const cfd_plan *plan, double *x_uh, double *x_lh, double 
 int nt_create(nt_plan **plan, int nz, int ny, int nx, int axis, const double coeffs[7]);
 int nt_solve(nt_plan *plan, double *d, void *stream);
 /* 1 if the plan uses the exact two-pass LU (one launch per sweep, 32 B/unknown) because the matrix is not
- * diagonally dominant enough for the one-pass kernel (pivots not converged by row 32, or |g|^32 > 1.2e-16). */
+ * diagonally dominant enough for a one-pass kernel (pivots not converged by row 32, or |g|^64 > 1.2e-16).
+ * nt_lookahead: chunks of backward look-ahead of the one-pass solve, derived from the coefficients
+ * (ceil(log(1.2e-16) / log|g| / 32): 1 for |g| <= 0.316, 2 up to 0.563, e.g. alpha = 1/3), 0 for the two-pass LU. */
 int nt_is_exact_two_pass(const nt_plan *plan);
+int nt_lookahead(const nt_plan *plan);
 void nt_destroy(nt_plan *plan);
 
 /* ---------------------------------------------------------------------------------------------------

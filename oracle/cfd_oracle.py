@@ -423,3 +423,67 @@ def npts_distributed_solve(r, npx, c_twin_product_zero=False):
             x_tilda = x_tilda + phi_firsts[m + 1] + x_last * product_2
         x[m] = phi[m] + x_tilda[:, :, None] * psi[m]
     return np.concatenate(x, axis=2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Compact schemes beyond the reference's Pade-4 first derivative.  The reference has no
+# implementation of them -- only its solver accepts their matrices (near_toeplitz.py:49-50) -- so the ground truth is
+# the published scheme (S. K. Lele, J. Comput. Phys. 103 (1992) 16-42: eqs. 2.1, 2.2, 4.1.4, 4.3.4), assembled here
+# with plain NumPy slices and solved with the banded LU the reference's own tests use (compact.py:189-203).
+# ------------------------------------------------------------------------------------------------
+SCHEMES = {"pade4": 0, "compact6": 1, "pade4-d2": 2}
+
+
+def scheme_system(n, h, scheme):
+    """(a, b, c) diagonals of the scheme's matrix for a line of n points."""
+    a, b, c = np.zeros(n), np.ones(n), np.zeros(n)
+    if scheme == "pade4":
+        a[:], c[:] = 0.25, 0.25
+        c[0], a[-1] = 2.0, 2.0
+    elif scheme == "compact6":
+        a[:], c[:] = 1.0 / 3, 1.0 / 3
+        a[1] = c[1] = a[-2] = c[-2] = 0.25              # 4th-order Pade rows next to the closures
+        c[0], a[-1] = 2.0, 2.0                          # 3rd-order closure rows (the reference's)
+    elif scheme == "pade4-d2":
+        a[:], c[:] = 0.1, 0.1
+        c[0], a[-1] = 11.0, 11.0
+    else:
+        raise ValueError(scheme)
+    a[0] = 0.0
+    c[-1] = 0.0
+    return a, b, c
+
+
+def scheme_rhs(f, h, scheme):
+    """Right-hand side along the LAST axis of f."""
+    f = np.asarray(f, dtype=np.float64)
+    r = np.empty_like(f)
+    if scheme == "pade4":
+        r[..., 1:-1] = (3. / (4 * h)) * (f[..., 2:] - f[..., :-2])
+        r[..., 0] = (1. / (2 * h)) * (-5 * f[..., 0] + 4 * f[..., 1] + f[..., 2])
+        r[..., -1] = -(1. / (2 * h)) * (-5 * f[..., -1] + 4 * f[..., -2] + f[..., -3])
+    elif scheme == "compact6":
+        r[..., 2:-2] = (14. / 9) * (f[..., 3:-1] - f[..., 1:-3]) / (2 * h) + (1. / 9) * (f[..., 4:] - f[..., :-4]) / (4 * h)
+        r[..., 1] = (3. / 4) * (f[..., 2] - f[..., 0]) / h
+        r[..., -2] = (3. / 4) * (f[..., -1] - f[..., -3]) / h
+        r[..., 0] = (-2.5 * f[..., 0] + 2 * f[..., 1] + 0.5 * f[..., 2]) / h
+        r[..., -1] = -(-2.5 * f[..., -1] + 2 * f[..., -2] + 0.5 * f[..., -3]) / h
+    elif scheme == "pade4-d2":
+        r[..., 1:-1] = (6. / 5) * (f[..., 2:] - 2 * f[..., 1:-1] + f[..., :-2]) / h ** 2
+        r[..., 0] = (13 * f[..., 0] - 27 * f[..., 1] + 15 * f[..., 2] - f[..., 3]) / h ** 2
+        r[..., -1] = (13 * f[..., -1] - 27 * f[..., -2] + 15 * f[..., -3] - f[..., -4]) / h ** 2
+    else:
+        raise ValueError(scheme)
+    return r
+
+
+def scheme_derivative(f, axis, h, scheme):
+    """Derivative (first, or second for 'pade4-d2') of f[nz,ny,nx] along axis 0 = x, 1 = y, 2 = z."""
+    f = _c(f)
+    ax = 2 - axis
+    g = np.moveaxis(f, ax, -1)
+    n = g.shape[-1]
+    a, b, c = scheme_system(n, h, scheme)
+    r = scheme_rhs(g, h, scheme)
+    x = scipy_solve_banded(a, b, c, r.reshape(-1, n).T).T.reshape(g.shape)
+    return np.ascontiguousarray(np.moveaxis(x, -1, ax))

@@ -316,11 +316,13 @@ def test_near_toeplitz_general_coefficients(C):
 
 
 @pytest.mark.parametrize("axis", [0, 1, 2])
-@pytest.mark.parametrize("coeffs,tol", [((1., 2., 1. / 3, 1., 1. / 3, 2., 1.), 1e-12),      # 6th-order Pade: |g| = 0.38
-                                        ((3., 1., 1., 2.5, 1., 1., 3.), 1e-12),              # weakly dominant
+@pytest.mark.parametrize("coeffs,tol", [((1., 2., 1. / 3, 1., 1. / 3, 2., 1.), 1e-12),      # 6th-order Pade, LA2 switched off
+                                        ((1., 2., .45, 1., .45, 2., 1.), 1e-12),             # |g| = 0.63: 0.63^64 = 1e-13
                                         ((1., 2., 3., 4., 5., 6., 7.), 1e-9)])               # not dominant at all
-def test_near_toeplitz_exact_two_pass(C, axis, coeffs, tol):
-    """Matrices the one-pass kernel refuses (slow decay / non-convergent pivots) go through the exact two-pass LU."""
+def test_near_toeplitz_exact_two_pass(C, axis, coeffs, tol, monkeypatch):
+    """Matrices the one-pass kernels refuse (coupling above 0.563 per row / non-convergent pivots) go through the exact
+    two-pass LU (and so does alpha = 1/3 when the two-chunk look-ahead is switched off: the round-1 path)."""
+    monkeypatch.setenv("CFD_NO_LA2", "1")
     rng = np.random.default_rng(axis)
     shape = [6, 10, 40]
     shape[2 - axis] = 200
@@ -331,6 +333,91 @@ def test_near_toeplitz_exact_two_pass(C, axis, coeffs, tol):
     s.solve(t)
     want = O.near_toeplitz_solve(d, coeffs, axis)
     assert relinf(t.cpu().numpy(), want) <= tol
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("n", [96, 97, 128, 161, 1000])
+def test_near_toeplitz_two_chunk_lookahead(C, axis, n):
+    """alpha = 1/3 (the 6th-order scheme's matrix, |g| = 0.382): the look-ahead is derived from the coefficients -- two
+    chunks, 0.382^64 = 2e-27 -- and the solve stays ONE pass (round 1: exact two-pass, 32 B / unknown)."""
+    rng = np.random.default_rng(n + axis)
+    co = (1., 2., 1. / 3, 1., 1. / 3, 2., 1.)
+    shape = [6, 40, 34]
+    shape[2 - axis] = n
+    d = rng.random(shape) - 0.5
+    s = C.NearToeplitzSolver(d.shape, co, axis=axis)
+    assert not s.two_pass and C.lib().nt_lookahead(s._handle) == 2
+    t = dev(d)
+    s.solve(t)
+    assert relinf(t.cpu().numpy(), O.scipy_solve_axis(d, co, axis)) <= TOL
+
+
+def test_lookahead_is_derived_from_the_coefficients(C):
+    L = C.lib()
+    for co, n, la, two_pass in (((1., 2., .25, 1., .25, 2., 1.), 512, 1, False),        # 0.268^32 = 5e-19
+                                ((1., 2., .3, 1., .3, 2., 1.), 512, 2, False),           # |g| = 0.333: 5e-16 / 3e-31
+                                ((1., 2., 1. / 3, 1., 1. / 3, 2., 1.), 512, 2, False),
+                                ((1., 2., 1. / 3, 1., 1. / 3, 2., 1.), 64, 1, False),    # two chunks: exact anyway
+                                ((1., 2., .45, 1., .45, 2., 1.), 512, 0, True),          # |g| = 0.63: two-pass
+                                ((1., 2., 3., 4., 5., 6., 7.), 512, 0, True)):
+        s = C.NearToeplitzSolver((2, 4, n), co)
+        assert L.nt_lookahead(s._handle) == la and s.two_pass == two_pass, (co, n)
+        d = np.random.default_rng(1).random((2, 4, n))
+        t = dev(d)
+        s.solve(t)
+        assert relinf(t.cpu().numpy(), O.scipy_solve_axis(d, co, 0)) <= 1e-11
+
+
+@pytest.mark.parametrize("scheme", ["compact6", "pade4-d2"])
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("n", [6, 7, 31, 32, 33, 34, 64, 65, 66, 96, 97, 127, 129, 200, 512])
+def test_scheme_derivative_random(C, scheme, axis, n):
+    """6th-order first derivative (two chunks of look-ahead) and 4th-order second derivative through the general
+    one-pass kernel, against the published schemes assembled with NumPy + banded LU; every chunk-count / ragged-tail
+    case (closure rows n-2, n-1 falling into the last or the second-to-last chunk)."""
+    rng = np.random.default_rng(7 * n + axis)
+    shape = [5, 36, 38]
+    shape[2 - axis] = n
+    f = rng.random(shape)
+    h = 0.37
+    s = C.CompactFiniteDifferenceSolver(tuple(shape), h, axis, scheme=scheme)
+    got = s(dev(f)).cpu().numpy()
+    want = O.scheme_derivative(f, axis, h, scheme)
+    assert relinf(got, want) <= TOL
+    la = C.lib().cfd_plan_lookahead(s._plan(axis, h).handle)
+    assert la == (2 if (scheme == "compact6" and n > 64) else 1)
+
+
+@pytest.mark.parametrize("scheme,interior_order", [("compact6", 6), ("pade4-d2", 4)])
+def test_scheme_order_of_accuracy(C, scheme, interior_order):
+    """Analytic check: sin(x) on [0, 3]; away from the 3rd-order closures the error falls by 2^order per doubling."""
+    errs = []
+    for n in (33, 65, 129):
+        x = np.linspace(0, 3.0, n)
+        h = x[1] - x[0]
+        f = np.broadcast_to(np.sin(x), (2, 32, n)).copy()
+        d = C.CompactFiniteDifferenceSolver(f.shape, h, 0, scheme=scheme)(dev(f)).cpu().numpy()[0, 0]
+        true = np.cos(x) if scheme == "compact6" else -np.sin(x)
+        errs.append(np.abs(d - true)[n // 4:3 * n // 4].max())
+    for a, b in zip(errs[:-1], errs[1:]):
+        assert a / b > 0.75 * 2 ** interior_order, errs
+
+
+def test_scheme_256_cubed_and_gradient_fallback(C):
+    """Full-size parity (256^3, all axes, both schemes) and the x/y pair of a non-Pade scheme (two launches inside
+    cfd_apply_xy)."""
+    N = 256
+    zz, yy, xx = smooth((N, N, N))
+    f = np.sin(xx) * np.cos(yy) + np.sin(zz) * xx
+    h = 2 * np.pi / (N - 1)
+    fd = dev(f)
+    for scheme in ("compact6", "pade4-d2"):
+        s = C.CompactFiniteDifferenceSolver((N, N, N), scheme=scheme)
+        for axis, fn in enumerate((s.dfdx, s.dfdy, s.dfdz)):
+            assert relinf(fn(fd, h).cpu().numpy(), O.scheme_derivative(f, axis, h, scheme)) <= TOL
+        gx, gy = s.dfdxy(fd, h, h)
+        assert relinf(gx.cpu().numpy(), O.scheme_derivative(f, 0, h, scheme)) <= TOL
+        assert relinf(gy.cpu().numpy(), O.scheme_derivative(f, 1, h, scheme)) <= TOL
 
 
 def test_one_pass_is_kept_for_pade(C):

@@ -325,3 +325,54 @@ def test_halo_weights_of_the_deferred_exchange(n, h):
             assert np.abs(g_lo + w_lo * (lo_true - guess_lo) - f_lo).max() <= 1e-13 * scale
         if rank < size - 1:
             assert np.abs(g_hi + w_hi * (hi_true - guess_hi) - f_hi).max() <= 1e-13 * scale
+
+
+def test_lookahead_from_coefficients_host():
+    """ceil(log(1.2e-16) / log|g| / 32) chunks of look-ahead, from the matrix alone (no device needed)."""
+    from compact_finite_differences_b200._lib import lib
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def la(co, n):
+        a = np.array(co, dtype=np.float64)
+        return lib().cfd_debug_lookahead(n, a.ctypes.data_as(dp))
+    assert la(PADE, 4096) == 1
+    assert la((1, 2, 1 / 3, 1, 1 / 3, 2, 1), 4096) == 2
+    assert la((1, 2, 1 / 3, 1, 1 / 3, 2, 1), 64) == 1            # at most two chunks: every sweep is exact
+    assert la((1, 2, .45, 1, .45, 2, 1), 4096) == 0             # two-pass
+    assert la((1, 2, 3, 4, 5, 6, 7), 4096) == 0
+    for alpha in (0.05, 0.2, 0.3, 0.35, 0.42):
+        g = (1 - np.sqrt(1 - 4 * alpha * alpha)) / (2 * alpha)   # interior coupling of (alpha, 1, alpha)
+        want = 1 if g ** 32 <= 1.2e-16 else 2 if g ** 64 <= 1.2e-16 else 0
+        assert la((1, 2, alpha, 1, alpha, 2, 1), 1024) == want, alpha
+
+
+@pytest.mark.parametrize("scheme", ["pade4", "compact6", "pade4-d2"])
+def test_scheme_definitions_match_the_published_schemes(scheme):
+    """The library's scheme tables (matrix rows, interior stencil, closure rows), applied with NumPy, reproduce the
+    oracle's independent assembly of the published formulas (Lele 1992) on random data."""
+    from compact_finite_differences_b200._lib import check, lib
+    dp = ctypes.POINTER(ctypes.c_double)
+    n, h = 41, 0.23
+    out = np.zeros(37)
+    check(lib().cfd_debug_scheme(O.SCHEMES[scheme], n, h, out.ctypes.data_as(dp)))
+    b1, c1, ai, bi, ci, an, bn, two, a2, b2, c2, am, bm, cm, c0, s1, s2, sgn, nsp = out[:19]
+    q, p = out[19:27].reshape(2, 4), out[27:35].reshape(2, 4)
+    a, b, c = np.full(n, ai), np.full(n, bi), np.full(n, ci)
+    a[0], b[0], c[0] = 0, b1, c1
+    a[-1], b[-1], c[-1] = an, bn, 0
+    if two:
+        a[1], b[1], c[1] = a2, b2, c2
+        a[-2], b[-2], c[-2] = am, bm, cm
+    wa, wb, wc = O.scheme_system(n, h, scheme)
+    assert np.allclose(a, wa, rtol=1e-15) and np.allclose(b, wb, rtol=1e-15) and np.allclose(c, wc, rtol=1e-15)
+    f = np.random.default_rng(3).random((5, n))
+    fp = np.pad(f, ((0, 0), (2, 2)))
+    r = c0 * f + s1 * (fp[:, 3:-1] + sgn * fp[:, 1:-3]) + s2 * (fp[:, 4:] + sgn * fp[:, :-4])
+    for k in range(int(nsp)):
+        r[:, k] = f[:, :4] @ q[k]
+        r[:, n - 1 - k] = f[:, ::-1][:, :4] @ p[k]
+    want = O.scheme_rhs(f, h, scheme)
+    assert relinf(r, want) < 1e-14
+    assert out[35] == 1                                         # 41 rows = two chunks: every sweep is exact
+    check(lib().cfd_debug_scheme(O.SCHEMES[scheme], 400, h, out.ctypes.data_as(dp)))
+    assert out[35] == (2 if scheme == "compact6" else 1) and out[36] ** (32 * out[35]) <= 1.2e-16
