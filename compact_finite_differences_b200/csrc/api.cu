@@ -427,6 +427,7 @@ struct cfd_plan {
     PairPool pool;                    // work counters of this plan's CAPTURED launches (see counter_pair)
     int scheme = 0;                   // CFD_SCHEME_*; schemes other than PADE4 run the general kernel
     int la = 1;                       // look-ahead chunks of the general kernel
+    bool second = false;              // the scheme is a second derivative (symmetric stencil)
     GParams gp;
     // multi-rank
     std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
@@ -907,7 +908,7 @@ static void fill_general(GParams &gp, const Geometry &g, const Pivots &pv, doubl
     gp.nspecial = 0;
 }
 
-template <bool CONTIG, bool STENCIL, int LA>
+template <bool CONTIG, int STENCIL, int LA>
 static int launch_general_la(const Geometry &g, GParams gp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
                              cudaStream_t stream, PairPool *pool)
 {
@@ -937,7 +938,7 @@ static int launch_general_la(const Geometry &g, GParams gp, const CUtensorMap &t
     return CFD_OK;
 }
 
-template <bool STENCIL>
+template <int STENCIL>
 static int launch_general(const Geometry &g, const GParams &gp, int la, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
                           cudaStream_t stream, PairPool *pool)
 {
@@ -1010,7 +1011,19 @@ extern "C" int cfd_create_scheme(cfd_plan **out, int nz, int ny, int nx, int axi
     p->la = lookahead_chunks(pv, p->g.K);
     if (p->la == 0) { delete p; return fail(CFD_EUNSUPPORTED, "internal: scheme %d is not diagonally dominant enough", scheme); }
     fill_general(p->gp, p->g, pv, 1.0);
-    p->gp.c0 = d.c0; p->gp.c1 = d.c1; p->gp.c2 = d.c2; p->gp.sgn = d.sgn; p->gp.nspecial = d.nspecial;
+    p->gp.c1 = d.c1; p->gp.c2 = d.c2; p->gp.nspecial = d.nspecial;
+    p->second = d.sgn > 0.0;
+    // the kernel evaluates every stencil over differences (kernels_general.cuh): that needs stencils that annihilate
+    // constants -- true of any derivative stencil, checked here
+    {
+        bool ok = std::fabs(d.c0 + (d.sgn > 0.0 ? 2.0 * (d.c1 + d.c2) : 0.0)) <= 1e-12 * (std::fabs(d.c1) + std::fabs(d.c2));
+        for (int r = 0; r < d.nspecial; r++) {
+            double sq = 0, sp = 0, aq = 0, ap = 0;
+            for (int k = 0; k < 4; k++) { sq += d.q[r][k]; sp += d.p[r][k]; aq += std::fabs(d.q[r][k]); ap += std::fabs(d.p[r][k]); }
+            ok = ok && std::fabs(sq) <= 1e-12 * aq && std::fabs(sp) <= 1e-12 * ap;
+        }
+        if (!ok) { delete p; return fail(CFD_EINVAL, "internal: scheme %d has a stencil that does not annihilate constants", scheme); }
+    }
     memcpy(p->gp.q, d.q, sizeof d.q);
     memcpy(p->gp.p, d.p, sizeof d.p);
     memset(&p->kp, 0, sizeof p->kp);
@@ -1084,8 +1097,10 @@ static int apply_impl(cfd_plan *p, const double *f, double *df, const double *ha
     MapPair mp;
     int rc = get_maps(p->cache, p->g, f, df, mp);
     if (rc) return rc;
-    if (p->scheme != CFD_SCHEME_PADE4)
-        return launch_general<true>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
+    if (p->scheme != CFD_SCHEME_PADE4) {
+        if (p->second) return launch_general<2>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
+        return launch_general<1>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
+    }
     // Experiment switch (CFD_RING_STAGING=1): whole, unpartitioned lines through the ring-staged kernel of
     // kernels_xy.cuh with one direction empty -- 32 KiB per warp, 6 warps per SM instead of 40 KiB and 4.
     if (p->size == 1 && !ab && getenv("CFD_RING_STAGING")) return launch_one_direction_ring(p, mp, (cudaStream_t)stream);
@@ -1645,7 +1660,7 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
     MapPair mp;
     int rc = get_maps(p->cache, p->g, d, d, mp);
     if (rc) return rc;
-    if (p->la > 0) return launch_general<false>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
+    if (p->la > 0) return launch_general<0>(p->g, p->gp, p->la, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool);
     if (p->exact) {
         const long L = (long)p->g.K * CH;
         const double *t = p->d_tab;
@@ -1914,8 +1929,10 @@ extern "C" int cfd_zpart_begin(cfd_zpart *z, const double *f, void *stream)
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // the producer of call s+1 overwrites what the consumer of call s-1 read (same parity): order it after the last
-    // coupled launch even when the caller runs begin() on a side stream
+    // coupled launch even when the caller runs begin() on a side stream -- and after an exchange that was begun on
+    // another stream and never picked up, so that the producers of consecutive calls finish in order
     if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+    if (z->pending && z->pending_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_begin, 0));
     ZPtrs q;
     rc = zpart_ptrs(z, z->seq + 1, q);
     if (rc) return rc;
@@ -1977,6 +1994,7 @@ extern "C" int cfd_zpart_apply_xyz(cfd_zpart *z, cfd_plan *px, cfd_plan *py, con
     rc = cfd_async_status();
     if (rc) return rc;
     if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+    if (z->pending && z->pending_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_begin, 0));   // see cfd_zpart_begin
     ZPtrs q;
     rc = zpart_ptrs(z, z->seq + 1, q);
     if (rc) return rc;

@@ -127,6 +127,15 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
+// Raise an arrival flag (possibly in a peer GPU's memory) to `seq`, with release semantics at system scope.  A max,
+// not a store: flags only ever grow, even if two producer launches of consecutive calls (issued on different streams)
+// finish out of order -- a plain store of the older call number would then hide the newer one from the waiter.
+__device__ __forceinline__ void flag_raise(unsigned long long *p, unsigned long long v)
+{
+    __threadfence_system();
+    atomicMax_system(p, v);
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -873,9 +882,8 @@ __device__ __forceinline__ void publish_when_grid_done(unsigned long long *done,
     if (threadIdx.x == 0) {
         if (atomicAdd(done, 1ULL) == (unsigned long long)gridDim.x - 1) {
             *done = 0ULL;
-            __threadfence_system();
-            if (flag_a) st_release_sys(flag_a, seq);
-            if (flag_b) st_release_sys(flag_b, seq);
+            if (flag_a) flag_raise(flag_a, seq);
+            if (flag_b) flag_raise(flag_b, seq);
         }
     }
 }

@@ -5,11 +5,14 @@
 //     6th-order tridiagonal scheme (alpha = 1/3, |g| = 0.382: 0.382^64 = 2e-27) -- still read-once / write-once, where
 //     round 1 fell back to the exact two-pass kernel (32 B / unknown).  The look-ahead width is derived from the
 //     coefficients on the host (api.cu lookahead_chunks).
-//   * GENERAL RIGHT-HAND SIDES.  r_i = c0 f_i + c1 (f_{i+1} + s f_{i-1}) + c2 (f_{i+2} + s f_{i-2}) in the interior
-//     (s = -1: first derivatives, s = +1: second derivatives), up to two closure rows per end with 4-point one-sided
-//     stencils, and a matrix whose first two and last two rows may differ from the Toeplitz interior.  Serves the
-//     6th-order first derivative and the 4th-order second derivative; the reference solver's general
-//     [b1, c1, ai, bi, ci, an, bn] matrices are the STENCIL = false case (right-hand side = the tile itself).
+//   * GENERAL RIGHT-HAND SIDES.  Interior: STENCIL = 1 (first derivatives) r_i = c1 (f_{i+1} - f_{i-1}) + c2 (f_{i+2} - f_{i-2});
+//     STENCIL = 2 (second derivatives) r_i = c1 ((f_{i+1} - f_i) + (f_{i-1} - f_i)) + c2 ((f_{i+2} - f_i) + (f_{i-2} - f_i)).
+//     Up to two closure rows per end with 4-point one-sided stencils, r = sum_k q_k (f_k - f_0): every derivative
+//     stencil annihilates constants, and written over DIFFERENCES of neighbouring points it loses eps |h f'| / h^m to
+//     round-off instead of eps |f| / h^m (two digits at 256^3 for the second derivative).  The matrix may differ from
+//     the Toeplitz interior in its first two and last two rows.  Serves the 6th-order first derivative and the
+//     4th-order second derivative; the reference solver's general [b1, c1, ai, bi, ci, an, bn] matrices are the
+//     STENCIL = 0 case (right-hand side = the tile itself).
 //
 // Same warp-autonomous TMA ring, dynamic bundle draw and TMA stores as stream_kernel.  What differs: the forward
 // values e of the LA chunks that wait for their backward sweep live in SHARED memory (LA + 1 slots per warp, in the
@@ -29,11 +32,11 @@ struct GParams {
     // constants in between.  sk multiplies the right-hand side (beta_i, times the caller's scale for STENCIL = false).
     double sk_mid, l_mid, g_mid;
     RowTab head, tail2, tail;
-    // right-hand side stencil (STENCIL = true)
-    double c0, c1, c2, sgn;
+    // right-hand side stencil (STENCIL != 0)
+    double c1, c2;
     int nspecial;                 // closure rows per end: 1 or 2
-    double q[2][4];               // row 0, row 1:     r = sum_k q[.][k] f[k]
-    double p[2][4];               // row n-1, row n-2: r = sum_k p[.][k] f[n-1-k]
+    double q[2][4];               // row 0, row 1:     r = sum_{k>=1} q[.][k] (f[k] - f[0])          (q[.][0] = -sum of the rest)
+    double p[2][4];               // row n-1, row n-2: r = sum_{k>=1} p[.][k] (f[n-1-k] - f[n-1])
 };
 
 template <bool CONTIG>
@@ -61,7 +64,7 @@ __device__ __forceinline__ double load_row(const unsigned char *slot, int lane, 
 
 // Forward elimination of chunk k.  TAB: 0 = constants, 1 = table chunk (head / tail2 / tail; rows located at run time).
 // History: h1, h2, h3 = f[i-1], f[i-2], f[i-3] on entry; pk0, pk1 = first two rows of the next tile (0 past the end).
-template <bool STENCIL, int TAB>
+template <int STENCIL, int TAB>
 __device__ __forceinline__ void gfwd_chunk(const GParams &p, const RowTab *T, int k, const double (&F)[CH], double pk0,
                                            double pk1, double (&e)[CH], double &eprev, double &h1, double &h2, double &h3)
 {
@@ -70,21 +73,22 @@ __device__ __forceinline__ void gfwd_chunk(const GParams &p, const RowTab *T, in
 #pragma unroll
     for (int j = 0; j < CH; j++) {
         double r;
-        if constexpr (STENCIL) {
+        if constexpr (STENCIL != 0) {
             const double a1 = (j >= 1) ? F[j - 1] : h1, a2 = (j >= 2) ? F[j - 2] : (j == 1 ? h1 : h2);
             const double b1 = (j < CH - 1) ? F[j + 1] : pk0, b2 = (j < CH - 2) ? F[j + 2] : (j == CH - 2 ? pk0 : pk1);
-            r = fma(p.c2, fma(p.sgn, a2, b2), fma(p.c1, fma(p.sgn, a1, b1), p.c0 * F[j]));
+            if constexpr (STENCIL == 1) r = fma(p.c2, b2 - a2, p.c1 * (b1 - a1));
+            else                        r = fma(p.c2, (b2 - F[j]) + (a2 - F[j]), p.c1 * ((b1 - F[j]) + (a1 - F[j])));
             if constexpr (TAB == 1) {
                 const int row = row0 + j;
                 if (k == 0 && j < 2 && j < p.nspecial) {          // closure rows 0 (, 1): forward one-sided, inside chunk 0
-                    r = fma(p.q[j][3], F[3], fma(p.q[j][2], F[2], fma(p.q[j][1], F[1], p.q[j][0] * F[0])));
+                    r = fma(p.q[j][3], F[3] - F[0], fma(p.q[j][2], F[2] - F[0], p.q[j][1] * (F[1] - F[0])));
                 }
                 const int back = n - 1 - row;                     // 0: row n-1, 1: row n-2
                 if (back >= 0 && back < p.nspecial) {
-                    // f[n-1], f[n-2], f[n-3], f[n-4] relative to this row
                     const double a3 = (j >= 3) ? F[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-                    if (back == 0) r = fma(p.p[0][3], a3, fma(p.p[0][2], a2, fma(p.p[0][1], a1, p.p[0][0] * F[j])));
-                    else           r = fma(p.p[1][3], a2, fma(p.p[1][2], a1, fma(p.p[1][1], F[j], p.p[1][0] * b1)));
+                    // differences from f[n-1]: this row (back = 0) or the next one (back = 1)
+                    if (back == 0) r = fma(p.p[0][3], a3 - F[j], fma(p.p[0][2], a2 - F[j], p.p[0][1] * (a1 - F[j])));
+                    else           r = fma(p.p[1][3], a2 - b1, fma(p.p[1][2], a1 - b1, p.p[1][1] * (F[j] - b1)));
                 }
             }
         } else {
@@ -94,7 +98,7 @@ __device__ __forceinline__ void gfwd_chunk(const GParams &p, const RowTab *T, in
         else                    eprev = fma(-p.l_mid, eprev, p.sk_mid * r);
         e[j] = eprev;
     }
-    if constexpr (STENCIL) { h3 = F[CH - 3]; h2 = F[CH - 2]; h1 = F[CH - 1]; }
+    if constexpr (STENCIL != 0) { h3 = F[CH - 3]; h2 = F[CH - 2]; h1 = F[CH - 1]; }
 }
 
 // Backward sweep over one chunk held in registers; OUT writes x over the values of `slot` (tile layout).
@@ -112,7 +116,7 @@ __device__ __forceinline__ void gbwd_chunk(const GParams &p, const RowTab *T, co
     if constexpr (OUT) store_chunk<CONTIG>(slot, lane, X);
 }
 
-template <bool CONTIG, bool STENCIL, int LA>
+template <bool CONTIG, int STENCIL, int LA>
 __global__ void __launch_bounds__(160, 1)
 stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ GParams p)
@@ -220,7 +224,7 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         mbar_wait(bar0 + 8 * slot, phase);
         load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
         double pk0 = 0.0, pk1 = 0.0;
-        if constexpr (STENCIL) {
+        if constexpr (STENCIL != 0) {
             if (!last) {
                 const int s1 = (slot + 1 == NS) ? 0 : slot + 1;
                 const uint32_t ph1 = (slot + 1 == NS) ? (phase ^ 1u) : phase;

@@ -321,9 +321,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
             const unsigned long long prev = atomicAdd(ex.done, edge_pending);
             if (prev + edge_pending == (unsigned long long)ex.nedge) {     // all edge items of the launch are done
                 *ex.done = 0ULL;
-                __threadfence_system();
-                if (ex.flag_lo) st_release_sys(ex.flag_lo, ex.seq);
-                if (ex.flag_hi) st_release_sys(ex.flag_hi, ex.seq);
+                if (ex.flag_lo) flag_raise(ex.flag_lo, ex.seq);
+                if (ex.flag_hi) flag_raise(ex.flag_hi, ex.seq);
             }
         }
         edge_pending = 0;
