@@ -544,9 +544,9 @@ def run_ours(args):
         o.zero_()                      # first touch here, on the bound cores
     # "pipelined" = HostGradient: H2D in z-slabs, fused d/dx + d/dy per slab, D2H overlapping the remaining H2D, then
     # d/dz + D2H (at N > 1 each rank pipelines its own slab and d/dz is the partitioned operator).  "sequential" =
-    # H2D, gradient, D2H one after the other.  Measured: pipelined wins on one GPU (62.7 vs ~78 ms per step); with two
-    # ranks on one host the concurrent H2D + D2H of both slow each other down (412 vs 370 ms) -> sequential at N > 1.
-    e2e_mode = args.e2e if args.e2e != "auto" else ("pipelined" if world == 1 else "sequential")
+    # H2D, gradient, D2H one after the other.  Measured (round 2, profiles/r2e_bench_n2*.json): pipelined reaches
+    # 98 % (N = 1) and 99.7 % (N = 2) of the pinned-copy ceiling, sequential 86 % at N = 2 -> pipelined at every N.
+    e2e_mode = args.e2e if args.e2e != "auto" else "pipelined"
     if e2e_mode == "pipelined":
         hg = C.HostGradient((nz_loc, N, N), (h, h, h), slabs=8, ddz=ddz if world > 1 else None)
 

@@ -175,7 +175,9 @@ class CompactFiniteDifferenceSolver:
                 "the stage methods with explicit halo planes"
             assert dist.get_world_size(self._group) == self.part[1] and dist.get_rank(self._group) == self.part[0], \
                 "the line's process group does not match (rank, size) of the line_da"
-            op = PartitionedDerivative(self.shape, spacing, axis, group=self._group, mode="fused", comm="pairwise")
+            # z lines exchange over NVLink peer memory (cfd_zpart), x / y lines (strided boundary planes) over NCCL
+            op = PartitionedDerivative(self.shape, spacing, axis, group=self._group, mode="fused",
+                                       comm="nvlink" if axis == 2 else "pairwise")
             self._line_ops[key] = op
         return op
 
@@ -206,10 +208,10 @@ class CompactFiniteDifferenceSolver:
         """f_local (the reference's ghosted scratch array) is accepted and ignored: no ghost copy is made."""
         return self._apply(0, self._h(dx, 0), f, out)
 
-    def dfdy(self, f, dy=None, out=None):
+    def dfdy(self, f, dy=None, out=None, f_local=None):
         return self._apply(1, self._h(dy, 1), f, out)
 
-    def dfdz(self, f, dz=None, out=None):
+    def dfdz(self, f, dz=None, out=None, f_local=None):
         return self._apply(2, self._h(dz, 2), f, out)
 
     def _h(self, h, axis):

@@ -126,6 +126,25 @@ if rank == 0:
           f"{3 * N ** 3 / ms.item() * 1e3:.3e} pts/s per derivative", flush=True)
 del refx, refy, full
 
+# (b2) the reference's own call shapes on a multi-rank line (code/cuda/compact.py:18-44): the operator built from a
+#      line_da, (i) one dfdz call that does everything inside, (ii) the five stages one by one
+lda = C.LineDA((nl, N, N), rank, world, direction=2)
+cfd = C.CompactFiniteDifferenceSolver(lda)
+x_d = torch.empty_like(slab)
+cfd.dfdz(slab, h, x_d, None)                                          # dfdx(f_d, dx, x_d, f_local_d) of the reference
+report("reference call shape: CompactFiniteDifferenceSolver(line_da).dfdz(f, dz, x, f_local) vs single-GPU",
+       ((x_d - ref).abs().max() / ref.abs().max()).item())
+halo_lo, halo_hi = C.exchange_halo_planes(slab[0].contiguous(), slab[-1].contiguous(), rank, world)
+cfd2 = C.CompactFiniteDifferenceSolver(C.LineDA((nl, N, N), rank, world, direction=2))
+cfd2.compute_RHS(slab, h, x_d, None, halo_lo=halo_lo, halo_hi=halo_hi)
+x_UH, x_LH = cfd2.solve_secondary_systems()
+cfd2.solve_primary_system(x_d)
+alpha, beta = cfd2.solve_reduced_system(x_UH, x_LH, x_d)
+cfd2.sum_solutions(x_UH, x_LH, x_d, alpha, beta)
+report("reference stages: compute_RHS, solve_secondary_systems, solve_primary_system, solve_reduced_system, "
+       "sum_solutions vs single-GPU", ((x_d - ref).abs().max() / ref.abs().max()).item())
+del x_d
+
 # (c) Cartesian process grids (grid.DA): x-, y- and z-partitioned lines through PartitionedDerivative, field
 #     generated per block on the device with DA_arange, result gathered with DA_gather_blocks and checked on rank 0
 #     against the oracle on the global field (the reference's 2x2x2 test layout, code/cuda/test/test_compact.py:19-57)
