@@ -336,7 +336,8 @@ extern "C" int cfd_async_status(void)
 
 template <bool CONTIG, bool DERIV, int NSLOT>
 static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                            cudaStream_t stream, bool in_place, PairPool *pool)
+                            cudaStream_t stream, bool in_place, PairPool *pool, int force_kseg = 0,
+                            const CUtensorMap *tm_aux = nullptr)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
@@ -368,7 +369,9 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
             if (want > g.K / 16) want = g.K / 16;
             if (want > 1) kseg = (int)((g.K + want - 1) / want);
         }
+        if (force_kseg > 0) kseg = force_kseg;       // in place with the side buffer: the plan fixed the cut
         if (kseg > 0 && kseg < g.K) { kp.kseg = kseg; kp.nseg = (g.K + kseg - 1) / kseg; }
+        kp.aux_on = (tm_aux != nullptr && kp.nseg > 1) ? 1 : 0;
     }
     const long nitems = g.nb * kp.nseg;
     if (!g_warps) {   // small problems: spread the work items over all SMs before stacking warps on one
@@ -393,19 +396,20 @@ static int launch_stream_ns(const Geometry &g, KParams kp, const CUtensorMap &tm
     const long cap = (long)dinfo.sms * ctas;
     if (blocks > cap) blocks = cap;
     if (const char *e = getenv("CFD_CTAS")) { if (atol(e) >= 1 && atol(e) < blocks) blocks = atol(e); }    // experiment
-    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, kp));
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, kp, tm_aux ? *tm_aux : tm_out));
     g_launches++;
     return CFD_OK;
 }
 
 template <bool CONTIG, bool DERIV>
 static int launch_stream(const Geometry &g, const KParams &kp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
-                         cudaStream_t stream, PairPool *pool, bool in_place = false)
+                         cudaStream_t stream, PairPool *pool, bool in_place = false, int force_kseg = 0,
+                         const CUtensorMap *tm_aux = nullptr)
 {
     switch (g_slots ? g_slots : 3) {
-        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream, in_place, pool);
-        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream, in_place, pool);
-        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream, in_place, pool);
+        case 3: return launch_stream_ns<CONTIG, DERIV, 3>(g, kp, tm_in, tm_out, stream, in_place, pool, force_kseg, tm_aux);
+        case 4: return launch_stream_ns<CONTIG, DERIV, 4>(g, kp, tm_in, tm_out, stream, in_place, pool, force_kseg, tm_aux);
+        case 5: return launch_stream_ns<CONTIG, DERIV, 5>(g, kp, tm_in, tm_out, stream, in_place, pool, force_kseg, tm_aux);
         default: return fail(CFD_EINVAL, "ring slots must be 3, 4 or 5");
     }
 }
@@ -459,10 +463,14 @@ struct nt_plan {
     int la = 0;                       // > 0: the general one-pass kernel with this many look-ahead chunks
     GParams gp;
     double *d_tab = nullptr;          // [4][K*32]: forward pc, qc; backward pc, qc
-    // Starved shape (long lines, fewer bundles than warps): the lines are cut into segments, which is only safe
-    // out of place -- solve into this scratch field, then copy it back over d (both tiny by definition).
-    double *d_scratch = nullptr;
-    MapCache scratch_cache;
+    // Starved shape (long lines, few bundles): the lines are cut into segments so that every warp finds work.  In
+    // place that is only safe if no segment's result lands on a tile a neighbouring segment still has to read: the
+    // first and last result chunk of every segment go to this side buffer (2 chunks per segment, <= 1/4 of the field)
+    // and are copied into place by a second, small launch.
+    double *d_aux = nullptr;
+    int aux_kseg = 0, aux_nseg = 0;
+    Geometry g_aux;
+    MapCache aux_cache;
 };
 
 #define CFD_ESLOWPATH (-100)   /* internal: matrix needs the exact two-pass solver */
@@ -1642,10 +1650,30 @@ extern "C" int nt_create(nt_plan **out, int nz, int ny, int nx, int axis, const 
     }
     if (rc) { delete p; return rc; }
     p->kp.lo_closure = 1; p->kp.hi_closure = 1;
-    // (measured, scripts/sweep_solver.py: the detour pays below ~256 bundles; at 512 the plain in-place kernel wins)
+    // (measured, scripts/sweep_solver.py: cutting the lines pays below ~256 bundles; at 512 whole lines win)
     if (!p->exact && p->g.K >= 16 && p->g.nb <= 256) {
-        const size_t bytes = (size_t)p->g.nlines * p->g.n * sizeof(double);
-        if (cudaMalloc(&p->d_scratch, bytes) != cudaSuccess) { cudaGetLastError(); p->d_scratch = nullptr; }
+        DeviceInfo di;
+        if (device_info(di) == CFD_OK) {
+            long want = (4L * di.sms * 4 + p->g.nb - 1) / p->g.nb;            // ~4 work items per warp
+            if (want > p->g.K / 8) want = p->g.K / 8;                         // segments of >= 8 chunks
+            if (want > 1) {
+                p->aux_kseg = (int)((p->g.K + want - 1) / want);
+                p->aux_nseg = (p->g.K + p->aux_kseg - 1) / p->aux_kseg;
+                // the side buffer is a field of the same plane geometry with 2 * nseg chunks per line
+                const int n_aux = 2 * p->aux_nseg * CH;
+                int rc2;
+                if (axis == 0)      rc2 = make_geometry(p->g_aux, nz, ny, n_aux, 0);
+                else if (axis == 1) rc2 = make_geometry(p->g_aux, nz, n_aux, nx, 1);
+                else                rc2 = make_geometry(p->g_aux, n_aux, ny, nx, 2);
+                const size_t bytes = (size_t)p->g.nlines * n_aux * sizeof(double);
+                if (rc2 != CFD_OK || cudaMalloc(&p->d_aux, bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    g_err.clear();
+                    p->d_aux = nullptr;                                        // whole lines instead: slower, still right
+                    p->aux_kseg = p->aux_nseg = 0;
+                }
+            }
+        }
     }
     *out = p;
     return CFD_OK;
@@ -1675,17 +1703,22 @@ extern "C" int nt_solve(nt_plan *p, double *d, void *stream)
         return launch_recurrence<false, true>(p->g, t + 2 * L, t + 3 * L, mp.tm_in, mp.tm_out, st, &p->pool);
     }
     KParams kp = p->kp;
-    if (p->d_scratch) {
-        MapPair ms;
-        rc = get_maps(p->scratch_cache, p->g, d, p->d_scratch, ms);
+    if (p->d_aux) {
+        MapPair ma;                                   // only tm_out of this pair is used: the side buffer as a store target
+        rc = get_maps(p->aux_cache, p->g_aux, p->d_aux, p->d_aux, ma);
         if (rc) return rc;
-        rc = p->g.contig ? launch_stream<true, false>(p->g, kp, ms.tm_in, ms.tm_out,
-                                                      (cudaStream_t)stream, &p->pool, false)
-                         : launch_stream<false, false>(p->g, kp, ms.tm_in, ms.tm_out,
-                                                       (cudaStream_t)stream, &p->pool, false);
+        rc = p->g.contig ? launch_stream<true, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool, true,
+                                                      p->aux_kseg, &ma.tm_out)
+                         : launch_stream<false, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool, true,
+                                                       p->aux_kseg, &ma.tm_out);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d, p->d_scratch, (size_t)p->g.nlines * p->g.n * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        const int n_aux = 2 * p->aux_nseg * CH;
+        const long total = p->g.nlines * n_aux;
+        const int bs = 256;
+        scatter_aux_kernel<<<(unsigned)((total + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+            d, p->d_aux, total, p->g.n, n_aux, p->g.inner, p->aux_kseg, p->g.K);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
         return CFD_OK;
     }
     if (p->g.contig) return launch_stream<true, false>(p->g, kp, mp.tm_in, mp.tm_out, (cudaStream_t)stream, &p->pool, true);
@@ -1696,7 +1729,7 @@ extern "C" void nt_destroy(nt_plan *p)
 {
     if (!p) return;
     cudaFree(p->d_tab);
-    cudaFree(p->d_scratch);
+    cudaFree(p->d_aux);
     delete p;
 }
 

@@ -44,6 +44,7 @@ struct KParams {
     int K;             // chunks per line = ceil(n / 32)
     int jl;            // position of row n-1 inside the last chunk
     int kseg, nseg;    // line segmentation: chunks per segment, segments per line (nseg == 1: whole lines)
+    int aux_on;        // in-place solve with segments: the first and last result chunk of every segment go to tm_aux
     int inner;         // STRIDED: extent of the contiguous dimension the lanes map to
     int inner_tiles;   // STRIDED: ceil(inner / 32)
     int outer;         // STRIDED: number of outer slices
@@ -336,7 +337,7 @@ __device__ __forceinline__ void bwd_chunk(const KParams &p, const double (&e)[CH
 template <bool CONTIG, bool DERIV, int NS>
 __global__ void __launch_bounds__(224, 1)
 stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-              const __grid_constant__ KParams p)
+              const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_aux)
 {
     extern __shared__ unsigned char smem_raw[];
     constexpr int PER_WARP = (NS + 2) * SLOT_BYTES;     // ring + two result staging slots
@@ -513,11 +514,26 @@ stream_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
+                // In-place solve of segmented lines (solver-only): a segment's first and last result chunk are its
+                // neighbours' look-ahead / warm-up INPUT tiles, so they must not land in the field while any segment
+                // may still read them.  They go to the side buffer tm_aux (a field of 2 chunks per segment: chunk
+                // 2 seg = first, 2 seg + 1 = last) and are copied into place by scatter_aux_kernel afterwards.
+                const CUtensorMap *tm = &tm_out;
+                int row = kc * CH;
+                if constexpr (!DERIV) {
+                    if (p.aux_on) {
+                        const int c1 = (kout + kseg < K) ? kout + kseg : K;
+                        if (kc == kout || kc == c1 - 1) {
+                            tm = &tm_aux;
+                            row = (2 * (kout / kseg) + (kc == kout ? 0 : 1)) * CH;
+                        }
+                    }
+                }
                 if constexpr (CONTIG) {
-                    tma_store_2d(&tm_out, smem_u32(oslot), kc * CH, (int)(b * CH));
-                    tma_store_2d(&tm_out, smem_u32(oslot) + 4096, kc * CH + 16, (int)(b * CH));
+                    tma_store_2d(tm, smem_u32(oslot), row, (int)(b * CH));
+                    tma_store_2d(tm, smem_u32(oslot) + 4096, row + 16, (int)(b * CH));
                 } else {
-                    tma_store_3d(&tm_out, smem_u32(oslot), oc0, kc * CH, oc2);
+                    tma_store_3d(tm, smem_u32(oslot), oc0, row, oc2);
                 }
                 tma_commit();
             }
@@ -1004,6 +1020,25 @@ sum_solutions_kernel(double *__restrict__ x, const double *__restrict__ alpha, c
     const long i = (p / stride) % n;
     const long line = (p / (stride * n)) * stride + (p % stride);
     x[p] += alpha[line] * x_uh[i] + beta[line] * x_lh[i];
+}
+
+// Second half of the in-place solve of segmented lines: the first / last result chunk of every segment, parked in the
+// side buffer by stream_kernel (aux_on), into their place in the field.  aux is a field with n_aux = 2 nseg 32 rows per
+// line; element (line, r): chunk a = r / 32 -> segment a / 2, first (a even) or last (a odd) chunk of the segment.
+__global__ void __launch_bounds__(256)
+scatter_aux_kernel(double *__restrict__ d, const double *__restrict__ aux, long total, int n, int n_aux, long inner,
+                   int kseg, int K)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long c = t % inner, rest = t / inner;
+    const int r = (int)(rest % n_aux);
+    const long o = rest / n_aux;
+    const int a = r / CH, seg = a >> 1;
+    const int c0 = seg * kseg, c1 = (c0 + kseg < K) ? c0 + kseg : K;
+    if ((a & 1) && c1 - 1 == c0) return;                    // one-chunk segment: its only chunk was stored as "first"
+    const int row = ((a & 1) ? c1 - 1 : c0) * CH + (r % CH);
+    if (row < n) d[(o * n + row) * inner + c] = aux[t];
 }
 
 // Thread-parallel Thomas over interleaved systems sharing one matrix (reference reducedSolverKernel,

@@ -878,8 +878,8 @@ def test_segmented_lines(C, kseg):
 
 
 def test_auto_segmentation_small_batch(C):
-    """32 bundles of 4096-long lines: the launcher cuts the lines automatically (out-of-place derivative only; the
-    in-place solver keeps whole lines); results unchanged."""
+    """32 bundles of 4096-long lines: the launcher cuts the lines automatically (the in-place solver through its side
+    buffer, test_in_place_solver_on_starved_shapes); results unchanged."""
     rng = np.random.default_rng(5)
     d = rng.random((1, 1024, 4096))
     t = dev(d)
@@ -887,6 +887,26 @@ def test_auto_segmentation_small_batch(C):
     assert relinf(t.cpu().numpy(), O.near_toeplitz_solve(d, O.PADE)) <= TOL
     got = C.CompactFiniteDifferenceSolver(d.shape, 0.2, 0)(dev(d)).cpu().numpy()
     assert relinf(got, O.derivative(d, 0, 0.2)) <= TOL
+
+
+@pytest.mark.parametrize("shape,axis", [((1, 64, 4096), 0), ((1, 1024, 4096), 0), ((2, 40, 1000), 0), ((2, 2048, 64), 1),
+                                        ((1024, 4, 64), 2), ((545, 2, 96), 2), ((3, 100, 8192), 0)])
+def test_in_place_solver_on_starved_shapes(C, shape, axis):
+    """Long lines, few bundles: the solver cuts the lines into segments IN PLACE -- each segment's first and last
+    result chunk (its neighbours' look-ahead / warm-up inputs) take a detour through a side buffer of 2 chunks per
+    segment and a small scatter launch -- instead of round 1's field-sized scratch + device copy."""
+    rng = np.random.default_rng(sum(shape) + axis)
+    d = rng.random(shape) - 0.5
+    for co in (O.PADE, (1.5, 0.3, 0.2, 1.0, 0.25, 0.1, 2.0)):
+        s = C.NearToeplitzSolver(shape, co, axis=axis)
+        t = dev(d)
+        n0 = C.lib().cfd_launch_count()
+        s.solve(t)
+        launches = C.lib().cfd_launch_count() - n0
+        assert relinf(t.cpu().numpy(), O.scipy_solve_axis(d, co, axis)) <= TOL
+        assert launches == 2                   # segmented kernel + scatter (one launch would mean whole lines)
+        s.solve(t)                             # and again on its own output: the side buffer is re-usable
+        assert relinf(t.cpu().numpy(), O.scipy_solve_axis(O.scipy_solve_axis(d, co, axis), co, axis)) <= 10 * TOL
 
 
 def test_very_long_lines(C):
