@@ -916,20 +916,20 @@ static void fill_general(GParams &gp, const Geometry &g, const Pivots &pv, doubl
     gp.nspecial = 0;
 }
 
-template <bool CONTIG, int STENCIL, int LA>
-static int launch_general_la(const Geometry &g, GParams gp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+template <bool CONTIG, int STENCIL, int LA, int NS>
+static int launch_general_ns(const Geometry &g, GParams gp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
                              cudaStream_t stream, PairPool *pool)
 {
     static DeviceInfo dinfo;
     if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
-    constexpr int per_warp = (3 + LA + 1) * SLOT_BYTES + 3 * 16;
-    int warps = g_warps ? g_warps : 4;
-    const int max_warps = (LA == 1) ? 5 : 4;
+    constexpr int per_warp = NS * SLOT_BYTES + NS * 16;
+    constexpr int max_warps = (232448 - 1024) / per_warp < 7 ? (232448 - 1024) / per_warp : 7;
+    int warps = g_warps ? g_warps : max_warps;
     if (warps > max_warps) warps = max_warps;
     const long per_sm = (g.nb + dinfo.sms - 1) / dinfo.sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     const size_t smem = (size_t)warps * per_warp + 1024;
-    auto kern = stream_kernel_g<CONTIG, STENCIL, LA>;
+    auto kern = stream_kernel_g<CONTIG, STENCIL, LA, NS>;
     static size_t configured[MAX_DEVICES] = {0};
     int dev = 0;
     { int rc = current_device(dev); if (rc) return rc; }
@@ -944,6 +944,16 @@ static int launch_general_la(const Geometry &g, GParams gp, const CUtensorMap &t
     CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, tm_in, tm_out, gp));
     g_launches++;
     return CFD_OK;
+}
+
+template <bool CONTIG, int STENCIL, int LA>
+static int launch_general_la(const Geometry &g, const GParams &gp, const CUtensorMap &tm_in, const CUtensorMap &tm_out,
+                             cudaStream_t stream, PairPool *pool)
+{
+    // 4 ring slots per warp (32 KiB) and 7 warps per SM.  Measured at 512^3 (scripts/time_schemes.py,
+    // profiles/r2j_time_schemes_512.txt): the kernel is latency-bound on its recurrence chains, time x warps ~ const --
+    // 6th-order derivative 0.465 / 0.418 / 0.381 / 0.351 ms with 4 / 5 / 6 / 7 warps; 5 slots x 5 warps 0.379 ms.
+    return launch_general_ns<CONTIG, STENCIL, LA, 4>(g, gp, tm_in, tm_out, stream, pool);
 }
 
 template <int STENCIL>

@@ -14,10 +14,8 @@
 //     4th-order second derivative; the reference solver's general [b1, c1, ai, bi, ci, an, bn] matrices are the
 //     STENCIL = 0 case (right-hand side = the tile itself).
 //
-// Same warp-autonomous TMA ring, dynamic bundle draw and TMA stores as stream_kernel.  What differs: the forward
-// values e of the LA chunks that wait for their backward sweep live in SHARED memory (LA + 1 slots per warp, in the
-// tile layout), not in registers -- two chunks of look-ahead would need 96 doubles per lane -- and the result of a chunk
-// is written over its e values in place and leaves by TMA from that slot.  Whole lines only (no segmentation).
+// Same warp-autonomous TMA ring, dynamic bundle draw and TMA stores as stream_kernel; whole lines only (no
+// segmentation).  Where the forward values of the waiting chunks live is described at the kernel.
 #pragma once
 #include "kernels.cuh"
 
@@ -116,19 +114,26 @@ __device__ __forceinline__ void gbwd_chunk(const GParams &p, const RowTab *T, co
     if constexpr (OUT) store_chunk<CONTIG>(slot, lane, X);
 }
 
-template <bool CONTIG, int STENCIL, int LA>
-__global__ void __launch_bounds__(160, 1)
+// Register / shared-memory budget (second version; the first kept every waiting chunk's e-values in shared memory,
+// 40-48 KiB per warp, 4 warps per SM: latency-bound on the recurrence chains, issue slots 16-18 % busy,
+// profiles/r2i_ncu_full_raw_general_kernel_512_first_version.csv).  Now the two newest chunks' e-values stay in
+// registers (eB = chunk k, eA = chunk k-1, as in stream_kernel) and shared memory is the NS-slot tile ring and nothing
+// else, as in stream_kernel_xy: the slot a tile was consumed from doubles as
+//   LA = 1: the staging slot of result chunk k-1, shipped in the same step, refilled one step later;
+//   LA = 2: the parking slot of e(k-1), which waits one step there for its backward sweep (chunk k-2 is swept, in
+//           place, in the slot parked the step before), shipped then, refilled two steps after it was consumed.
+// 32 KiB per warp with NS = 4 -> 6 warps per SM.
+template <bool CONTIG, int STENCIL, int LA, int NS>
+__global__ void __launch_bounds__(224, 1)
 stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ GParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int NS = 3, NE = LA + 1;
-    constexpr int PER_WARP = (NS + NE) * SLOT_BYTES;
+    constexpr int PER_WARP = NS * SLOT_BYTES;
     constexpr int CTRL = NS * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *wbase = base + warp * PER_WARP;
-    unsigned char *ebase = wbase + NS * SLOT_BYTES;
     unsigned char *ctrl = base + nwarps * PER_WARP + warp * CTRL;
     const uint32_t bar0 = smem_u32(ctrl);
     volatile long long *tag = reinterpret_cast<volatile long long *>(ctrl + NS * 8);
@@ -180,7 +185,7 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         if (c == K - 2) return &p.tail2;
         return nullptr;
     };
-    auto ship = [&](int c, long b, unsigned char *slot) {     // TMA store of result chunk c from its slot
+    auto ship = [&](int c, long b, unsigned char *slot) {     // TMA store of result chunk c from `slot`
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -193,11 +198,8 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             tma_commit();
         }
     };
-    // sweep x through the e values of chunk c held in its shared-memory slot; OUT: results over them, then shipped
-    auto sweep_slot = [&](int c, long b, double &x, bool out) {
-        unsigned char *slot = ebase + (c % NE) * SLOT_BYTES;
-        double E[CH];
-        load_chunk<CONTIG>(slot, lane, E);
+    // backward sweep over a chunk held in registers; `out`: results staged in `slot` and shipped
+    auto sweep_regs = [&](const double (&E)[CH], int c, long b, double &x, bool out, unsigned char *slot) {
         const RowTab *T = table_of(c);
         if (out) {
             if (T) gbwd_chunk<CONTIG, 1, true>(p, T, E, x, slot, lane);
@@ -209,10 +211,12 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
     };
 
-    double F[CH], e[CH];
+    double F[CH], eA[CH], eB[CH];
     double eprev = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
     long b = 0;
     int k = 0, slot = 0;
+    int skip = LA;                                // refills lag the consumer by LA steps (see above)
+    unsigned char *parked = nullptr;              // LA = 2: the slot holding e(k-2)
     uint32_t phase = 0;
     for (;;) {
         if (k == 0) {
@@ -221,8 +225,9 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             eprev = 0.0; h1 = 0.0; h2 = 0.0; h3 = 0.0;
         }
         const bool last = (k == K - 1);
+        unsigned char *cur = wbase + slot * SLOT_BYTES;
         mbar_wait(bar0 + 8 * slot, phase);
-        load_chunk<CONTIG>(wbase + slot * SLOT_BYTES, lane, F);
+        load_chunk<CONTIG>(cur, lane, F);
         double pk0 = 0.0, pk1 = 0.0;
         if constexpr (STENCIL != 0) {
             if (!last) {
@@ -233,36 +238,57 @@ stream_kernel_g(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
                 pk1 = load_row<CONTIG>(wbase + s1 * SLOT_BYTES, lane, 1);
             }
         }
-        const RowTab *T = table_of(k);
-        if (T) gfwd_chunk<STENCIL, 1>(p, T, k, F, pk0, pk1, e, eprev, h1, h2, h3);
-        else   gfwd_chunk<STENCIL, 0>(p, T, k, F, pk0, pk1, e, eprev, h1, h2, h3);
+        {
+            const RowTab *T = table_of(k);
+            if (T) gfwd_chunk<STENCIL, 1>(p, T, k, F, pk0, pk1, eB, eprev, h1, h2, h3);
+            else   gfwd_chunk<STENCIL, 0>(p, T, k, F, pk0, pk1, eB, eprev, h1, h2, h3);
+        }
+        // refill the slot that was shipped in the previous step (consumed LA steps ago)
         __syncwarp();
-        if (lane == 0) issue();
+        if (lane == 0) {
+            if (skip == 0) { tma_wait_read0(); issue(); }
+        }
+        if (skip > 0) --skip;
         __syncwarp();
 
-        // the slot e(k) goes to was shipped LA + 1 steps ago: its TMA store must have finished reading it
-        if (lane == 0) tma_wait_read0();
-        __syncwarp();
-        unsigned char *eslot = ebase + (k % NE) * SLOT_BYTES;
         double x = 0.0;
         if (last) {                                   // exact sweep from the true end of the line
-            if (T) gbwd_chunk<CONTIG, 1, true>(p, T, e, x, eslot, lane);
-            else   gbwd_chunk<CONTIG, 0, true>(p, T, e, x, eslot, lane);
-            ship(k, b, eslot);
-#pragma unroll 1
-            for (int c = k - 1; c >= 0 && c >= k - LA; c--) sweep_slot(c, b, x, true);
-        } else {
-            if (k >= LA) {                            // a result chunk follows: warm the sweep up through chunk k
-                if (T) gbwd_chunk<CONTIG, 1, false>(p, T, e, x, eslot, lane);
-                else   gbwd_chunk<CONTIG, 0, false>(p, T, e, x, eslot, lane);
+            sweep_regs(eB, k, b, x, true, cur);
+            if (k >= 1) {
+                if (lane == 0) tma_wait_read0();      // chunks K-1 and K-2 share the staging slot
+                __syncwarp();
+                sweep_regs(eA, k - 1, b, x, true, cur);
             }
-            store_chunk<CONTIG>(eslot, lane, e);
-            __syncwarp();
-            if (k >= LA) {
-                if constexpr (LA == 2) sweep_slot(k - 1, b, x, false);          // ... and through chunk k-1
-                sweep_slot(k - LA, b, x, true);
+            if constexpr (LA == 2) {
+                if (k >= 2) {
+                    double E[CH];
+                    load_chunk<CONTIG>(parked, lane, E);
+                    sweep_regs(E, k - 2, b, x, true, parked);
+                }
+            }
+        } else if constexpr (LA == 1) {
+            if (k >= 1) {
+                sweep_regs(eB, k, b, x, false, cur);  // warm-up through chunk k
+                sweep_regs(eA, k - 1, b, x, true, cur);
+            }
+        } else {
+            if (k >= 2) {
+                sweep_regs(eB, k, b, x, false, cur);  // warm-up through chunks k and k-1
+                sweep_regs(eA, k - 1, b, x, false, cur);
+            }
+            unsigned char *old = parked;
+            if (k >= 1) {                             // e(k-1) waits one step in the slot tile k came from
+                store_chunk<CONTIG>(cur, lane, eA);
+                parked = cur;
+            }
+            if (k >= 2) {                             // chunk k-2: swept in place in the slot parked the step before
+                double E[CH];
+                load_chunk<CONTIG>(old, lane, E);
+                sweep_regs(E, k - 2, b, x, true, old);
             }
         }
+#pragma unroll
+        for (int j = 0; j < CH; j++) eA[j] = eB[j];
         if (++k == K) k = 0;
         if (++slot == NS) { slot = 0; phase ^= 1u; }
     }

@@ -29,6 +29,24 @@ def timeit(fn, reps=20):
 
 
 print(f"N = {N}")
+if os.environ.get("SCHEME_SWEEP"):           # launch shape of the general kernel: (warps per SM, ring slots)
+    co = (1., 2., 1. / 3, 1., 1. / 3, 2., 1.)
+    for w, ns in ((0, 0), (7, 0), (6, 0), (5, 0), (4, 0)):
+        C.lib().cfd_set_launch(w, 0, ns)
+        line = f"general kernel warps={w or 'default'} slots={ns or 'default'}:"
+        for scheme in ("compact6", "pade4-d2"):
+            res = []
+            for a in range(3):
+                op = C.CompactFiniteDifferenceSolver(shape, 0.1, a, scheme=scheme)
+                res.append(timeit(lambda: op(f, df)))
+            line += f"  {scheme} " + "/".join(f"{r:.4f}" for r in res)
+        res = []
+        for a in range(3):
+            s = C.NearToeplitzSolver(shape, co, axis=a)
+            res.append(timeit(lambda: s.solve(f)))
+        line += "  solve(1/3) " + "/".join(f"{r:.4f}" for r in res)
+        print(line, flush=True)
+    C.lib().cfd_set_launch(0, 0, 0)
 for scheme in ("pade4", "compact6", "pade4-d2"):
     res = []
     for a in range(3):
