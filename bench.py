@@ -345,9 +345,23 @@ def extra_configs(C, dev, peak):
     def grad():
         g.gradient(fs[k[0] & 3], (h, h, h), (ds[0], ds[1], ds[2]))
         k[0] += 1
-    per_axis["gradient_ms"] = _time_calls(grad)
+    per_axis["gradient_ms"] = _time_calls(grad)            # cfd_apply_xyz: d/dz on the library's side stream
+    os.environ["CFD_XYZ_SERIAL"] = "1"
+    per_axis["gradient_one_stream_ms"] = _time_calls(grad)
+    os.environ.pop("CFD_XYZ_SERIAL")
     out["256^3 (configs[1])"] = per_axis
     del fs, ds
+    # the 512^3 step of the headline as gradient() issues it (x/y launch and d/dz launch on two streams)
+    N = 512
+    h = 2 * np.pi / (N - 1)
+    f = torch.rand((N, N, N), dtype=torch.float64, device=dev)
+    d3 = [torch.empty_like(f) for _ in range(3)]
+    g = C.CompactFiniteDifferenceSolver((N, N, N))
+    ms = _time_calls(lambda: g.gradient(f, (h, h, h), d3))
+    out["512^3 gradient() with d/dz on the library's side stream (cfd_apply_xyz)"] = {
+        "ms_per_step": ms, "points_per_s_per_derivative": 3 * N ** 3 / (ms * 1e-3),
+        "note": "the timed step of `value` issues the two launches on ONE stream so that each has its own CUDA-event duration"}
+    del f, d3, g
     sweep = []
     for n, batch in ((32, 1 << 10), (32, 1 << 20), (4096, 1 << 10), (4096, 1 << 18)):      # 2^30-unknown cap
         d = torch.rand((1, batch, n), dtype=torch.float64, device=dev)

@@ -23,6 +23,7 @@ SIGNATURES = {
     "cfd_plan_lookahead": (_i, [_vp]),
     "cfd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_apply_xy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_apply_xyz": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_plan_set_xy_warps": (_i, [_vp, _i]),
     "cfd_compute_rhs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cfd_plan_coeffs": (_i, [_vp, _dp]),

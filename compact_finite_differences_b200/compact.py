@@ -196,12 +196,19 @@ class CompactFiniteDifferenceSolver:
         return out_x, out_y
 
     def gradient(self, f, spacings, out=None):
-        """(df/dx, df/dy, df/dz) with spacings = (dx, dy, dz): x and y in one launch, z in a second."""
+        """(df/dx, df/dy, df/dz) with spacings = (dx, dy, dz): x and y in one launch, z in a second one on a side
+        stream of the library (cfd_apply_xyz: forked and joined with events, ordered on the current stream)."""
+        import torch
         dx, dy, dz = spacings
-        out = (None, None, None) if out is None else out
-        gx, gy = self.dfdxy(f, dx, dy, out[0], out[1])
-        gz = self.dfdz(f, dz, out[2])
-        return gx, gy, gz
+        assert f.is_cuda and f.dtype == torch.float64 and f.is_contiguous() and tuple(f.shape) == self.shape
+        out = [torch.empty_like(f) if o is None else o for o in (out if out is not None else (None, None, None))]
+        if self.part != (0, 1):
+            gx, gy = self.dfdxy(f, dx, dy, out[0], out[1])
+            return gx, gy, self.dfdz(f, dz, out[2])
+        px, py, pz = self._plan(0, float(dx)), self._plan(1, float(dy)), self._plan(2, float(dz))
+        check(lib().cfd_apply_xyz(px.handle, py.handle, pz.handle, f.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                  out[2].data_ptr(), _stream_ptr(f)))
+        return tuple(out)
 
     # reference spellings (code/ocl/compact.py:26,41,52; code/cuda/compact.py:29)
     def dfdx(self, f, dx=None, out=None, f_local=None):

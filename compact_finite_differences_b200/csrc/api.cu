@@ -452,6 +452,9 @@ struct cfd_plan {
     double xy_active = -1.0;
     int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
     double w_lo = 0.0, w_hi = 0.0;    // d(lo face)/d f[-1], d(hi face)/d f[n]: cfd_reduced_unknowns_deferred
+    // cfd_apply_xyz (axis-2 plans): side stream of the d/dz launch and the fork / join events
+    cudaStream_t gside = nullptr;
+    cudaEvent_t gev_fork = nullptr, gev_join = nullptr;
 };
 
 struct nt_plan {
@@ -833,6 +836,9 @@ extern "C" void cfd_destroy(cfd_plan *p)
     cudaFree(p->d_x_uh); cudaFree(p->d_x_lh); cudaFree(p->d_lu); cudaFree(p->d_lu_nb);
     cudaFree(p->d_f); cudaFree(p->d_df); cudaFree(p->d_xy_order);
     if (p->hstream) cudaStreamDestroy(p->hstream);
+    if (p->gside) cudaStreamDestroy(p->gside);
+    if (p->gev_fork) cudaEventDestroy(p->gev_fork);
+    if (p->gev_join) cudaEventDestroy(p->gev_join);
     if (p->hcopy) cudaStreamDestroy(p->hcopy);
     if (p->hback) cudaStreamDestroy(p->hback);
     for (auto e : p->hev) if (e) cudaEventDestroy(e);
@@ -1326,6 +1332,53 @@ extern "C" int cfd_apply_xy(cfd_plan *px, cfd_plan *py, const double *f, double 
         case 4: return launch_xy<4>(px, py, mx, my, nitems, (cudaStream_t)stream);
         default: return fail(CFD_EINVAL, "cfd_apply_xy: ring slots must be 3 or 4");
     }
+}
+
+// The whole gradient of an unpartitioned field: the fused d/dx + d/dy launch on the caller's stream and the d/dz launch
+// on a plan-owned side stream, forked and joined with events.  The three results are independent (out of place, same
+// input), and both kernels are persistent with one CTA per SM: run one after the other each pays its own ramp-up and
+// the tail of its dynamic draw (warps running dry within one bundle-time of each other); on two streams the second
+// kernel's CTAs take over the SMs one by one as the first one's CTAs retire.
+extern "C" int cfd_apply_xyz(cfd_plan *px, cfd_plan *py, cfd_plan *pz, const double *f, double *dfdx, double *dfdy,
+                             double *dfdz, void *stream)
+{
+    if (!px || !py || !pz || !f || !dfdx || !dfdy || !dfdz) return fail(CFD_EINVAL, "NULL argument");
+    if (pz->g.axis != 2 || pz->size != 1) return fail(CFD_EINVAL, "plan_z must be an unpartitioned axis-2 plan");
+    if (pz->g.nz != px->g.nz || pz->g.ny != px->g.ny || pz->g.nx != px->g.nx) return fail(CFD_EINVAL, "plans are for different shapes");
+    if (dfdz == dfdx || dfdz == dfdy || dfdz == f) return fail(CFD_EINVAL, "f and the three derivatives must be four different fields");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (!pz->gside && cs == cudaStreamCaptureStatusNone && !getenv("CFD_XYZ_SERIAL")) {
+        if (cudaStreamCreateWithFlags(&pz->gside, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pz->gev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pz->gev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (pz->gside) { cudaStreamDestroy(pz->gside); pz->gside = nullptr; }
+        }
+    }
+    // Measured (scripts/time_gradient.py, profiles/r2k_time_gradient_two_streams.txt): 128^3 0.0355 -> 0.0317 ms,
+    // 256^3 0.137 -> 0.129, 512^3 0.878 -> 0.862, but 1024^3 7.19 -> 7.36: beyond 2^27 points ramp-up and tail are noise
+    // and the late starters disturb the x/y wavefront -- large fields keep one stream.
+    const bool large = (long)pz->g.nz * pz->g.ny * pz->g.nx > (1L << 27) && !getenv("CFD_XYZ_TWO_STREAMS");
+    if (large || !pz->gside || !pz->gev_fork || !pz->gev_join || getenv("CFD_XYZ_SERIAL")) {     // one stream: x/y, then z
+        int rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+        return rc ? rc : cfd_apply(pz, f, dfdz, nullptr, nullptr, stream);
+    }
+    CUDA_TRY(cudaEventRecord(pz->gev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(pz->gside, pz->gev_fork, 0));
+    int rc;
+    if (getenv("CFD_XYZ_XY_FIRST")) {
+        rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+        if (!rc) rc = cfd_apply(pz, f, dfdz, nullptr, nullptr, pz->gside);
+    } else {
+        rc = cfd_apply(pz, f, dfdz, nullptr, nullptr, pz->gside);
+        if (!rc) rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+    }
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(pz->gev_join, pz->gside));
+    CUDA_TRY(cudaStreamWaitEvent(st, pz->gev_join, 0));
+    return CFD_OK;
 }
 
 extern "C" int cfd_edge_faces(cfd_plan *p, const double *f, const double *halo_lo, const double *halo_hi,

@@ -88,6 +88,12 @@ int cfd_apply(cfd_plan *plan, const double *f, double *df, const double *halo_lo
  * that every tile of f comes from HBM once and from L2 the second time.  Replaces two dfdx / dfdy calls of the
  * reference (code/ocl/compact.py:26-50).  Falls back to two launches when ny is not a multiple of 32. */
 int cfd_apply_xy(cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy, void *stream);
+/* d/dx, d/dy and d/dz of the same unpartitioned field (plans for axes 0, 1, 2 of the same shape): cfd_apply_xy on
+ * `stream` and the d/dz launch on a side stream owned by plan_z, forked and joined with events, so that the second
+ * kernel's CTAs take over the SMs as the first one's retire instead of each launch paying its own ramp-up and tail.
+ * On return everything is ordered on `stream` as if the three launches had been issued there. */
+int cfd_apply_xyz(cfd_plan *plan_x, cfd_plan *plan_y, cfd_plan *plan_z, const double *f, double *dfdx, double *dfdy,
+                  double *dfdz, void *stream);
 /* Warps per SM of that launch for an axis-0 plan (0 = default 6).  5 leaves room on the SMs for kernels that run
  * beside it on another stream, e.g. the exchange chain of a partitioned d/dz started before it. */
 int cfd_plan_set_xy_warps(cfd_plan *plan_x, int warps_per_sm);

@@ -268,6 +268,38 @@ def test_fused_xy_512_cubed_matches_separate_launches(C):
     assert torch.equal(gy, s.dfdy(f, 0.2))
 
 
+def test_gradient_two_streams_is_bit_equal_and_capturable(C, monkeypatch):
+    """gradient() = cfd_apply_xyz: d/dz on a side stream of the library, forked / joined with events; same bits as the
+    one-stream sequence, correct when called back to back on changing inputs, and capturable into a CUDA graph."""
+    import torch
+    rng = np.random.default_rng(77)
+    shape = (40, 64, 96)
+    hs = (0.1, 0.2, 0.3)
+    s = C.CompactFiniteDifferenceSolver(shape)
+    fs = [dev(rng.random(shape)) for _ in range(3)]
+    monkeypatch.setenv("CFD_XYZ_SERIAL", "1")
+    refs = [[o.clone() for o in s.gradient(f, hs)] for f in fs]
+    monkeypatch.delenv("CFD_XYZ_SERIAL")
+    out = [torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(3)]
+    for rep in range(3):
+        for f, ref in zip(fs, refs):
+            s.gradient(f, hs, out)
+            chk = [o.clone() for o in out]            # ordered on the current stream: the join event has been waited on
+            assert all(torch.equal(a, b) for a, b in zip(chk, ref))
+    for a in range(3):
+        assert relinf(refs[0][a].cpu().numpy(), O.derivative(fs[0].cpu().numpy(), a, hs[a])) <= TOL
+    st = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(graph, stream=st):
+        s.gradient(fs[1], hs, out)
+    for o in out:
+        o.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(out, refs[1]))
+
+
 def test_fused_xy_rejects_bad_arguments(C):
     import torch
     f = torch.rand((4, 32, 32), dtype=torch.float64, device="cuda")
