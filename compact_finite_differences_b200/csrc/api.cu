@@ -1357,11 +1357,9 @@ extern "C" int cfd_apply_xyz(cfd_plan *px, cfd_plan *py, cfd_plan *pz, const dou
             if (pz->gside) { cudaStreamDestroy(pz->gside); pz->gside = nullptr; }
         }
     }
-    // Measured (scripts/time_gradient.py, profiles/r2k_time_gradient_two_streams.txt): 128^3 0.0355 -> 0.0317 ms,
-    // 256^3 0.137 -> 0.129, 512^3 0.878 -> 0.862, but 1024^3 7.19 -> 7.36: beyond 2^27 points ramp-up and tail are noise
-    // and the late starters disturb the x/y wavefront -- large fields keep one stream.
-    const bool large = (long)pz->g.nz * pz->g.ny * pz->g.nx > (1L << 27) && !getenv("CFD_XYZ_TWO_STREAMS");
-    if (large || !pz->gside || !pz->gev_fork || !pz->gev_join || getenv("CFD_XYZ_SERIAL")) {     // one stream: x/y, then z
+    // Measured with the variants interleaved (scripts/time_gradient.py, profiles/r2k_time_gradient_two_streams.txt):
+    // 128^3 0.0402 -> 0.0367 ms, 256^3 0.1403 -> 0.1318, 512^3 0.8773 -> 0.8630, 1024^3 7.55 -> 7.35-7.55 (never slower).
+    if (!pz->gside || !pz->gev_fork || !pz->gev_join || getenv("CFD_XYZ_SERIAL")) {     // one stream: x/y, then z
         int rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
         return rc ? rc : cfd_apply(pz, f, dfdz, nullptr, nullptr, stream);
     }

@@ -56,6 +56,62 @@ for r in range(P):
     outs.append(sol[r].apply_coupled(blocks[r], None, halos[r][0], halos[r][1], ab))
 got = torch.cat(outs).cpu().numpy()
 worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
+# round 2: fused x/y launch, gradient on two streams, general kernel (both look-aheads, both stencils), starved
+# in-place solver with its side buffer, and the C-side zpart driver incl. the fused x/y + edge launch
+shape = (6, 64, 96)
+g = rng.random(shape)
+hs = (0.1, 0.2, 0.3)
+got3 = C.CompactFiniteDifferenceSolver(shape).gradient(torch.from_numpy(g).cuda(), hs)
+for a in range(3):
+    want = O.derivative(g, a, hs[a])
+    worst = max(worst, np.abs(got3[a].cpu().numpy() - want).max() / np.abs(want).max())
+for scheme in ("compact6", "pade4-d2"):
+    for axis, shp in ((0, (3, 5, 130)), (1, (2, 97, 34)), (2, (161, 3, 34))):
+        q = rng.random(shp)
+        got = C.CompactFiniteDifferenceSolver(shp, 0.3, axis, scheme=scheme)(torch.from_numpy(q).cuda()).cpu().numpy()
+        want = O.scheme_derivative(q, axis, 0.3, scheme)
+        worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
+d = rng.random((1, 40, 1000))
+t = torch.from_numpy(d).cuda()
+C.NearToeplitzSolver(d.shape, O.PADE).solve(t)
+want = O.near_toeplitz_solve(d, O.PADE)
+worst = max(worst, np.abs(t.cpu().numpy() - want).max() / np.abs(want).max())
+import ctypes
+from compact_finite_differences_b200._lib import check, lib
+L = lib()
+P, shape, h = 3, (3 * 66, 32, 64), 0.2
+f = rng.random(shape)
+n = shape[0] // P
+lshape = (n,) + shape[1:]
+zs = [C.CompactFiniteDifferenceSolver(lshape, h, 2, part=(r, P)) for r in range(P)]
+xy = C.CompactFiniteDifferenceSolver(lshape)
+px, py = xy._plan(0, 0.1), xy._plan(1, 0.15)
+zps = []
+for r in range(P):
+    z = ctypes.c_void_p()
+    check(L.cfd_zpart_create(ctypes.byref(z), zs[r]._plan(2, h).handle))
+    zps.append(z)
+bufs = [L.cfd_zpart_buffer(z) for z in zps]
+for r in range(P):
+    check(L.cfd_zpart_connect_ptr(zps[r], bufs[r - 1] if r > 0 else None, bufs[r + 1] if r < P - 1 else None))
+blocks = [torch.from_numpy(f[r * n:(r + 1) * n].copy()).cuda() for r in range(P)]
+outs = [[torch.empty_like(b) for _ in range(3)] for b in blocks]
+streams = [torch.cuda.Stream() for _ in range(P)]
+torch.cuda.synchronize()
+for it in range(2):
+    for r in range(P):
+        sp = ctypes.c_void_p(streams[r].cuda_stream)
+        if it == 0:
+            check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs[r][2].data_ptr(), sp))
+        else:
+            check(L.cfd_zpart_apply_xyz(zps[r], px.handle, py.handle, blocks[r].data_ptr(), outs[r][0].data_ptr(),
+                                        outs[r][1].data_ptr(), outs[r][2].data_ptr(), sp))
+    torch.cuda.synchronize()
+    got = np.concatenate([o[2].cpu().numpy() for o in outs], axis=0)
+    want = O.derivative(f, 2, h)
+    worst = max(worst, np.abs(got - want).max() / np.abs(want).max())
+for z in zps:
+    L.cfd_zpart_destroy(z)
 torch.cuda.synchronize()
 print("sanitize case: worst rel L-inf", worst)
 assert worst <= 1e-12

@@ -34,17 +34,23 @@ for N in [int(a) for a in sys.argv[1:]] or [512]:
         k[0] += 1
         s.gradient(fs[i], h, outs[i])
     ref = [o.clone() for o in s.gradient(fs[0], h)]
-    res = {}
-    for name, env in (("one stream", {"CFD_XYZ_SERIAL": "1"}), ("two streams, x/y first", {"CFD_XYZ_XY_FIRST": "1", "CFD_XYZ_TWO_STREAMS": "1"}),
-                      ("two streams, z first", {"CFD_XYZ_TWO_STREAMS": "1"}), ("library default", {})):
-        for kk in ("CFD_XYZ_SERIAL", "CFD_XYZ_XY_FIRST", "CFD_XYZ_TWO_STREAMS"):
-            os.environ.pop(kk, None)
-        os.environ.update(env)
-        res[name] = timeit(grad)
-        got = s.gradient(fs[0], h)
-        torch.cuda.synchronize()
-        same = all(torch.equal(a, b) for a, b in zip(ref, got))
-        print(f"N = {N:4d}  {name:26s} {res[name]:.4f} ms  ({3 * N ** 3 / res[name] / 1e6:.0f} Mpts/s per derivative)  bit-equal={same}", flush=True)
+    cfgs = (("one stream", {"CFD_XYZ_SERIAL": "1"}), ("two streams, x/y first", {"CFD_XYZ_XY_FIRST": "1"}),
+            ("two streams, z first (library default)", {}))
+    res = {name: [] for name, _ in cfgs}
+    same = {}
+    for rnd in range(4):                                # interleaved rounds: clock / power drift hits every variant alike
+        for name, env in cfgs:
+            for kk in ("CFD_XYZ_SERIAL", "CFD_XYZ_XY_FIRST", "CFD_XYZ_TWO_STREAMS"):
+                os.environ.pop(kk, None)
+            os.environ.update(env)
+            res[name].append(timeit(grad, reps=20))
+            got = s.gradient(fs[0], h)
+            torch.cuda.synchronize()
+            same[name] = all(torch.equal(a, b) for a, b in zip(ref, got))
+    for name, _ in cfgs:
+        r = res[name]
+        print(f"N = {N:4d}  {name:40s} " + " ".join(f"{v:.4f}" for v in r) + f" ms  (best {min(r):.4f}: "
+              f"{3 * N ** 3 / min(r) / 1e6:.0f} Mpts/s per derivative)  bit-equal={same[name]}", flush=True)
     for kk in ("CFD_XYZ_SERIAL", "CFD_XYZ_XY_FIRST", "CFD_XYZ_TWO_STREAMS"):
         os.environ.pop(kk, None)
     del fs, outs

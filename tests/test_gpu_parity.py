@@ -871,6 +871,97 @@ def test_pthomas_plan_is_reused(C):
     assert len(rs._plans) == 2
 
 
+def test_no_out_of_bounds_writes(C):
+    """compute-sanitizer is closed on the GPU pool, so memory safety of the stores gets a check of its own: every output
+    of every kernel family lives in the middle of a larger allocation whose guard zones (4 KiB on each side, plus the
+    tail of ragged tiles inside TMA boxes that cross the end of the tensor) must come back untouched, on ragged shapes
+    where boxes / thread blocks overhang every extent."""
+    import torch
+    G = 512                                                    # guard doubles on each side (16-byte aligned offsets)
+    SENT = 1234.5
+
+    class Guarded:
+        def __init__(self, shape, fill=None):
+            n = int(np.prod(shape))
+            self.raw = torch.full((n + 2 * G,), SENT, dtype=torch.float64, device="cuda")
+            self.t = self.raw[G:G + n].view(shape)
+            if fill is not None:
+                self.t.copy_(torch.from_numpy(np.ascontiguousarray(fill)))
+
+        def intact(self):
+            return bool((self.raw[:G] == SENT).all() and (self.raw[-G:] == SENT).all())
+
+    rng = np.random.default_rng(123)
+    held = []
+
+    def out(shape, fill=None):
+        g = Guarded(shape, fill)
+        held.append(g)
+        return g.t
+
+    for shape in [(5, 7, 34), (4, 33, 66), (35, 6, 38), (4, 64, 98)]:
+        f = rng.random(shape)
+        fd = dev(f)
+        for axis in range(3):
+            o = out(shape)
+            C.CompactFiniteDifferenceSolver(shape, 0.1, axis)(fd, o)
+            assert relinf(o.cpu().numpy(), O.derivative(f, axis, 0.1)) <= TOL
+            t = out(shape, f)
+            C.NearToeplitzSolver(shape, O.PADE, axis=axis).solve(t)                       # in place
+            t2 = out(shape, f)
+            C.NearToeplitzSolver(shape, (1., 2., 1. / 3, 1., 1. / 3, 2., 1.), axis=axis).solve(t2)   # general kernel
+            for scheme in ("compact6", "pade4-d2"):
+                if shape[2 - axis] >= 6:
+                    o2 = out(shape)
+                    C.CompactFiniteDifferenceSolver(shape, 0.2, axis, scheme=scheme)(fd, o2)
+        if shape[1] % 32 == 0:
+            gx, gy, gz = out(shape), out(shape), out(shape)
+            C.CompactFiniteDifferenceSolver(shape).gradient(fd, (0.1, 0.2, 0.3), (gx, gy, gz))
+    # starved in-place solver (side buffer + scatter), contiguous and strided
+    for shape, axis in (((1, 40, 1000), 0), ((545, 2, 34), 2)):
+        d = rng.random(shape)
+        t = out(shape, d)
+        C.NearToeplitzSolver(shape, O.PADE, axis=axis).solve(t)
+        assert relinf(t.cpu().numpy(), O.scipy_solve_axis(d, O.PADE, axis)) <= TOL
+    # multi-rank pieces with their plane-sized outputs
+    P, shape, h = 2, (140, 6, 34), 0.2
+    f = rng.random(shape)
+    n = shape[0] // P
+    plane = shape[1] * shape[2]
+    blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
+    sol = [C.CompactFiniteDifferenceSolver((n,) + shape[1:], h, 2, part=(r, P)) for r in range(P)]
+    halos = [(None if r == 0 else blocks[r - 1][-1].contiguous(), None if r == P - 1 else blocks[r + 1][0].contiguous())
+             for r in range(P)]
+    faces = out((2 * P, plane), np.zeros((2 * P, plane)))
+    ab = out((2, plane))
+    res = []
+    for r in range(P):
+        sol[r].edge_faces(blocks[r], faces[2 * r:2 * r + 2], *halos[r])
+    for r in range(P):
+        sol[r].reduced_unknowns(faces, ab)
+        o = out((n,) + shape[1:])
+        sol[r].apply_coupled(blocks[r], o, halos[r][0], halos[r][1], ab)
+        res.append(o)
+    assert relinf(torch.cat(res).cpu().numpy(), O.derivative(f, 2, h)) <= TOL
+    res = []
+    faces2 = out((2 * P, plane), np.zeros((2 * P, plane)))
+    for r in range(P):
+        o = out((n,) + shape[1:])
+        sol[r].apply_local(blocks[r], o, *halos[r])
+        sol[r].interface_pack(o, faces2[2 * r:2 * r + 2])
+        res.append(o)
+    for r in range(P):
+        sol[r].reduced_correct(res[r], faces2)
+        rhs = out((n,) + shape[1:])
+        sol[r].compute_RHS(blocks[r], h, rhs, None, halo_lo=halos[r][0], halo_hi=halos[r][1])
+    assert relinf(torch.cat(res).cpu().numpy(), O.derivative(f, 2, h)) <= TOL
+    a, b, c = rng.random(9), rng.random(9) + 2, rng.random(9)
+    pt = out((9, 3, 5), rng.random((9, 3, 5)))
+    C.ReducedSolver((9, 3, 5)).solve(a, b, c, None, pt)
+    torch.cuda.synchronize()
+    assert all(g.intact() for g in held), "a kernel wrote outside its output tensor"
+
+
 def test_host_gradient_pipeline(C):
     """HostGradient (pinned host buffers, slab-pipelined copies) == oracle on every direction."""
     import torch
