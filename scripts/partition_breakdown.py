@@ -39,7 +39,14 @@ def timed(name, fn, reps=10):
 
 plain = C.CompactFiniteDifferenceSolver((nl, N, N), h, 2)
 timed("single-rank kernel on the slab (no coupling)", lambda: plain(f, out))
-for comm in ("nvlink", "pairwise", "allgather"):
+opn = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm="nvlink")
+opn(f, out)
+timed("[nvlink] exchange chain only (cfd_zpart_begin)", lambda: opn._zp.begin(f))
+timed("[nvlink] full d/dz (cfd_zpart_apply)", lambda: opn(f, out))
+g3 = [torch.empty_like(f) for _ in range(3)]
+timed("[nvlink] slab gradient, three launches (cfd_zpart_apply_xyz)", lambda: opn.gradient(f, h, h, g3))
+del g3
+for comm in ("pairwise", "allgather"):
     op = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm=comm)
     op(f, out)
     res = op._exchange(f)
@@ -55,25 +62,6 @@ timed("NCCL interface send/recv", lambda: exchange_interface_planes(faces_nb, ow
 timed("NCCL interface all-gather", lambda: gather_interface_planes(faces, world, None, faces_all))
 timed("reduced_unknowns kernel (neighbour-only)", lambda: op.solver.reduced_unknowns(faces_nb, op._ab, neighbours_only=True))
 timed("reduced_unknowns kernel (all 2P planes)", lambda: op.solver.reduced_unknowns(faces_all, op._ab))
-if world > 1:
-    import ctypes
-    from compact_finite_differences_b200._lib import check, lib
-    opn = C.ZPartitionedDerivative((nl, N, N), h, 2, mode="fused", comm="nvlink")
-    opn(f, out)
-    px = opn._peer
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    left, right = (rank - 1 if rank > 0 else None), (rank + 1 if rank < world - 1 else None)
-
-    def push_wait():
-        px.seq += 1
-        seq, par = px.seq, px.seq & 1
-        check(lib().cfd_push_planes(
-            f[0].data_ptr() if left is not None else None, px.halo(left, par, 1) if left is not None else None,
-            f[-1].data_ptr() if right is not None else None, px.halo(right, par, 0) if right is not None else None,
-            N * N, px.flag(left, 1) if left is not None else None, px.flag(right, 0) if right is not None else None,
-            seq, st))
-        check(lib().cfd_wait_flags(px.flag(rank, 0) if left is not None else None,
-                                   px.flag(rank, 1) if right is not None else None, seq, st))
-    timed("NVLink halo push + flag wait", push_wait)
 dist.barrier()
+opn.close()
 dist.destroy_process_group()
