@@ -49,6 +49,7 @@ SIGNATURES = {
     "cfd_zpart_connect": (_i, [_vp, _vp, _vp]),
     "cfd_zpart_buffer": (_vp, [_vp]),
     "cfd_zpart_connect_ptr": (_i, [_vp, _vp, _vp]),
+    "cfd_zpart_set_ctas": (_i, [_vp, _i]),
     "cfd_zpart_begin": (_i, [_vp, _vp, _vp]),
     "cfd_zpart_apply": (_i, [_vp, _vp, _vp, _vp]),
     "cfd_zpart_apply_xyz": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

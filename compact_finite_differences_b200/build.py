@@ -7,8 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "api.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", n) for n in ("kernels.cuh", "kernels_xy.cuh", "tables.h")] + \
-    [os.path.join(HERE, "..", "include", "cfd_b200.h")]
+DEPS = SRC + [os.path.join(HERE, "csrc", n) for n in sorted(os.listdir(os.path.join(HERE, "csrc")))
+              if n.endswith((".cuh", ".h"))] + [os.path.join(HERE, "..", "include", "cfd_b200.h")]
 OUT = os.path.join(HERE, "libcfd_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "kernels_xy.cuh"
 #include "kernels_general.cuh"
+#include "kernels_zx.cuh"
 
 using namespace cfd;
 
@@ -1864,6 +1865,8 @@ extern "C" int cfd_pthomas(const double *a, const double *b, const double *c, do
 //     halo  [2 parities][2][plane]   slot 0: last plane of rank-1, slot 1: first plane of rank+1
 //     faces [2 parities][6][plane]   the neighbour-only interface planes (cfd_reduced_unknowns layout)
 //     flags [16] (uint64)            2 / 3: the left / right neighbour's faces + halo of call `seq` have landed
+//     ll    [2 parities][4][plane]   (16-byte words) receive arrays of the one-kernel path (kernels_zx.cuh): 0 / 1 = the left
+//                                    neighbour's hi face / last row, 2 / 3 = the right neighbour's lo face / first row
 // The parity is seq & 1 and flags only grow, so nothing is ever reset and no global barrier exists: a neighbour can
 // be at most one call ahead (its call s+1 needs our producer launch of call s+1, which is stream-ordered after our
 // consumer of call s), and then it writes the other parity.
@@ -1880,15 +1883,48 @@ struct cfd_zpart {
     bool applied = false, pending = false;
     const double *pending_f = nullptr;
     cudaStream_t pending_stream = nullptr;
+    int max_ctas = 0;                 // 0 = one CTA per SM; tests that keep several ranks on ONE device lower it
     double *halo(double *base, int par, int slot) const { return base + (long)(par * 2 + slot) * plane; }
+    ulonglong2 *ll(double *base, int par, int i) const
+    { return reinterpret_cast<ulonglong2 *>(base + 16 * plane + 16) + (long)(par * 4 + i) * plane; }
     double *faces(double *base, int par, int i) const { return base + 4 * plane + (long)(par * 6 + i) * plane; }
     unsigned long long *flag(double *base, int k) const { return reinterpret_cast<unsigned long long *>(base + 16 * plane) + k; }
 };
+
+// With lazy module loading (the CUDA default) the FIRST launch of a kernel loads its code, and that load can need the
+// device to go idle.  A process that drives several ranks of a line on one device (tests, smoke) would then hang until
+// the time-out: rank 0's consumer kernel spins for data that rank 1's producer -- whose first launch is stuck loading --
+// never gets to store.  Every kernel the partitioned paths launch is therefore loaded when the first zpart is created.
+static void preload_zpart_kernels()
+{
+    static bool done = false;
+    if (done) return;
+    cudaFuncAttributes at;
+    cudaFuncGetAttributes(&at, edge_faces_kernel);
+    cudaFuncGetAttributes(&at, reduced_planes_kernel);
+    cudaFuncGetAttributes(&at, reduced_planes_deferred_kernel);
+    cudaFuncGetAttributes(&at, push_planes_kernel);
+    cudaFuncGetAttributes(&at, wait_flags_kernel);
+    cudaFuncGetAttributes(&at, stream_kernel<false, true, 3>);
+    cudaFuncGetAttributes(&at, stream_kernel<false, true, 4>);
+    cudaFuncGetAttributes(&at, stream_kernel<false, true, 5>);
+    cudaFuncGetAttributes(&at, stream_kernel<true, true, 3>);
+    cudaFuncGetAttributes(&at, stream_kernel_zx<4>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<4, false, false>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<4, true, false>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<4, false, true>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<4, true, true>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<3, false, false>);
+    cudaFuncGetAttributes(&at, stream_kernel_xy<3, true, false>);
+    cudaGetLastError();
+    done = true;
+}
 
 extern "C" int cfd_zpart_create(cfd_zpart **out, cfd_plan *plan)
 {
     if (!out || !plan) return fail(CFD_EINVAL, "NULL argument");
     *out = nullptr;
+    preload_zpart_kernels();
     if (plan->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: nothing to exchange");
     if (plan->g.axis != 2) return fail(CFD_EUNSUPPORTED, "cfd_zpart serves lines along z (contiguous boundary planes)");
     if (plan->g.n < 2 * CH + 2)
@@ -1897,7 +1933,7 @@ extern "C" int cfd_zpart_create(cfd_zpart **out, cfd_plan *plan)
     cfd_zpart *z = new cfd_zpart();
     z->plan = plan;
     z->plane = plan->g.nlines;
-    const size_t bytes = (size_t)(16 * z->plane + 16) * sizeof(double);
+    const size_t bytes = (size_t)(32 * z->plane + 16) * sizeof(double);
     if (cudaMalloc(&z->buf, bytes) != cudaSuccess || cudaMemset(z->buf, 0, bytes) != cudaSuccess ||
         cudaMalloc(&z->ab, (size_t)2 * z->plane * sizeof(double)) != cudaSuccess ||
         cudaEventCreateWithFlags(&z->ev_begin, cudaEventDisableTiming) != cudaSuccess ||
@@ -2016,6 +2052,75 @@ static int zpart_ptrs(cfd_zpart *z, unsigned long long seq, ZPtrs &q)
     return CFD_OK;
 }
 
+extern "C" int cfd_zpart_set_ctas(cfd_zpart *z, int max_ctas)
+{
+    if (!z || max_ctas < 0) return fail(CFD_EINVAL, "bad argument");
+    z->max_ctas = max_ctas;
+    return CFD_OK;
+}
+
+// The partitioned d/dz in ONE launch (kernels_zx.cuh): edge faces, exchange, reduced system and coupled solve per bundle.
+static int launch_zx(cfd_zpart *z, const double *f, double *df, unsigned long long seq, cudaStream_t stream)
+{
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
+    cfd_plan *p = z->plan;
+    const bool has_lo = p->rank > 0, has_hi = p->rank < p->size - 1;
+    if ((has_lo && !z->peer[0]) || (has_hi && !z->peer[1]))
+        return fail(CFD_EINVAL, "cfd_zpart: neighbours are not connected (cfd_zpart_connect)");
+    MapPair mp;
+    int rc = get_maps(p->cache, p->g, f, df, mp);
+    if (rc) return rc;
+    KParams kp = p->kp;
+    kp.halo_lo = kp.halo_hi = kp.ab = nullptr;
+    kp.nlines = p->g.nlines;
+    kp.kseg = p->g.K; kp.nseg = 1;
+    ZXParams q;
+    memset(&q, 0, sizeof q);
+    const int par = (int)(seq & 1);
+    q.in_face_lo = z->ll(z->buf, par, 0); q.in_halo_lo = z->ll(z->buf, par, 1);
+    q.in_face_hi = z->ll(z->buf, par, 2); q.in_halo_hi = z->ll(z->buf, par, 3);
+    if (has_lo) { q.out_face_lo = z->ll(z->peer[0], par, 2); q.out_halo_lo = z->ll(z->peer[0], par, 3); }
+    if (has_hi) { q.out_face_hi = z->ll(z->peer[1], par, 0); q.out_halo_hi = z->ll(z->peer[1], par, 1); }
+    q.tag = (unsigned int)(seq & 0xffffffffULL);
+    if (q.tag == 0) q.tag = 0x80000000u;                  // 0 is what a fresh buffer holds
+    q.pv = p->nb_pv; q.own = p->nb_own;
+    q.w_lo = p->w_lo; q.w_hi = p->w_hi;
+    q.sk_last = p->kp.tail.sk[p->g.jl]; q.l_last = p->kp.tail.l[p->g.jl];
+    if (p->lu_nb.size() > 36) return fail(CFD_EINVAL, "internal: neighbour table too large");
+    for (size_t i = 0; i < p->lu_nb.size(); i++) q.lu[i] = p->lu_nb[i];
+    q.wait = wait_params();
+    q.hints = 7;
+    if (const char *e = getenv("CFD_ZX_HINTS")) q.hints = atoi(e);
+    constexpr int NS = 4;
+    constexpr int per_warp = NS * SLOT_BYTES + NS * 16;
+    int warps = g_warps ? g_warps : 7;
+    if (const char *e = getenv("CFD_ZX_WARPS")) warps = atoi(e) > 0 ? atoi(e) : warps;
+    if (warps > 7) warps = 7;
+    const long per_sm = (p->g.nb + dinfo.sms - 1) / dinfo.sms;
+    if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    const size_t smem = (size_t)warps * per_warp + 1024;
+    auto kern = stream_kernel_zx<NS>;
+    static size_t configured[MAX_DEVICES] = {0};
+    int dev = 0;
+    rc = current_device(dev);
+    if (rc) return rc;
+    if (configured[dev] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * per_warp + 1024));
+        configured[dev] = 7 * per_warp + 1024;
+    }
+    rc = counter_pair(&kp.counter, stream, &p->pool);
+    if (rc) return rc;
+    long blocks = (p->g.nb + warps - 1) / warps;
+    if (blocks > dinfo.sms) blocks = dinfo.sms;
+    if (z->max_ctas > 0 && blocks > z->max_ctas) blocks = z->max_ctas;
+    CUDA_TRY(launch_k(kern, (unsigned)blocks, warps * 32, smem, stream, mp.tm_in, mp.tm_out, kp, q));
+    g_launches++;
+    return CFD_OK;
+}
+
+static bool zx_enabled() { return getenv("CFD_NO_ZX") == nullptr; }
+
 extern "C" int cfd_zpart_begin(cfd_zpart *z, const double *f, void *stream)
 {
     if (!z || !f) return fail(CFD_EINVAL, "NULL argument");
@@ -2046,7 +2151,22 @@ extern "C" int cfd_zpart_begin(cfd_zpart *z, const double *f, void *stream)
 extern "C" int cfd_zpart_apply(cfd_zpart *z, const double *f, double *df, void *stream)
 {
     if (!z || !f || !df) return fail(CFD_EINVAL, "NULL argument");
+    if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!(z->pending && z->pending_f == f) && zx_enabled()) {
+        // nothing was begun early: the whole partitioned derivative is one launch
+        int rc = cfd_async_status();
+        if (rc) return rc;
+        if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+        if (z->pending && z->pending_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_begin, 0));
+        z->pending = false;
+        rc = launch_zx(z, f, df, z->seq + 1, st);
+        if (rc) return rc;
+        ++z->seq;
+        CUDA_TRY(cudaEventRecord(z->ev_apply, st));
+        z->applied = true;
+        return CFD_OK;
+    }
     if (!(z->pending && z->pending_f == f)) {
         int rc = cfd_zpart_begin(z, f, stream);
         if (rc) return rc;
@@ -2079,6 +2199,10 @@ extern "C" int cfd_zpart_apply_xyz(cfd_zpart *z, cfd_plan *px, cfd_plan *py, con
         return fail(CFD_EINVAL, "f and the three derivatives must be four different fields");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    if (zx_enabled()) {                                // two launches: the plain x/y launch, the one-kernel d/dz
+        rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+        return rc ? rc : cfd_zpart_apply(z, f, dfdz, stream);
+    }
     if (!xy_eligible(px->g) || getenv("CFD_NO_XY") || getenv("CFD_NO_XY_EDGE") || (g_slots && g_slots != 4)) {
         rc = cfd_zpart_begin(z, f, stream);            // separate edge launch, then the x / y launch(es)
         if (!rc) rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);

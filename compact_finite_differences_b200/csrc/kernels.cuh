@@ -106,6 +106,33 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// L2 eviction-priority hints for tiles with a known future: evict_last = will be read again soon, evict_first = never.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2,
+                                                 unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -281,6 +281,7 @@ int cfd_zpart_export(cfd_zpart *zp, void *handle);
 int cfd_zpart_connect(cfd_zpart *zp, const void *handle_lo, const void *handle_hi);
 void *cfd_zpart_buffer(cfd_zpart *zp);
 int cfd_zpart_connect_ptr(cfd_zpart *zp, void *buffer_lo, void *buffer_hi);
+int cfd_zpart_set_ctas(cfd_zpart *zp, int max_ctas);   /* 0 = one CTA per SM (default); see below */
 int cfd_zpart_begin(cfd_zpart *zp, const double *f, void *stream);
 int cfd_zpart_apply(cfd_zpart *zp, const double *f, double *dfdz, void *stream);
 int cfd_zpart_apply_xyz(cfd_zpart *zp, cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy,

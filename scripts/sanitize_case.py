@@ -90,6 +90,7 @@ zps = []
 for r in range(P):
     z = ctypes.c_void_p()
     check(L.cfd_zpart_create(ctypes.byref(z), zs[r]._plan(2, h).handle))
+    check(L.cfd_zpart_set_ctas(z, 148 // P))
     zps.append(z)
 bufs = [L.cfd_zpart_buffer(z) for z in zps]
 for r in range(P):

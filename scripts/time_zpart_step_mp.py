@@ -29,8 +29,14 @@ xy = C.CompactFiniteDifferenceSolver((nzl, N, N))
 ddz = C.ZPartitionedDerivative((nzl, N, N), h, 2, mode="fused", comm="nvlink")
 
 
-def fused():
+def zx():
     ddz.gradient(f, h, h, out)
+
+
+def fused():
+    os.environ["CFD_NO_ZX"] = "1"
+    ddz.gradient(f, h, h, out)
+    os.environ.pop("CFD_NO_ZX")
 
 
 def chain(warps):
@@ -66,24 +72,25 @@ def timeit(name, fn):
               f"{3 * nzl * world * N * N / t.item() / 1e6:.0f} Mpts/s per derivative, whole job", flush=True)
 
 
-fused()
+zx()
 assert ddz.comm == "nvlink", ddz.comm
 if rank == 0:
     print(f"P = {world}, slab [{nzl}, {N}, {N}] per rank, {reps} reps")
 ref = None
 for rnd in range(2):
-    for name, fn in (("fused (cfd_zpart_apply_xyz)", fused), ("chain beside xy, 5 warps (round-1 step)", chain(5)),
+    for name, fn in (("zx: x/y launch + one-kernel d/dz (default)", zx), ("fused: edge items in the x/y kernel, 3 launches", fused),
+                     ("chain beside xy, 5 warps (round-1 step)", chain(5)),
                      ("chain beside xy, 6 warps", chain(6)), ("serial (edge+reduce, xy, z)", serial)):
         timeit(name, fn)
         torch.cuda.synchronize()
         if ref is None:
             ref = [o.clone() for o in out]
         else:
-            same = all(torch.equal(a, b) for a, b in zip(ref, out))
-            t = torch.tensor([1 if same else 0], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            if rank == 0 and t.item() == 0:
-                print("   RESULTS DIFFER from the fused step", flush=True)
+            worst = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(out, ref))
+            t = torch.tensor([worst], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0 and t.item() > 1e-13:
+                print(f"   RESULTS DIFFER from the first variant: rel {t.item():.2e}", flush=True)
 timeit("x/y launch alone (no exchange)", lambda: xy.dfdxy(f, h, h, out[0], out[1], warps=6))
 timeit("partitioned d/dz alone (cfd_zpart_apply)", lambda: ddz(f, out[2]))
 assert C.lib().cfd_async_status() == 0

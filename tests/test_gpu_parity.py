@@ -696,12 +696,14 @@ def test_one_launch_exchange_one_device(C, P, shape):
             assert relinf(got, want) <= 4 * relinf(whole, want) + 1e-15
 
 
-@pytest.mark.parametrize("P,shape", [(2, (132, 64, 96)), (3, (3 * 66, 32, 40)), (4, (4 * 70, 32, 64)), (2, (140, 12, 34))])
-def test_zpart_c_abi_one_process(C, P, shape):
+@pytest.mark.parametrize("P,shape", [(2, (132, 64, 96)), (3, (3 * 66, 32, 40)), (4, (4 * 70, 32, 64)), (2, (140, 12, 34)),
+                                     (3, (3 * 128, 64, 256))])
+def test_zpart_c_abi_one_process(C, P, shape, monkeypatch):
     """cfd_zpart_* (the C-side driver of the partitioned d/dz) with all P ranks in ONE process on one device: buffers
-    wired with cfd_zpart_connect_ptr, one stream per rank (a rank's consumer spins until its neighbours' producers,
-    enqueued later on other streams, have run).  cfd_zpart_apply (separate edge launch) and cfd_zpart_apply_xyz (edge
-    items inside the fused x/y kernel) against the oracle, and bit-equal to each other / to cfd_apply_xy."""
+    wired with cfd_zpart_connect_ptr, one stream per rank, CTA counts capped so that the P persistent kernels are
+    co-resident (a rank's phase B polls for what its neighbours' phase A, on another stream, stores).  Default path
+    (one-kernel d/dz, kernels_zx.cuh) and the three-launch path (CFD_NO_ZX: edge items inside the x/y kernel or a
+    separate edge launch, reduce, coupled kernel) against the oracle and against each other."""
     import ctypes
     import torch
     from compact_finite_differences_b200._lib import check, lib
@@ -717,6 +719,7 @@ def test_zpart_c_abi_one_process(C, P, shape):
     for r in range(P):
         h = ctypes.c_void_p()
         check(L.cfd_zpart_create(ctypes.byref(h), zsol[r]._plan(2, hs[2]).handle))
+        check(L.cfd_zpart_set_ctas(h, 148 // P))
         zps.append(h)
     bufs = [L.cfd_zpart_buffer(z) for z in zps]
     for r in range(P):
@@ -724,40 +727,51 @@ def test_zpart_c_abi_one_process(C, P, shape):
     assert L.cfd_zpart_connect_ptr(zps[0], bufs[1], bufs[1]) != 0        # rank 0 has no left neighbour
     streams = [torch.cuda.Stream() for _ in range(P)]
     zz, yy, xx = smooth(shape)
+
+    def run(kind, blocks, outs):
+        torch.cuda.synchronize()
+        for r in range(P):
+            sp = ctypes.c_void_p(streams[r].cuda_stream)
+            if kind == "begin+apply":
+                check(L.cfd_zpart_begin(zps[r], blocks[r].data_ptr(), sp))
+            if kind in ("apply", "begin+apply"):
+                check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs[r][2].data_ptr(), sp))
+            else:
+                check(L.cfd_zpart_apply_xyz(zps[r], px.handle, py.handle, blocks[r].data_ptr(), outs[r][0].data_ptr(),
+                                            outs[r][1].data_ptr(), outs[r][2].data_ptr(), sp))
+        torch.cuda.synchronize()
+        assert L.cfd_async_status() == 0
+
     try:
-        for it in range(5):
-            f = rng.random(shape) if it < 4 else 1e3 * (np.sin(zz) * np.cos(yy) + xx)
+        for it in range(4):
+            f = rng.random(shape) if it < 3 else 1e3 * (np.sin(zz) * np.cos(yy) + xx)
             want = [O.derivative(f, a, hs[a]) for a in range(3)]
             blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
-            outs = [[torch.empty_like(b) for _ in range(3)] for b in blocks]
-            torch.cuda.synchronize()
-            for r in range(P):
-                sp = ctypes.c_void_p(streams[r].cuda_stream)
-                if it % 2 == 0:
-                    if it == 2:                  # exchange begun early (on the rank's stream), then picked up
-                        check(L.cfd_zpart_begin(zps[r], blocks[r].data_ptr(), sp))
-                    check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs[r][2].data_ptr(), sp))
+            results = {}
+            for name, env, kind in (("zx apply", None, "apply"), ("zx xyz", None, "xyz"),
+                                    ("3-launch apply", "1", "apply"), ("3-launch xyz", "1", "xyz"),
+                                    ("begin + apply", None, "begin+apply")):
+                if env:
+                    monkeypatch.setenv("CFD_NO_ZX", env)
                 else:
-                    check(L.cfd_zpart_apply_xyz(zps[r], px.handle, py.handle, blocks[r].data_ptr(), outs[r][0].data_ptr(),
-                                                outs[r][1].data_ptr(), outs[r][2].data_ptr(), sp))
-            torch.cuda.synchronize()
-            assert L.cfd_async_status() == 0
-            gz = np.concatenate([o[2].cpu().numpy() for o in outs], axis=0)
-            assert relinf(gz, want[2]) <= TOL
-            if it % 2 == 1:
-                for a in (0, 1):
-                    ga = np.concatenate([o[a].cpu().numpy() for o in outs], axis=0)
-                    assert relinf(ga, want[a]) <= TOL
-                # same field again through the separate-launch path: bit-identical d/dz, and x / y == cfd_apply_xy
-                outs2 = [torch.empty_like(b) for b in blocks]
-                for r in range(P):
-                    sp = ctypes.c_void_p(streams[r].cuda_stream)
-                    check(L.cfd_zpart_apply(zps[r], blocks[r].data_ptr(), outs2[r].data_ptr(), sp))
-                torch.cuda.synchronize()
-                for r in range(P):
-                    assert torch.equal(outs2[r], outs[r][2])
-                    ex, ey = xy.dfdxy(blocks[r], hs[0], hs[1])
-                    assert torch.equal(ex, outs[r][0]) and torch.equal(ey, outs[r][1])
+                    monkeypatch.delenv("CFD_NO_ZX", raising=False)
+                outs = [[torch.zeros_like(b) for _ in range(3)] for b in blocks]
+                run(kind, blocks, outs)
+                gz = np.concatenate([o[2].cpu().numpy() for o in outs], axis=0)
+                assert relinf(gz, want[2]) <= TOL, name
+                results[name] = gz
+                if kind == "xyz":
+                    for a in (0, 1):
+                        ga = np.concatenate([o[a].cpu().numpy() for o in outs], axis=0)
+                        assert relinf(ga, want[a]) <= TOL
+                    for r in range(P):
+                        ex, ey = xy.dfdxy(blocks[r], hs[0], hs[1])
+                        assert torch.equal(ex, outs[r][0]) and torch.equal(ey, outs[r][1])
+            monkeypatch.delenv("CFD_NO_ZX", raising=False)
+            assert np.array_equal(results["zx apply"], results["zx xyz"])
+            assert np.array_equal(results["3-launch apply"], results["3-launch xyz"])
+            assert np.array_equal(results["3-launch apply"], results["begin + apply"])
+            assert relinf(results["zx apply"], results["3-launch apply"]) <= 1e-14
     finally:
         torch.cuda.synchronize()
         for z in zps:
