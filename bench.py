@@ -227,7 +227,7 @@ def run_reference(args):
     print(json.dumps(line), file=RESULT, flush=True)
 
 
-def workload_config(n_gpus, comm="nvlink", overlap=True, fused_edge=False):
+def workload_config(n_gpus, comm="nvlink", overlap=True, fused_edge=False, zx=False):
     if n_gpus == 1:
         return {"workload": "512^3 fp64 field, derivative along x, y and z on 1 B200 (BASELINE configs[2])",
                 "grid": [512, 512, 512], "derivatives_per_step": 3, "partition": "none",
@@ -236,11 +236,15 @@ def workload_config(n_gpus, comm="nvlink", overlap=True, fused_edge=False):
     return {"workload": f"1024^3 fp64 field z-partitioned over {n_gpus} B200, derivative along x, y and z "
                         "(d/dz: one-plane halo + interface exchange with the z-neighbours + coupled solve; BASELINE configs[3])",
             "grid": [1024, 1024, 1024], "derivatives_per_step": 3, "partition": f"z/{n_gpus}",
-            "step": ("per rank three launches (cfd_zpart_apply_xyz): fused d/dx + d/dy kernel whose first work items are the "
-                     "edge faces of d/dz (pushed to the z-neighbours over NVLink), reduced solve, coupled d/dz kernel")
+            "step": ("per rank two launches (= cfd_zpart_apply_xyz): fused d/dx + d/dy kernel, then the one-kernel partitioned "
+                     "d/dz (per bundle: edge faces, self-validating words stored into the z-neighbours' memory over "
+                     "NVLink, reduced system in registers, coupled solve)") if zx else
+                    ("per rank three launches (cfd_zpart_apply_xyz, CFD_NO_ZX): fused d/dx + d/dy kernel whose first work items "
+                     "are the edge faces of d/dz (pushed to the z-neighbours over NVLink), reduced solve, coupled d/dz kernel")
             if fused_edge else "per rank: one fused d/dx + d/dy launch on the slab + the partitioned d/dz",
-            "ddz": f"fused (edge faces -> {comm} exchange -> coupled kernel)",
-            "overlap": ("exchange inside the x/y launch" if fused_edge else
+            "ddz": ("one kernel, exchange inside it" if zx else f"fused (edge faces -> {comm} exchange -> coupled kernel)"),
+            "overlap": ("exchange inside the d/dz launch, one bundle ahead of its use" if zx else
+                        "exchange inside the x/y launch" if fused_edge else
                         "d/dz exchange started before d/dx, d/dy" if overlap else "none"),
             "l2": "inputs (slab >= 1 GiB) larger than the 126 MB L2; no flush needed"}
 
@@ -458,11 +462,16 @@ def run_ours(args):
     ddz = C.ZPartitionedDerivative((nz_loc, N, N), h, 2, mode="fused", comm=args.comm) if world > 1 else \
         C.CompactFiniteDifferenceSolver((nz_loc, N, N), h, 2)
     pts_local = f.numel()
-    # N > 1, default: the whole slab gradient in three launches (cfd_zpart_apply_xyz) -- the edge-face work of d/dz
-    # rides in the fused d/dx + d/dy kernel as its first work items.  --chain = the round-1 step instead: exchange
-    # chain on a side stream beside the x/y launch (5 instead of 6 xy warps on thin slabs to leave it room).
-    fused_edge = world > 1 and args.comm == "nvlink" and not args.chain and not args.separate
-    xy_warps = 5 if (world > 1 and not fused_edge and not args.no_overlap and nz_loc <= 128) else None
+    # N > 1, default: two launches per rank and step -- the fused d/dx + d/dy kernel and the ONE-kernel partitioned d/dz
+    # (stream_kernel_zx: edge faces, NVLink exchange, reduced system and coupled solve per bundle) -- issued exactly
+    # as cfd_zpart_apply_xyz issues them (cfd_apply_xy, then cfd_zpart_apply), so that each has its own CUDA events.
+    # --three-launch = the first half of round 2 (edge items inside the x/y kernel, reduce, coupled d/dz; one C call);
+    # --chain = the round-1 step (exchange chain on a side stream beside the x/y launch, 5 xy warps on thin slabs).
+    zx = world > 1 and args.comm == "nvlink" and not args.chain and not args.three_launch
+    fused_edge = world > 1 and args.comm == "nvlink" and args.three_launch and not args.separate
+    if fused_edge:
+        os.environ["CFD_NO_ZX"] = "1"
+    xy_warps = 5 if (world > 1 and args.chain and not args.no_overlap and nz_loc <= 128) else None
 
     def gradient(src, events=None):
         if fused_edge:
@@ -472,7 +481,7 @@ def run_ours(args):
             if events is not None:
                 events[1][1].record()
             return
-        if world > 1 and not args.no_overlap:
+        if world > 1 and args.chain and not args.no_overlap:
             ddz.begin(src)           # halo + interface exchange of d/dz overlaps the d/dx + d/dy kernel
         if events is not None:
             events[0][0].record()
@@ -500,8 +509,8 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
-    if fused_edge:
-        assert ddz.comm == "nvlink", "CUDA IPC unavailable: the fused step fell back; rerun with --chain --comm pairwise"
+    if zx or fused_edge:
+        assert ddz.comm == "nvlink", "CUDA IPC unavailable: the step fell back; rerun with --chain --comm pairwise"
 
     # in-run correctness of the timed path, all three derivatives, every rank (cheap, outside the timed region)
     check = check_derivatives(f, df, h, N, rank, world, nz_loc, dev, dist)
@@ -610,7 +619,9 @@ def run_ours(args):
     dom = int(np.argmax(per_launch))
     names = ["stream_kernel d/dx, d/dy (two launches)" if args.separate else
              ("stream_kernel_xy (d/dx + d/dy + edge-face items of d/dz, one launch) + reduced_planes" if fused_edge else
-              "stream_kernel_xy (d/dx + d/dy, one launch)"), "stream_kernel d/dz"]
+              "stream_kernel_xy (d/dx + d/dy, one launch)"),
+             "stream_kernel_zx (partitioned d/dz in one launch: edge faces, NVLink exchange, reduced system, coupled solve)"
+             if zx else ("stream_kernel d/dz (coupled)" if world > 1 else "stream_kernel d/dz")]
     # dram bytes (read + write) per launch from `ncu --set full`, keyed by kernel and slab shape; null when this shape
     # has not been profiled (profiles/traffic.json names the capture each figure comes from)
     shape_key = f"{nz_loc}x{N}x{N}"
@@ -619,7 +630,8 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
-    tkeys = [("xy_edge@" if fused_edge else "xy@") + shape_key, ("z_coupled@" if world > 1 else "z@") + shape_key]
+    tkeys = [("xy_edge@" if fused_edge else "xy@") + shape_key,
+             ("zx@" if zx else "z_coupled@" if world > 1 else "z@") + shape_key]
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": gbps[dom], "peak": peak,
                 "unit": "GB/s", "frac": gbps[dom] / peak, "traffic": traffic.get(tkeys[dom]), "peak_source": peak_src,
                 "frac_of_8TBps_nominal": gbps[dom] / 8000.0,
@@ -650,7 +662,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, args.comm, not args.no_overlap, fused_edge),
+            "config": workload_config(world, args.comm, not args.no_overlap, fused_edge, zx),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pts_local * 8 * world,
                     "d2h_bytes_per_step": 3 * pts_local * 8 * world, "steps": e2e_steps, "verified": e2e_ok,
@@ -687,8 +699,10 @@ def main():
                     help="host-buffer leg: HostGradient slab pipeline, or H2D -> gradient -> D2H in sequence")
     ap.add_argument("--separate", action="store_true", help="d/dx and d/dy as two launches instead of cfd_apply_xy")
     ap.add_argument("--chain", action="store_true",
-                    help="N > 1: the round-1 step (exchange chain on a side stream beside the x/y launch) instead of "
-                         "the three-launch cfd_zpart_apply_xyz step")
+                    help="N > 1: the round-1 step (exchange chain on a side stream beside the x/y launch)")
+    ap.add_argument("--three-launch", action="store_true",
+                    help="N > 1: edge items inside the x/y kernel + reduce + coupled d/dz (first half of round 2) instead of "
+                         "the x/y launch + one-kernel d/dz")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the extra configurations (256^3, solver sweep, 1024^3)")
     args = ap.parse_args()
     _reserve_stdout()

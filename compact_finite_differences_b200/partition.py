@@ -157,14 +157,17 @@ class PartitionedDerivative:
         comm "allgather" : every rank receives all 2P interface planes (the reference's Gather+Scatter, rootless)
              "pairwise"  : one interface plane from each line neighbour by NCCL send/recv (exact in fp64 for blocks
                            >= 64 rows; fused mode only)
-             "nvlink"    : the same neighbour-only data flow, but the kernels store halo and interface planes
-                           straight into the neighbours' memory over NVLink/NVSwitch (cfd_zpart: CUDA IPC mappings)
-                           and synchronise with flags -- no NCCL call on the data path (fused mode, z lines only:
-                           their boundary planes are contiguous; other directions use "pairwise").  ONE producer
-                           launch (cfd_edge_faces_push: faces without the neighbour points + own boundary rows into
-                           the neighbours' buffers) and one consumer (cfd_reduced_unknowns_deferred: folds the halo
-                           terms in).  (The first, two-step protocol -- halo push, wait, edge faces, reduce -- lives on
-                           as C entry points only: cfd_push_planes / cfd_wait_flags / cfd_edge_faces_p2p.)
+             "nvlink"    : the same neighbour-only data flow, but the kernels store into the neighbours' memory over
+                           NVLink/NVSwitch themselves (cfd_zpart: CUDA IPC mappings) -- no NCCL call on the data path
+                           (fused mode, z lines only: their boundary planes are contiguous; other directions use
+                           "pairwise").  The whole partitioned derivative is ONE launch (stream_kernel_zx: per bundle
+                           edge faces, self-validating words into the neighbours' receive arrays, reduced system in
+                           registers, coupled solve).  begin() keeps the three-launch form for callers that want the
+                           exchange early on a side stream: cfd_edge_faces_push (faces without the neighbour points
+                           + own boundary rows into the neighbours' buffers, one flag per side),
+                           cfd_reduced_unknowns_deferred (folds the halo terms in), cfd_apply_coupled.  (The first,
+                           two-step protocol lives on as C entry points: cfd_push_planes / cfd_wait_flags /
+                           cfd_edge_faces_p2p.)
         """
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"
         self.group = group
@@ -309,10 +312,9 @@ class ZPartitionedDerivative(PartitionedDerivative):
     _part_axis = 2
 
     def gradient(self, f, dx, dy, out=None):
-        """(df/dx, df/dy, df/dz) of the slab.  With direction = 2 and comm = "nvlink": three launches
-        (cfd_zpart_apply_xyz) -- the fused d/dx + d/dy kernel with the edge-face work of d/dz as its first work
-        items (faces and halo planes cross NVLink while x / y are computed), the reduced solve, the coupled d/dz
-        kernel.  Otherwise the exchange is started on a side stream and the same results come from separate calls."""
+        """(df/dx, df/dy, df/dz) of the slab.  With direction = 2 and comm = "nvlink": two launches
+        (cfd_zpart_apply_xyz) -- the fused d/dx + d/dy kernel and the one-kernel partitioned d/dz.  Otherwise the
+        exchange is started on a side stream and the same results come from separate calls."""
         assert self.direction == 2, "gradient() belongs to the d/dz operator of the slab"
         out = [torch.empty_like(f) if o is None else o for o in (out if out is not None else (None, None, None))]
         if getattr(self, "_xy", None) is None:

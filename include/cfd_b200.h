@@ -262,15 +262,23 @@ int cfd_pthomas(const double *a, const double *b, const double *c, double *d, in
  *   (ranks living in ONE process -- tests, one process driving several devices with peer access enabled -- pass
  *    cfd_zpart_buffer() of the neighbours to cfd_zpart_connect_ptr instead).
  * Per call:
- *     cfd_zpart_apply(zp, f, dfdz, stream)       = cfd_edge_faces_push -> cfd_reduced_unknowns_deferred ->
- *                                                  cfd_apply_coupled: three launches, one point-to-point
- *                                                  synchronisation, no collective, no host synchronisation;
- *     cfd_zpart_begin(zp, f, side_stream)        optional: the first two launches early, on another stream, so that
- *                                                  the exchange overlaps other work; the next cfd_zpart_apply on the
- *                                                  same f picks them up (events order the streams both ways);
- *     cfd_zpart_apply_xyz(zp, px, py, f, ...)    the whole gradient of the slab in three launches: the fused
- *                                                  d/dx + d/dy kernel (cfd_apply_xy) with the edge-face work of d/dz
- *                                                  as its first work items, the reduced solve, the coupled d/dz.
+ *     cfd_zpart_apply(zp, f, dfdz, stream)       the partitioned d/dz in ONE launch (stream_kernel_zx): per 32-line
+ *                                                  bundle the two interface faces, their exchange with the z-neighbours
+ *                                                  (self-validating 16-byte words stored straight into the neighbours'
+ *                                                  receive arrays over NVLink: no flag, no fence, no collective), the
+ *                                                  reduced system in registers and the coupled one-pass solve; no host
+ *                                                  synchronisation.  DRAM traffic = the unpartitioned d/dz's;
+ *     cfd_zpart_apply_xyz(zp, px, py, f, ...)    the whole gradient of the slab in two launches: cfd_apply_xy, then the
+ *                                                  above;
+ *     cfd_zpart_begin(zp, f, side_stream)        optional, the three-launch form: cfd_edge_faces_push and
+ *                                                  cfd_reduced_unknowns_deferred early, on another stream; the next
+ *                                                  cfd_zpart_apply on the same f then only runs cfd_apply_coupled
+ *                                                  (events order the streams both ways).  CFD_NO_ZX=1 in the environment
+ *                                                  makes every call take this form (cfd_zpart_apply_xyz then carries the
+ *                                                  edge-face work as the first work items of the x/y kernel).
+ *   cfd_zpart_set_ctas(zp, n): the one-kernel d/dz is persistent (one CTA per SM) and its warps wait for data that the
+ *   NEIGHBOURS' kernels produce: with one rank per GPU that is always there; a process that keeps several ranks of a
+ *   line on ONE device (tests) must cap the CTA count so that all of their kernels are resident together.
  * A rank that never arrives makes the neighbours' reduced kernel give up after cfd_set_wait_timeout_ms (default
  * 120 s; it polls with back-off and never traps): the next cfd_zpart_* call, or cfd_async_status(), returns
  * CFD_ETIMEOUT and the results of that call are invalid.

@@ -1,12 +1,13 @@
 #!/bin/bash
+# 8 GPUs: record run with the one-kernel d/dz
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "zpart" > gpurun_out/j23_pytest_zpart.log 2>&1; tail -3 gpurun_out/j23_pytest_zpart.log
-for w in 7 6; do
-  echo "== zx warps=$w" >> gpurun_out/j23_zx.txt
-  CFD_ZX_WARPS=$w ZSTEP_ONLY="zx" python scripts/time_zpart_step.py 128 1024 20 2>&1 | grep "zx" >> gpurun_out/j23_zx.txt
-done
-python scripts/time_zpart_step.py 128 1024 20 >> gpurun_out/j23_zx.txt 2>&1
-python scripts/time_zpart_step.py 256 1024 20 >> gpurun_out/j23_zx.txt 2>&1
-cat gpurun_out/j23_zx.txt
-ZSTEP_ONLY="zx d/dz alone" ncu --set full --clock-control none -k regex:stream_kernel_zx -s 3 -c 1 -o gpurun_out/j23_ncu_zx python scripts/time_zpart_step.py 128 1024 3 > gpurun_out/j23_ncu.log 2>&1
-ncu -i gpurun_out/j23_ncu_zx.ncu-rep --page raw --csv > gpurun_out/j23_ncu_zx_raw.csv 2>/dev/null; rm -f gpurun_out/j23_ncu_zx.ncu-rep
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29581"
+timeout 400 $TR bench.py --gpus 8 --steps 100 --warmup 5 > gpurun_out/j25_bench_n8.json 2> gpurun_out/j25_bench_n8.err; echo "bench rc=$?"
+timeout 300 $TR scripts/time_zpart_step_mp.py 128 1024 50 > gpurun_out/j25_step_mp_128.txt 2>&1; echo "step rc=$?"
+grep -v "Warning\|^\*\*\*\|OMP" gpurun_out/j25_step_mp_128.txt | tail -14
+timeout 600 $TR scripts/check_partition_nccl.py 1024 > gpurun_out/j25_check_partition_p8.txt 2>&1; echo "check rc=$?"
+grep -c " OK" gpurun_out/j25_check_partition_p8.txt; grep "FAIL\|Error" gpurun_out/j25_check_partition_p8.txt | head
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/j25_bench_n8.json")); print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["frac_of_copy_ceiling"], d["check"], d["roofline"]["launches"], d["gpu_launches"])
+PY
