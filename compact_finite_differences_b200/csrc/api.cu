@@ -2200,6 +2200,29 @@ extern "C" int cfd_zpart_apply_xyz(cfd_zpart *z, cfd_plan *px, cfd_plan *py, con
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (zx_enabled()) {                                // two launches: the plain x/y launch, the one-kernel d/dz
+        // The two are independent (same input, different outputs).  CFD_ZX_TWO_STREAMS=1: d/dz on plan_z's side stream,
+        // forked and joined with events like cfd_apply_xyz, so that one kernel's CTAs take over as the other's retire.
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+        const bool two = getenv("CFD_ZX_TWO_STREAMS") != nullptr && !(z->pending && z->pending_f == f);
+        if (two && !pz->gside && cs == cudaStreamCaptureStatusNone) {
+            if (cudaStreamCreateWithFlags(&pz->gside, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&pz->gev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&pz->gev_join, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                if (pz->gside) { cudaStreamDestroy(pz->gside); pz->gside = nullptr; }
+            }
+        }
+        if (two && pz->gside && pz->gev_fork && pz->gev_join) {
+            CUDA_TRY(cudaEventRecord(pz->gev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(pz->gside, pz->gev_fork, 0));
+            rc = cfd_zpart_apply(z, f, dfdz, pz->gside);
+            if (!rc) rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(pz->gev_join, pz->gside));
+            CUDA_TRY(cudaStreamWaitEvent(st, pz->gev_join, 0));
+            return CFD_OK;
+        }
         rc = cfd_apply_xy(px, py, f, dfdx, dfdy, stream);
         return rc ? rc : cfd_zpart_apply(z, f, dfdz, stream);
     }

@@ -56,6 +56,12 @@ def xyz():
                                 out[2].data_ptr(), sp()))
 
 
+def xyz2():
+    os.environ["CFD_ZX_TWO_STREAMS"] = "1"
+    xyz()
+    os.environ.pop("CFD_ZX_TWO_STREAMS")
+
+
 def fused():
     os.environ["CFD_NO_ZX"] = "1"
     xyz()
@@ -98,6 +104,9 @@ def timeit(name, fn):
 
 print(f"slab {shape}, middle rank of 3, {reps} reps")
 cases = [("zx (zpart_apply_xyz: x/y launch + one-kernel d/dz)", xyz),
+         ("zx two streams (CFD_ZX_TWO_STREAMS)", xyz2),
+         ("zx (again)", xyz),
+         ("zx two streams (again)", xyz2),
          ("zx d/dz alone (cfd_zpart_apply, one launch)", lambda: check(L.cfd_zpart_apply(zp, f.data_ptr(), out[2].data_ptr(), sp()))),
          ("fused (CFD_NO_ZX: edge items in the x/y kernel)", fused),
          ("chain on side stream, xy 5 warps (round-1 step)", chain(5)),

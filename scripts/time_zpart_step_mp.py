@@ -33,6 +33,12 @@ def zx():
     ddz.gradient(f, h, h, out)
 
 
+def zx2():
+    os.environ["CFD_ZX_TWO_STREAMS"] = "1"
+    ddz.gradient(f, h, h, out)
+    os.environ.pop("CFD_ZX_TWO_STREAMS")
+
+
 def fused():
     os.environ["CFD_NO_ZX"] = "1"
     ddz.gradient(f, h, h, out)
@@ -78,7 +84,8 @@ if rank == 0:
     print(f"P = {world}, slab [{nzl}, {N}, {N}] per rank, {reps} reps")
 ref = None
 for rnd in range(2):
-    for name, fn in (("zx: x/y launch + one-kernel d/dz (default)", zx), ("fused: edge items in the x/y kernel, 3 launches", fused),
+    for name, fn in (("zx: x/y launch + one-kernel d/dz (default)", zx), ("zx, d/dz on a side stream (CFD_ZX_TWO_STREAMS)", zx2),
+                     ("fused: edge items in the x/y kernel, 3 launches", fused),
                      ("chain beside xy, 5 warps (round-1 step)", chain(5)),
                      ("chain beside xy, 6 warps", chain(6)), ("serial (edge+reduce, xy, z)", serial)):
         timeit(name, fn)
