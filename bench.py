@@ -558,7 +558,7 @@ def run_ours(args):
     value = (N ** 3) * 3 * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers in pinned memory through the public host API, copies inside the timed region
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     numa_node, prev_aff = bind_to_gpu_numa_node(local) if world > 1 else (None, None)   # NUMA-local pinned buffers
     f_host = torch.empty(f.shape, dtype=torch.float64, pin_memory=True)
     f_host.copy_(f)
@@ -587,11 +587,15 @@ def run_ours(args):
 
     e2e_step()
     fence()
-    t0 = time.perf_counter()
+    # every step is timed on its own (host clock, fence on both sides) and the MEDIAN step is reported: the leg is a
+    # few hundred milliseconds of host-driven copies, and one scheduling hiccup on a busy host would otherwise decide it
+    e2e_times = []
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         e2e_step()
-    fence()
-    e2e_s = time.perf_counter() - t0
+        fence()
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_times)) * e2e_steps
     step()                     # refresh df with the device-resident result for the comparison below
     torch.cuda.synchronize()
     e2e_ok = all(float((out_host[a] - df[a].cpu()).abs().max()) == 0.0 for a in range(3))
@@ -666,7 +670,9 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pts_local * 8 * world,
                     "d2h_bytes_per_step": 3 * pts_local * 8 * world, "steps": e2e_steps, "verified": e2e_ok,
-                    "mode": e2e_mode, "pinned_copy_ceiling": ceil_value, "frac_of_copy_ceiling": e2e_value / ceil_value,
+                    "mode": e2e_mode, "timing": "median of the per-step wall times",
+                    "step_ms": [round(1e3 * t, 2) for t in e2e_times],
+                    "pinned_copy_ceiling": ceil_value, "frac_of_copy_ceiling": e2e_value / ceil_value,
                     "numa_node_of_rank0_buffers": numa_node,
                     "ceiling": "H2D of f + D2H of three results, both directions at once on every rank, no kernels"},
             "gpu_launches": launches,
