@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/j29_pytest.log 2>&1; tail -3 gpurun_out/j29_pytest.log
-python bench.py --steps 100 --warmup 5 > gpurun_out/j29_bench_n1.json 2> gpurun_out/j29_bench_n1.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/j29_bench_ref.json 2> gpurun_out/j29_bench_ref.err; echo "ref rc=$?"
+python bench.py --steps 20 --warmup 5 --no-extra > gpurun_out/j31_bench_n1.json 2> gpurun_out/j31_bench_n1.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/j31_bench_n1.json")); print(d["value"], d["e2e"])
+PY
