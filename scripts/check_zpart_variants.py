@@ -1,3 +1,7 @@
+"""All P ranks of a z-partitioned line in ONE process on one device (cfd_zpart_connect_ptr, one stream per rank, CTA counts
+capped so that the persistent kernels are co-resident): the one-kernel d/dz and the three-launch form alternately,
+status word and error against the oracle after every call.  A 3 s wait time-out makes a protocol hang show up as
+status -4 instead of blocking.  usage: check_zpart_variants.py P nz ny nx [ctas]"""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, "/root/repo")
