@@ -53,6 +53,8 @@ SIGNATURES = {
     "cfd_zpart_begin": (_i, [_vp, _vp, _vp]),
     "cfd_zpart_apply": (_i, [_vp, _vp, _vp, _vp]),
     "cfd_zpart_apply_xyz": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cfd_create_npts": (_i, [_pp, _i, _i, _i, _i, _d, _i, _i]),
+    "cfd_zpart_apply_npts": (_i, [_vp, _vp, _vp, _vp]),
     "cfd_zpart_destroy": (None, [_vp]),
     "cfd_set_wait_timeout_ms": (_i, [_l]),
     "cfd_async_status": (_i, []),

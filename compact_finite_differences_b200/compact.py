@@ -32,10 +32,14 @@ def _stream_ptr(t):
 class _Plan:
     """Owns one cfd_plan (cfd_create / cfd_destroy)."""
 
-    def __init__(self, shape, axis, spacing, part_rank=0, part_size=1, scheme="pade4"):
+    def __init__(self, shape, axis, spacing, part_rank=0, part_size=1, scheme="pade4", npts=False):
         nz, ny, nx = (int(s) for s in shape)
         self.handle = ctypes.c_void_p()
-        if scheme == "pade4":
+        if npts:                        # this rank's slice of the LU of the whole line (distributed npts)
+            assert scheme == "pade4"
+            check(lib().cfd_create_npts(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
+                                        int(part_rank), int(part_size)))
+        elif scheme == "pade4":
             check(lib().cfd_create(ctypes.byref(self.handle), nz, ny, nx, int(axis), float(spacing),
                                    int(part_rank), int(part_size)))
         else:

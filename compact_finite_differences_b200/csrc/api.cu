@@ -433,6 +433,7 @@ struct cfd_plan {
     int scheme = 0;                   // CFD_SCHEME_*; schemes other than PADE4 run the general kernel
     int la = 1;                       // look-ahead chunks of the general kernel
     bool second = false;              // the scheme is a second derivative (symmetric stencil)
+    bool npts = false;                // tables are this rank's slice of the GLOBAL LU (cfd_create_npts)
     GParams gp;
     // multi-rank
     std::vector<double> x_uh, x_lh, ra, rb, rc, lu;
@@ -1058,6 +1059,55 @@ extern "C" int cfd_create_scheme(cfd_plan **out, int nz, int ny, int nx, int axi
 }
 
 extern "C" int cfd_plan_lookahead(const cfd_plan *p) { return p ? p->la : 0; }
+
+// Plan of one rank for the distributed npts solve: the LU of the WHOLE line, pivots handed from rank to rank
+// (lanl-implementation/npts.c:580-655 precompute_beta_gam; here every rank computes the global sequence itself, it
+// depends on the line length only) and this rank's rows cut out of it.
+extern "C" int cfd_create_npts(cfd_plan **out, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size)
+{
+    if (!out) return fail(CFD_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    if (!(h > 0.0) || !std::isfinite(h)) return fail(CFD_EINVAL, "spacing h = %g must be positive", h);
+    if (part_size < 2 || part_rank < 0 || part_rank >= part_size || part_size > 64)
+        return fail(CFD_EINVAL, "partition position %d of %d is invalid (npts plans are for partitioned lines)", part_rank, part_size);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(CFD_ECUDA, "no CUDA device: libcfd_b200 has no CPU path");
+    }
+    cfd_plan *p = new cfd_plan();
+    int rc = make_geometry(p->g, nz, ny, nx, axis);
+    if (!rc && p->g.n < 2 * CH + 2) rc = fail(CFD_EUNSUPPORTED, "distributed npts needs >= %d rows per block (have %d)", 2 * CH + 2, p->g.n);
+    if (!rc) rc = ensure_counters();
+    if (!rc) rc = ensure_err_word();
+    if (rc) { delete p; return rc; }
+    p->h = h; p->rank = part_rank; p->size = part_size; p->npts = true;
+    const int n = p->g.n;
+    const LineCoeffs whole = {1.0, 2.0, 0.25, 1.0, 0.25, 2.0, 1.0};
+    const Pivots gp = build_pivots(n * part_size, whole);
+    Pivots pv;                                               // this rank's slice
+    pv.beta.assign(gp.beta.begin() + (long)part_rank * n, gp.beta.begin() + (long)(part_rank + 1) * n);
+    pv.l.assign(gp.l.begin() + (long)part_rank * n, gp.l.begin() + (long)(part_rank + 1) * n);
+    pv.g.assign(gp.g.begin() + (long)part_rank * n, gp.g.begin() + (long)(part_rank + 1) * n);
+    const double scale = 3.0 / (4.0 * h);
+    KParams &kp = p->kp;
+    memset(&kp, 0, sizeof kp);
+    kp.n = n; kp.K = p->g.K; kp.jl = p->g.jl; kp.kseg = p->g.K; kp.nseg = 1;
+    kp.inner = (int)p->g.inner; kp.inner_tiles = p->g.inner_tiles; kp.outer = (int)p->g.outer;
+    kp.nb = p->g.nb; kp.rows = p->g.nlines;
+    kp.head = chunk_table(pv, n, 0, scale);
+    kp.tail = chunk_table(pv, n, p->g.K - 1, scale);
+    kp.sk_mid = pv.beta[CH] * scale; kp.l_mid = pv.l[CH]; kp.g_mid = pv.g[CH];
+    kp.lo_closure = (part_rank == 0);
+    kp.hi_closure = (part_rank == part_size - 1);
+    kp.s0c = pv.beta[0] / (2.0 * h);                         // closure rows of the global ends (ranks 0 and P-1 only)
+    kp.snc = pv.beta[n - 1] / (2.0 * h);
+    kp.snb = kp.hi_closure ? 0.0 : pv.g[n - 1];              // gamma of the next rank's first row = beta_{n-1} c_i
+    // the backward sweep of the last chunk ends at row n-1 with x_{n-1} = e_{n-1} - snb x~ : no g beyond it
+    kp.tail.g[p->g.jl] = 0.0;
+    *out = p;
+    return CFD_OK;
+}
 
 // Host-only inspection (no device): look-ahead chunks for a line of n rows of the matrix coeffs, and the definition
 // of a scheme: out[0..6] = b1,c1,ai,bi,ci,an,bn; [7] = two special rows per end; [8..13] = a2,b2,c2,am,bm,cm;
@@ -1905,6 +1955,8 @@ static void preload_zpart_kernels()
     cudaFuncGetAttributes(&at, reduced_planes_deferred_kernel);
     cudaFuncGetAttributes(&at, push_planes_kernel);
     cudaFuncGetAttributes(&at, wait_flags_kernel);
+    cudaFuncGetAttributes(&at, npts_edge_kernel<0>);
+    cudaFuncGetAttributes(&at, npts_edge_kernel<1>);
     cudaFuncGetAttributes(&at, stream_kernel<false, true, 3>);
     cudaFuncGetAttributes(&at, stream_kernel<false, true, 4>);
     cudaFuncGetAttributes(&at, stream_kernel<false, true, 5>);
@@ -1926,6 +1978,7 @@ extern "C" int cfd_zpart_create(cfd_zpart **out, cfd_plan *plan)
     *out = nullptr;
     preload_zpart_kernels();
     if (plan->size < 2) return fail(CFD_EINVAL, "plan has part_size 1: nothing to exchange");
+    if (plan->scheme != CFD_SCHEME_PADE4) return fail(CFD_EUNSUPPORTED, "cfd_zpart serves the Pade-4 scheme");
     if (plan->g.axis != 2) return fail(CFD_EUNSUPPORTED, "cfd_zpart serves lines along z (contiguous boundary planes)");
     if (plan->g.n < 2 * CH + 2)
         return fail(CFD_EUNSUPPORTED, "cfd_zpart needs >= %d planes per slab (have %d)", 2 * CH + 2, plan->g.n);
@@ -2177,6 +2230,80 @@ extern "C" int cfd_zpart_apply(cfd_zpart *z, const double *f, double *df, void *
     int rc = zpart_ptrs(z, z->seq, q);
     if (rc) return rc;
     rc = cfd_apply_coupled(z->plan, f, df, q.halo_lo, q.halo_hi, z->ab, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(z->ev_apply, st));
+    z->applied = true;
+    return CFD_OK;
+}
+
+// The partitioned d/dz by the distributed npts method (kernels.cuh npts_edge_kernel): halo planes, u~ to the right,
+// x~ to the left, coupled one-pass solve with this rank's slice of the global LU.  An alternative to the reduced-system
+// method of cfd_zpart_apply (the measured path), kept for the reference's second algorithm; `zp` must have been
+// created from a cfd_create_npts plan.
+extern "C" int cfd_zpart_apply_npts(cfd_zpart *z, const double *f, double *df, void *stream)
+{
+    if (!z || !f || !df) return fail(CFD_EINVAL, "NULL argument");
+    if (f == df) return fail(CFD_EINVAL, "the derivative is out of place: f and df must differ");
+    cfd_plan *p = z->plan;
+    if (!p->npts) return fail(CFD_EINVAL, "cfd_zpart_apply_npts needs a zpart of a cfd_create_npts plan");
+    int rc = cfd_async_status();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (z->applied) CUDA_TRY(cudaStreamWaitEvent(st, z->ev_apply, 0));
+    const bool has_lo = p->rank > 0, has_hi = p->rank < p->size - 1;
+    if ((has_lo && !z->peer[0]) || (has_hi && !z->peer[1]))
+        return fail(CFD_EINVAL, "cfd_zpart: neighbours are not connected (cfd_zpart_connect)");
+    const unsigned long long seq = ++z->seq;
+    const int par = (int)(seq & 1);
+    const long plane = z->plane, n = p->g.n;
+    // (1) halo planes of f: first plane -> left neighbour's halo slot 1, last plane -> right neighbour's slot 0
+    rc = cfd_push_planes(has_lo ? f : nullptr, has_lo ? z->halo(z->peer[0], par, 1) : nullptr,
+                         has_hi ? f + (n - 1) * plane : nullptr, has_hi ? z->halo(z->peer[1], par, 0) : nullptr, plane,
+                         has_lo ? z->flag(z->peer[0], 1) : nullptr, has_hi ? z->flag(z->peer[1], 0) : nullptr, seq, stream);
+    if (rc) return rc;
+    rc = cfd_wait_flags(has_lo ? z->flag(z->buf, 0) : nullptr, has_hi ? z->flag(z->buf, 1) : nullptr, seq, stream);
+    if (rc) return rc;
+    double *halo_lo = has_lo ? z->halo(z->buf, par, 0) : nullptr, *halo_hi = has_hi ? z->halo(z->buf, par, 1) : nullptr;
+    EdgeP ep;
+    memset(&ep, 0, sizeof ep);
+    ep.nlines = p->g.nlines; ep.inner = p->g.inner; ep.n = p->g.n; ep.jl = p->g.jl;
+    ep.lo_closure = p->kp.lo_closure; ep.hi_closure = p->kp.hi_closure;
+    ep.sk_mid = p->kp.sk_mid; ep.l_mid = p->kp.l_mid;
+    ep.sk_last = p->kp.tail.sk[p->g.jl]; ep.l_last = p->kp.tail.l[p->g.jl];
+    ep.halo_lo = halo_lo; ep.halo_hi = halo_hi;
+    ep.head = p->kp.head;
+    ep.seq = seq;
+    const int bs = 128;
+    const unsigned grid = (unsigned)((ep.nlines + bs - 1) / bs);
+    // u~ / x~ live in the interface planes 0 / 1 of this call's parity, adjacent: exactly the `ab` planes the coupled
+    // kernel reads
+    double *ab = z->faces(z->buf, par, 0);
+    if (has_hi) {                                            // (2) u at our last row -> the right neighbour's plane 0
+        rc = counter_pair(&ep.done, st, &p->pool);
+        if (rc) return rc;
+        npts_edge_kernel<0><<<grid, bs, 0, st>>>(f, ep, nullptr, z->faces(z->peer[1], par, 0), z->flag(z->peer[1], 4));
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (has_lo) {                                            // (3) x at our first row -> the left neighbour's plane 1
+        rc = cfd_wait_flags(z->flag(z->buf, 4), nullptr, seq, stream);
+        if (rc) return rc;
+        rc = counter_pair(&ep.done, st, &p->pool);
+        if (rc) return rc;
+        npts_edge_kernel<1><<<grid, bs, 0, st>>>(f, ep, ab, z->faces(z->peer[0], par, 1), z->flag(z->peer[0], 5));
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        CUDA_TRY(cudaMemsetAsync(ab, 0, plane * sizeof(double), st));            // rank 0: no incoming u~
+    }
+    if (has_hi) {
+        rc = cfd_wait_flags(z->flag(z->buf, 5), nullptr, seq, stream);
+        if (rc) return rc;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(ab + plane, 0, plane * sizeof(double), st));    // last rank: no incoming x~
+    }
+    // (4) both sweeps in one pass
+    rc = apply_impl(p, f, df, halo_lo, halo_hi, ab, stream);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(z->ev_apply, st));
     z->applied = true;

@@ -986,6 +986,64 @@ edge_faces_kernel(const double *__restrict__ f, double *__restrict__ faces, cons
     if (p.done) publish_when_grid_done(p.done, p.flag_lo, p.flag_hi, p.seq);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Distributed npts (lanl-implementation/npts.c:329-562, python/npts.py:228-382), the LANL alternative
+// to the reduced-system method: ONE LU of the whole line with pivots handed from rank to rank (precompute_beta_gam),
+// every rank sweeping its block as  u = phi + u~ psi  (L->R) and  x = phi' + x~ psi'  (R->L), where u~ is the
+// forward-eliminated value at the left neighbour's last row and x~ the solution at the right neighbour's first row.
+// The reference runs both sweeps from zero states, materialises phi, psi, u (five full-size arrays), all-gathers the end
+// faces and combines prefixes over all ranks.  Here psi is never formed: a sweep that STARTS from the incoming value is
+// phi + u~ psi, so the coupled stream_kernel does both sweeps in one pass once u~ and x~ are known -- and since psi decays
+// by 0.268 per row, u~ and x~ depend on the 32 rows next to the interface only (0.268^32 = 5e-19; the prefix
+// combination over ranks further away multiplies by psi_last ~ 1e-37):
+//   PHASE 0 (u~ for the right neighbour): rows n-32..n-1 forward from a zero state, GLOBAL pivots; stored into the right
+//            neighbour's buffer;
+//   PHASE 1 (x~ for the left neighbour): rows 0..31 forward from the received u~, back-substitution from x_31 = u_31;
+//            stored into the left neighbour's buffer.
+// One thread per line, the layout and tables of edge_faces_kernel (tables = this rank's slice of the global pivots).
+template <int PHASE>
+__global__ void __launch_bounds__(128)
+npts_edge_kernel(const double *__restrict__ f, const __grid_constant__ EdgeP p, const double *u_in, double *peer_out,
+                 unsigned long long *peer_flag)
+{
+    const long line = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = line < p.nlines;
+    const long o = active ? line / p.inner : 0, col = active ? line % p.inner : 0;
+    const double *fl = f + (o * p.n) * p.inner + col;
+    const long st = p.inner;
+    if (active) {
+        if constexpr (PHASE == 0) {
+            const double *ft = fl + (long)(p.n - CH) * st;         // rows n-32 .. n-1
+            double F[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j++) F[j] = EDGE_LD(ft + (long)j * st);
+            const double hval = __ldg(p.halo_hi + line);
+            double eprev = 0.0;
+#pragma unroll
+            for (int j = 1; j < CH - 1; j++)
+                eprev = fma(-p.l_mid, eprev, p.sk_mid * (F[j + 1] - F[j - 1]));
+            eprev = fma(-p.l_last, eprev, p.sk_last * (hval - F[CH - 2]));
+            peer_out[line] = eprev;                                // u at this block's last row
+        } else {
+            double F[CH], e[CH - 1];
+#pragma unroll
+            for (int j = 0; j < CH; j++) F[j] = EDGE_LD(fl + (long)j * st);
+            double fm1 = __ldg(p.halo_lo + line), eprev = peer_ld(u_in + line);
+#pragma unroll
+            for (int j = 0; j < CH - 1; j++) {
+                eprev = fma(-p.head.l[j], eprev, p.head.sk[j] * (F[j + 1] - fm1));
+                e[j] = eprev;
+                fm1 = F[j];
+            }
+            double x = 0.0;
+#pragma unroll
+            for (int j = CH - 2; j >= 0; j--) x = fma(-p.head.g[j], x, e[j]);
+            peer_out[line] = x;                                    // solution at this block's first row
+        }
+    }
+    publish_when_grid_done(p.done, peer_flag, nullptr, p.seq);
+}
+
 // Halo push over NVLink: copy this rank's first / last plane of f into the neighbours' halo buffers (peer
 // addresses) and raise their arrival flags (replaces the NCCL send/recv pair of the halo exchange).
 __global__ void __launch_bounds__(256)

@@ -126,6 +126,10 @@ class ZPart:
         self._check(self._lib.cfd_zpart_apply(self.handle, f.data_ptr(), out.data_ptr(), self._sp(f)))
         return out
 
+    def apply_npts(self, f, out):
+        self._check(self._lib.cfd_zpart_apply_npts(self.handle, f.data_ptr(), out.data_ptr(), self._sp(f)))
+        return out
+
     def apply_xyz(self, plan_x, plan_y, f, out_x, out_y, out_z):
         self._check(self._lib.cfd_zpart_apply_xyz(self.handle, plan_x.handle, plan_y.handle, f.data_ptr(),
                                                   out_x.data_ptr(), out_y.data_ptr(), out_z.data_ptr(), self._sp(f)))
@@ -154,6 +158,9 @@ class PartitionedDerivative:
         """
         mode "fused"     : edge faces -> exchange -> ONE coupled kernel (final derivative, no correction pass)
              "reference" : local solve -> pack -> all-gather -> correction sweep (the reference's order)
+             "npts"      : the LANL distributed npts method instead of the reduced system (z lines, >= 66 planes per
+                           slab): one LU of the whole line, u~ handed to the right and x~ to the left over NVLink,
+                           both sweeps in one coupled pass (cfd_create_npts / cfd_zpart_apply_npts)
         comm "allgather" : every rank receives all 2P interface planes (the reference's Gather+Scatter, rootless)
              "pairwise"  : one interface plane from each line neighbour by NCCL send/recv (exact in fp64 for blocks
                            >= 64 rows; fused mode only)
@@ -177,8 +184,18 @@ class PartitionedDerivative:
         self.local_shape = tuple(int(s) for s in local_shape)
         part = (self.rank, self.size) if self._partitioned else (0, 1)
         self.solver = CompactFiniteDifferenceSolver(self.local_shape, spacing, self.direction, part=part)
-        assert mode in ("fused", "reference") and comm in ("allgather", "pairwise", "nvlink")
+        assert mode in ("fused", "reference", "npts") and comm in ("allgather", "pairwise", "nvlink")
         self._zp = None
+        self._npts = None
+        if mode == "npts":
+            from .compact import _Plan
+            assert self._partitioned and self.size > 1 and self._dim == 0 and self.local_shape[0] >= 66, \
+                "mode 'npts' serves z-partitioned lines with >= 66 planes per slab"
+            self._npts_plan = _Plan(self.local_shape, 2, spacing, self.rank, self.size, npts=True)
+            self._npts = ZPart(self._npts_plan, self.rank, self.size, self.group)
+            self.mode, self.comm = "npts", "nvlink"
+            self._buf = self._side = self._pending = None
+            return
         self.mode = mode if self.local_shape[self._dim] >= 66 else "reference"
         self.comm = comm if self.mode == "fused" else "allgather"
         if self.comm == "nvlink" and self._dim != 0:
@@ -282,6 +299,10 @@ class PartitionedDerivative:
         self._pending = (f.data_ptr(), res, ev)
 
     def __call__(self, f, out=None):
+        if getattr(self, "_npts", None) is not None:
+            if out is None:
+                out = torch.empty_like(f)
+            return self._npts.apply_npts(f, out)
         if not self._partitioned or self.size == 1:
             return self.solver(f, out)
         if self.mode == "fused" and self._zpart(f) is not None:
@@ -332,3 +353,6 @@ class ZPartitionedDerivative(PartitionedDerivative):
         if self._zp is not None:
             self._zp.close()
             self._zp = None
+        if getattr(self, "_npts", None) is not None:
+            self._npts.close()
+            self._npts = None

@@ -294,6 +294,15 @@ int cfd_zpart_begin(cfd_zpart *zp, const double *f, void *stream);
 int cfd_zpart_apply(cfd_zpart *zp, const double *f, double *dfdz, void *stream);
 int cfd_zpart_apply_xyz(cfd_zpart *zp, cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *dfdx, double *dfdy,
                         double *dfdz, void *stream);
+/* The LANL distributed npts method (lanl-implementation/npts.c:275-655, python/npts.py:172-382) as an alternative to
+ * the reduced-system method: cfd_create_npts builds this rank's plan from the LU of the WHOLE line (pivots handed from
+ * rank to rank, precompute_beta_gam), cfd_zpart_apply_npts runs the two sweeps u = phi + u~ psi, x = phi' + x~ psi' as
+ * ONE coupled pass once the incoming values u~ (forward-eliminated value at the left neighbour's last row) and x~
+ * (solution at the right neighbour's first row) have crossed NVLink -- each from the 32 rows next to the interface
+ * (psi decays by 0.268 per row).  Launches: halo push, wait, u~ kernel, wait, x~ kernel, wait, coupled kernel.  The
+ * zpart is created from the npts plan with cfd_zpart_create and connected like any other. */
+int cfd_create_npts(cfd_plan **plan, int nz, int ny, int nx, int axis, double h, int part_rank, int part_size);
+int cfd_zpart_apply_npts(cfd_zpart *zp, const double *f, double *dfdz, void *stream);
 void cfd_zpart_destroy(cfd_zpart *zp);
 int cfd_set_wait_timeout_ms(long milliseconds);
 int cfd_async_status(void);

@@ -55,7 +55,7 @@ nl = N // world
 ref = C.CompactFiniteDifferenceSolver((N, N, N), h, 2)(full)[rank * nl:(rank + 1) * nl]
 slab = full[rank * nl:(rank + 1) * nl].contiguous()
 COMMS = os.environ.get("CFD_COMMS", "nvlink,pairwise,allgather").split(",")
-for mode, comm in [("fused", c) for c in COMMS] + [("reference", "allgather")]:
+for mode, comm in [("fused", c) for c in COMMS] + [("reference", "allgather"), ("npts", "nvlink")]:
     op = C.ZPartitionedDerivative((nl, N, N), h, 2, mode=mode, comm=comm)
     got = op(slab)
     report(f"smooth {N}^3 d/dz P={world} mode={op.mode}/{op.comm} vs single-GPU",

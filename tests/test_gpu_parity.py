@@ -778,6 +778,54 @@ def test_zpart_c_abi_one_process(C, P, shape, monkeypatch):
             L.cfd_zpart_destroy(z)
 
 
+@pytest.mark.parametrize("P,shape", [(2, (132, 12, 34)), (3, (3 * 66, 32, 40)), (4, (4 * 70, 8, 64)), (2, (2 * 200, 6, 32))])
+def test_distributed_npts_one_process(C, P, shape):
+    """The LANL distributed npts method on the GPU (cfd_create_npts + cfd_zpart_apply_npts: one LU of the whole line,
+    u~ to the right, x~ to the left, both sweeps in one coupled pass), all P ranks in one process, one stream per
+    rank: against the one-rank derivative AND against the oracle's restatement of the reference's distributed
+    algorithm (python/npts.py:228-382: full phi / psi sweeps, all-gathers, prefix combinations)."""
+    import ctypes
+    import torch
+    from compact_finite_differences_b200._lib import check, lib
+    from compact_finite_differences_b200.compact import _Plan
+    L = lib()
+    rng = np.random.default_rng(60 + P)
+    h = 0.21
+    n = shape[0] // P
+    lshape = (n,) + tuple(shape[1:])
+    plans = [_Plan(lshape, 2, h, r, P, npts=True) for r in range(P)]
+    zps = []
+    for r in range(P):
+        z = ctypes.c_void_p()
+        check(L.cfd_zpart_create(ctypes.byref(z), plans[r].handle))
+        zps.append(z)
+    bufs = [L.cfd_zpart_buffer(z) for z in zps]
+    for r in range(P):
+        check(L.cfd_zpart_connect_ptr(zps[r], bufs[r - 1] if r > 0 else None, bufs[r + 1] if r < P - 1 else None))
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    zz, yy, xx = smooth(shape)
+    try:
+        for it in range(4):                      # both parities, twice
+            f = rng.random(shape) if it < 3 else 1e3 * (np.sin(zz) * np.cos(yy) + xx)
+            blocks = [dev(f[r * n:(r + 1) * n]) for r in range(P)]
+            outs = [torch.zeros_like(b) for b in blocks]
+            torch.cuda.synchronize()
+            for r in range(P):
+                check(L.cfd_zpart_apply_npts(zps[r], blocks[r].data_ptr(), outs[r].data_ptr(),
+                                             ctypes.c_void_p(streams[r].cuda_stream)))
+            torch.cuda.synchronize()
+            assert L.cfd_async_status() == 0
+            got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+            assert relinf(got, O.derivative(f, 2, h)) <= TOL
+            rhs_x = np.ascontiguousarray(np.moveaxis(O.rhs(f, 2, h), 0, 2))           # z lines as the oracle's x lines
+            ref = np.moveaxis(O.npts_distributed_solve(rhs_x, P), 2, 0)
+            assert relinf(got, ref) <= TOL
+    finally:
+        torch.cuda.synchronize()
+        for z in zps:
+            L.cfd_zpart_destroy(z)
+
+
 def test_zpart_rejects_bad_arguments(C):
     import ctypes
     from compact_finite_differences_b200._lib import CFD_EINVAL, CFD_EUNSUPPORTED, lib

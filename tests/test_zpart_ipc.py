@@ -56,8 +56,16 @@ def _worker(rank, world, port, shape, h, ret):
                 for g, w in zip((gx, gy, gz), want):
                     errs.append(float(np.abs(g.cpu().numpy() - w).max() / np.abs(w).max()))
         assert op.comm == "nvlink", f"fell back to {op.comm}: the IPC path was not exercised"
+        # the distributed npts method over the same IPC plumbing
+        op2 = C.ZPartitionedDerivative((n,) + tuple(shape[1:]), h, 2, mode="npts")
+        for it in range(2):
+            f = rng.random(shape)
+            fl = torch.from_numpy(f[rank * n:(rank + 1) * n].copy()).cuda()
+            w = O.derivative(f, 2, h)[rank * n:(rank + 1) * n]
+            errs.append(float(np.abs(op2(fl).cpu().numpy() - w).max() / np.abs(w).max()))
         assert C.lib().cfd_async_status() == 0
         ret[rank] = max(errs)
+        op2.close()
         op.close()
     finally:
         dist.barrier()
