@@ -1259,6 +1259,8 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.slot_items = (float)(2.0 * active);
     // Start-up stagger: pays on long lines only (>= 32 tiles: [128,1024,1024] 0.596 -> 0.577 ms with 1 us per slot;
     // 512^3, 16 tiles: 0.531 -> 0.534), profiles/r1n_time_xy_startup_stagger.txt.  CFD_XY_TAU overrides (ns).
+    q.hints = 1;                  // evict_last on the tile loads of the long-line (SEG) variants: -1.5 % on 128 x 1024^2
+    if (const char *e = getenv("CFD_XY_HINTS")) q.hints = atoi(e);
     q.tau_ns = (px->g.K + py->g.K >= 64) ? 1000.f : 0.f;
     if (const char *e = getenv("CFD_XY_TAU")) q.tau_ns = (float)atof(e);
     const size_t smem = (size_t)warps * per_warp + 1024;
@@ -1313,6 +1315,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     q.nxy = p->g.nb;
     q.order = nullptr;
     q.kseg = 0;
+    q.hints = 0;
     q.tau_ns = 0.f; q.slot_items = 0.f;
     int warps = g_warps ? g_warps : 6;
     if (warps > 7) warps = 7;

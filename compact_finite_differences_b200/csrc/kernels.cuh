@@ -127,6 +127,19 @@ __device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
+                                                 unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *tm, uint32_t src, int c0, int c1, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, unsigned long long pol)
 {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"

@@ -24,6 +24,9 @@ struct XYParams {
     // s * tau_ns late, so that the wavefront exists from the first generation of items on instead of all resident
     // warps starting together (worth 3 % on lines of >= 32 tiles, nothing on shorter ones).
     float tau_ns, slot_items;
+    // SEG variants only (long lines, sub-plane wavefronts): L2 eviction hints -- bit 0: evict_last on the tile loads
+    // (every tile has a second reader a few microseconds away), bit 1: evict_first on the result stores (never read)
+    int hints;
 };
 
 // One item = all chunks of one bundle, x (CONTIG) or y (STRIDED).  Ring state is shared across items.
@@ -36,7 +39,8 @@ struct XYParams {
 template <bool CONTIG, int NS, bool SEG, class Issue>
 __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap *tm_out, long b, int oc0, int oc2,
                                             unsigned char *wbase, uint32_t bar0, int lane, int &slot, uint32_t &phase,
-                                            bool &first_step, Issue &issue, int kbeg_, int kend_, int kout_, int kstop_)
+                                            bool &first_step, Issue &issue, int kbeg_, int kend_, int kout_, int kstop_,
+                                            int hints = 0)
 {
     // Tiles kbeg .. kend of the line, results for chunks kout .. kstop-1: the whole line (0, K-1, 0, K), or a
     // segment with one warm-up chunk in front (forward sweep from a zero state, exact to
@@ -82,11 +86,26 @@ __device__ __forceinline__ void xy_run_item(const KParams &p, const CUtensorMap 
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if constexpr (CONTIG) {
-                    tma_store_2d(tm_out, smem_u32(cur), kc * CH, (int)(b * CH));
-                    tma_store_2d(tm_out, smem_u32(cur) + 4096, kc * CH + 16, (int)(b * CH));
-                } else {
-                    tma_store_3d(tm_out, smem_u32(cur), oc0, kc * CH, oc2);
+                bool hinted = false;
+                if constexpr (SEG) {
+                    if (hints & 2) {
+                        const unsigned long long pol = l2_policy_evict_first();
+                        if constexpr (CONTIG) {
+                            tma_store_2d_hint(tm_out, smem_u32(cur), kc * CH, (int)(b * CH), pol);
+                            tma_store_2d_hint(tm_out, smem_u32(cur) + 4096, kc * CH + 16, (int)(b * CH), pol);
+                        } else {
+                            tma_store_3d_hint(tm_out, smem_u32(cur), oc0, kc * CH, oc2, pol);
+                        }
+                        hinted = true;
+                    }
+                }
+                if (!hinted) {
+                    if constexpr (CONTIG) {
+                        tma_store_2d(tm_out, smem_u32(cur), kc * CH, (int)(b * CH));
+                        tma_store_2d(tm_out, smem_u32(cur) + 4096, kc * CH + 16, (int)(b * CH));
+                    } else {
+                        tma_store_3d(tm_out, smem_u32(cur), oc0, kc * CH, oc2);
+                    }
                 }
                 tma_commit();
             }
@@ -293,6 +312,14 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
             if (EDGE && iedge) {             // head tile = planes 0..31, tail tile = planes n-32..n-1
                 const int row = (ex.has_lo && ik == 0) ? 0 : ex.n - CH;
                 tma_load_3d(dst, &tmz_in, bar, (int)(ib * CH), row, 0);
+            } else if (SEG && (q.hints & 1)) {
+                const unsigned long long pol = l2_policy_evict_last();
+                if (icontig) {
+                    tma_load_2d_hint(dst, &tmx_in, bar, ik * CH, (int)(ib * CH), pol);
+                    tma_load_2d_hint(dst + 4096, &tmx_in, bar, ik * CH + 16, (int)(ib * CH), pol);
+                } else {
+                    tma_load_3d_hint(dst, &tmy_in, bar, ic0, ik * CH, ic2, pol);
+                }
             } else if (icontig) {
                 tma_load_2d(dst, &tmx_in, bar, ik * CH, (int)(ib * CH));
                 tma_load_2d(dst + 4096, &tmx_in, bar, ik * CH + 16, (int)(ib * CH));
@@ -342,8 +369,8 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
             }
             if (edge_pending) edge_report();
         }
-        if (contig) xy_run_item<true, NS, SEG>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
-        else        xy_run_item<false, NS, SEG>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp);
+        if (contig) xy_run_item<true, NS, SEG>(px, &tmx_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp, q.hints);
+        else        xy_run_item<false, NS, SEG>(py, &tmy_out, b, c0, c2, wbase, bar0, lane, slot, phase, first_step, issue, kb, ke, ko, kp, q.hints);
     }
     if constexpr (EDGE) {
         if (edge_pending) edge_report();
