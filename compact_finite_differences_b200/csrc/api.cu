@@ -17,6 +17,7 @@
 #ifndef CFD_PDL_DEFAULT
 #define CFD_PDL_DEFAULT 0
 #endif
+#include <algorithm>
 #include <utility>
 #include "../../include/cfd_b200.h"
 #include "kernels.cuh"
@@ -678,16 +679,42 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int su
     const long nv = (long)nz * ngy * ngx;      // squares ("virtual planes"), z-major, then y block, then x block
     const int M = sy > sx ? sy : sx;
     const double sigma = (double)M / active;   // slots between the starts of consecutive squares
+    // Skew: square (a, b) of a plane starts (a + b) * M slots after square (0, 0), so that the warm-up / look-ahead
+    // tile a segment shares with the neighbouring square is asked for when that square's own readers ask for it (the
+    // plane-wide wavefront, tile (j, k) at j + k, kept although the lines are cut).  Without it the squares of a plane
+    // start together and the shared tiles are read M tile-times apart: one of the two reads goes to DRAM.
+    static const bool skew = !(getenv("CFD_XY_SKEW") && atoi(getenv("CFD_XY_SKEW")) == 0);
+    auto emit = [&](long v, long j) {
+        const int z = (int)(v / (ngy * ngx)), a = (int)((v / ngx) % ngy), b = (int)(v % ngx);
+        const long xj = (long)a * sy + j, yk = (long)b * sx + j;
+        if (j < sy && xj < nxp) order.push_back((int)((((long)z * ipp + xj) << 3) | (ngx > 1 ? b + 1 : 0)));
+        if (j < sx && yk < nyp) order.push_back((int)((((long)z * ipp + nxp + yk) << 3) | (ngy > 1 ? a + 1 : 0)));
+    };
+    if (skew && ngx * ngy > 1) {
+        std::vector<std::pair<long, long>> starts;             // (start slot, square)
+        starts.reserve((size_t)nv);
+        for (long v = 0; v < nv; v++) {
+            const long z = v / (ngy * ngx), a = (v / ngx) % ngy, b = v % ngx;
+            starts.emplace_back((long)std::floor((double)(z * ngy * ngx) * sigma) + (a + b) * M, v);
+        }
+        std::stable_sort(starts.begin(), starts.end());
+        size_t lo = 0;
+        for (long s = 0; lo < starts.size(); s++) {
+            for (size_t i = lo; i < starts.size() && starts[i].first <= s; i++) {
+                const long j = s - starts[i].first;
+                if (j >= M) { if (i == lo) lo++; continue; }
+                emit(starts[i].second, j);
+            }
+        }
+        return order;
+    }
     auto start = [&](long v) { return (long)std::floor(v * sigma); };
     long vlo = 0;
     for (long s = 0; vlo < nv; s++) {
         for (long v = vlo; v < nv && start(v) <= s; v++) {
             const long j = s - start(v);
             if (j >= M) { if (v == vlo) vlo++; continue; }
-            const int z = (int)(v / (ngy * ngx)), a = (int)((v / ngx) % ngy), b = (int)(v % ngx);
-            const long xj = (long)a * sy + j, yk = (long)b * sx + j;
-            if (j < sy && xj < nxp) order.push_back((int)((((long)z * ipp + xj) << 3) | (ngx > 1 ? b + 1 : 0)));
-            if (j < sx && yk < nyp) order.push_back((int)((((long)z * ipp + nxp + yk) << 3) | (ngy > 1 ? a + 1 : 0)));
+            emit(v, j);
         }
     }
     return order;

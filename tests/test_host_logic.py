@@ -289,6 +289,14 @@ def test_xy_draw_order_sub_planes(nz, nxp, nyp, sub):
             if j // sy == a and k // sx == b:
                 pairs += 1
     assert pairs >= nz * min(nxp, nyp) // 2
+    # skewed starts: segment b + 1 of a line is drawn about one square (a square = ~2 * ks draws of its own, other
+    # squares in between) after segment b, so that the tile the two share is asked for by both within a tile-time
+    pos = {}
+    for i, (e, sg) in enumerate(zip(order.tolist(), seg.tolist())):
+        pos[(e, sg)] = i
+    for (e, sg), i in pos.items():
+        if sg >= 1 and (e, sg + 1) in pos:
+            assert pos[(e, sg + 1)] - i >= ks, (e, sg)
 
 
 # ---------------------------------------------------------------------------------------------------
