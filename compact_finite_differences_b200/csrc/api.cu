@@ -450,7 +450,7 @@ struct cfd_plan {
     std::mutex xy_mu;
     int *d_xy_order = nullptr;
     long xy_entries = 0;              // entries of the table (> items when lines are cut into segments)
-    int xy_kseg = 0, xy_sub = -1;
+    int xy_kseg = 0, xy_ksegy = 0, xy_sub = -1;     // segment lengths of the x / y lines in the draw table (0 = whole)
     long xy_nedge = 0;                // edge entries in front of the table (drawn by cfd_zpart_apply_xyz only)
     double xy_active = -1.0;
     int xy_warps = 0;                 // 0 = default; cfd_plan_set_xy_warps
@@ -655,31 +655,35 @@ extern "C" int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_h
 // segments of `sub` chunks (one warm-up chunk in front, the look-ahead chunk behind, both served by L2); every square
 // is then a wavefront of its own, as short as a small plane's.  Entries are (item << 3) | segment, segment 0 = whole
 // line.  Returns the effective segment length in `kseg` (0 = nothing was cut).
-static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int sub, int &kseg, long nedge = 0)
+// `sub` = segment length of the x lines | segment length of the y lines << 8 (a zero high byte = the same for both;
+// a length >= the line's tile count leaves that direction whole); ksegx / ksegy return what was cut (0 = whole lines).
+static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int sub, int &ksegx, int &ksegy, long nedge = 0)
 {
     const int ipp = nxp + nyp;
-    kseg = 0;
+    ksegx = ksegy = 0;
     if (sub > 0) {
-        const int kmax = nxp > nyp ? nxp : nyp;
-        if (sub * 7 < kmax) sub = (kmax + 6) / 7;             // at most 7 segments fit the 3-bit code
-        if (nxp > sub || nyp > sub) kseg = sub;
+        int subx = sub & 255, suby = (sub >> 8) ? (sub >> 8) : (sub & 255);
+        if (subx * 7 < nyp) subx = (nyp + 6) / 7;             // at most 7 segments fit the 3-bit code
+        if (suby * 7 < nxp) suby = (nxp + 6) / 7;
+        if (nyp > subx) ksegx = subx;                          // an x line is nyp tiles long
+        if (nxp > suby) ksegy = suby;                          // a y line is nxp tiles long
     }
-    const int ngx = (kseg && nyp > kseg) ? (nyp + kseg - 1) / kseg : 1;     // segments of an x line (nyp tiles long)
-    const int ngy = (kseg && nxp > kseg) ? (nxp + kseg - 1) / kseg : 1;     // segments of a y line (nxp tiles long)
-    const int sy = ngy > 1 ? kseg : nxp, sx = ngx > 1 ? kseg : nyp;         // x bundles / y bundles per square
+    const int ngx = ksegx ? (nyp + ksegx - 1) / ksegx : 1;     // segments of an x line
+    const int ngy = ksegy ? (nxp + ksegy - 1) / ksegy : 1;     // segments of a y line
+    const int sy = ngy > 1 ? ksegy : nxp, sx = ngx > 1 ? ksegx : nyp;       // x bundles / y bundles per rectangle
     std::vector<int> order;
     order.reserve((size_t)nz * (nxp * ngx + nyp * ngy) + (size_t)nedge);
     // edge items of a z-partitioned d/dz (ids from nz * ipp on) go FIRST: their faces have the whole launch to travel
     for (long t = 0; t < nedge; t++) order.push_back((int)(((long)nz * ipp + t) << 3));
     if (active <= 0.0) {                       // plain plane-by-plane order (whole lines)
-        kseg = 0;
+        ksegx = ksegy = 0;
         for (long w = 0; w < (long)nz * ipp; w++) order.push_back((int)(w << 3));
         return order;
     }
     const long nv = (long)nz * ngy * ngx;      // squares ("virtual planes"), z-major, then y block, then x block
     const int M = sy > sx ? sy : sx;
     const double sigma = (double)M / active;   // slots between the starts of consecutive squares
-    // Skew: square (a, b) of a plane starts (a + b) * M slots after square (0, 0), so that the warm-up / look-ahead
+    // Skew: rectangle (a, b) of a plane starts a * sy + b * sx slots after (0, 0), so that the warm-up / look-ahead
     // tile a segment shares with the neighbouring square is asked for when that square's own readers ask for it (the
     // plane-wide wavefront, tile (j, k) at j + k, kept although the lines are cut).  Without it the squares of a plane
     // start together and the shared tiles are read M tile-times apart: one of the two reads goes to DRAM.
@@ -695,7 +699,7 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int su
         starts.reserve((size_t)nv);
         for (long v = 0; v < nv; v++) {
             const long z = v / (ngy * ngx), a = (v / ngx) % ngy, b = v % ngx;
-            starts.emplace_back((long)std::floor((double)(z * ngy * ngx) * sigma) + (a + b) * M, v);
+            starts.emplace_back((long)std::floor((double)(z * ngy * ngx) * sigma) + a * sy + b * sx, v);
         }
         std::stable_sort(starts.begin(), starts.end());
         size_t lo = 0;
@@ -723,8 +727,8 @@ static std::vector<int> xy_order(int nz, int nxp, int nyp, double active, int su
 extern "C" long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *out, long capacity)
 {
     if (nz < 1 || nxp < 0 || nyp < 0 || nxp + nyp < 1 || sub < 0) return fail(CFD_EINVAL, "cfd_debug_xy_order: bad argument");
-    int kseg = 0;
-    const std::vector<int> order = xy_order(nz, nxp, nyp, active, sub, kseg);
+    int ksegx = 0, ksegy = 0;
+    const std::vector<int> order = xy_order(nz, nxp, nyp, active, sub, ksegx, ksegy);
     if (out) {
         if ((long)order.size() > capacity) return fail(CFD_EINVAL, "cfd_debug_xy_order: %ld entries, capacity %ld", (long)order.size(), capacity);
         memcpy(out, order.data(), order.size() * sizeof(int));
@@ -739,13 +743,17 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
     int Kx = gx.K, Ky = (gx.ny + CH - 1) / CH;
     // Sub-plane wavefronts for lines of >= 32 tiles ([128,1024,1024]: 0.578 -> 0.561 ms with squares of 16 x 16 tiles;
     // 512^3 with 8 x 8: 0.541 -> 0.582, so shorter lines stay whole).  CFD_XY_SUB overrides (0 = never cut).
-    sub = (Kx >= 32 || Ky >= 32) ? 16 : 0;
+    // Rectangles instead of squares (round 2): x lines cut at 16 tiles, y lines only beyond 32 -- every cut line walks
+    // two extra tiles per segment, and with the skewed starts of xy_order the wavefront no longer needs both
+    // directions cut: 128 / 256 / 512 planes of 1024^2: -1.5 / -4.5 / -2.4 % (profiles/r2s_xy_rectangles.txt).
+    sub = (Kx >= 32 || Ky >= 32) ? (16 | (32 << 8)) : 0;
     if (const char *e = getenv("CFD_XY_SUB")) sub = atoi(e) > 0 ? atoi(e) : 0;
     if (sub > 0) {                                             // tiles an item walks when its line is cut
-        const int kmax = Kx > Ky ? Kx : Ky;
-        const int ks = sub * 7 < kmax ? (kmax + 6) / 7 : sub;
-        if (Kx > ks) Kx = ks + 2;
-        if (Ky > ks) Ky = ks + 2;
+        int subx = sub & 255, suby = (sub >> 8) ? (sub >> 8) : (sub & 255);
+        if (subx * 7 < Kx) subx = (Kx + 6) / 7;
+        if (suby * 7 < Ky) suby = (Ky + 6) / 7;
+        if (Kx > subx) Kx = subx + 2;
+        if (Ky > suby) Ky = suby + 2;
     }
     const long nitems = (long)gx.nz * (gx.ny / CH + (gx.nx + CH - 1) / CH);
     warps = g_warps ? g_warps : (plan_warps ? plan_warps : def_warps);
@@ -767,14 +775,15 @@ static int xy_prepare(cfd_plan *px, double active, int sub)
     std::lock_guard<std::mutex> lock(px->xy_mu);
     if (px->d_xy_order && px->xy_active == active && px->xy_sub == sub) return CFD_OK;
     const int nxp = px->g.ny / CH, nyp = (px->g.nx + CH - 1) / CH;
-    int kseg = 0;
-    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active, sub, kseg, nedge);
+    int kseg = 0, ksegy = 0;
+    const std::vector<int> order = xy_order(px->g.nz, nxp, nyp, active, sub, kseg, ksegy, nedge);
     if ((long)order.size() < (long)px->g.nz * (nxp + nyp) + nedge) return fail(CFD_EINVAL, "internal: xy draw order is incomplete");
     if (px->d_xy_order && (long)order.size() > px->xy_entries) { cudaFree(px->d_xy_order); px->d_xy_order = nullptr; }
     if (!px->d_xy_order) CUDA_TRY(cudaMalloc(&px->d_xy_order, order.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(px->d_xy_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
     px->xy_entries = (long)order.size();
     px->xy_kseg = kseg;
+    px->xy_ksegy = ksegy;
     px->xy_active = active;
     px->xy_sub = sub;
     px->xy_nedge = nedge;
@@ -1283,6 +1292,7 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.nitems = px->xy_entries - (edge ? 0 : px->xy_nedge);
     q.nxy = nitems;
     q.kseg = px->xy_kseg;
+    q.ksegy = px->xy_ksegy;
     q.slot_items = (float)(2.0 * active);
     // Start-up stagger: pays on long lines only (>= 32 tiles: [128,1024,1024] 0.596 -> 0.577 ms with 1 us per slot;
     // 512^3, 16 tiles: 0.531 -> 0.534), profiles/r1n_time_xy_startup_stagger.txt.  CFD_XY_TAU overrides (ns).
@@ -1291,7 +1301,7 @@ static int launch_xy(cfd_plan *px, cfd_plan *py, const MapPair &mx, const MapPai
     q.tau_ns = (px->g.K + py->g.K >= 64) ? 1000.f : 0.f;
     if (const char *e = getenv("CFD_XY_TAU")) q.tau_ns = (float)atof(e);
     const size_t smem = (size_t)warps * per_warp + 1024;
-    const bool seg = q.kseg > 0;          // whole lines only: the variant without segment state
+    const bool seg = q.kseg > 0 || q.ksegy > 0;          // whole lines only: the variant without segment state
     auto kern = seg ? stream_kernel_xy<NSLOT, true, false> : stream_kernel_xy<NSLOT, false, false>;
     if (edge) {
         if constexpr (NSLOT == 4) kern = seg ? stream_kernel_xy<4, true, true> : stream_kernel_xy<4, false, true>;
@@ -1341,7 +1351,7 @@ static int launch_one_direction_ring(cfd_plan *p, const MapPair &mp, cudaStream_
     q.nitems = p->g.nb;
     q.nxy = p->g.nb;
     q.order = nullptr;
-    q.kseg = 0;
+    q.kseg = 0; q.ksegy = 0;
     q.hints = 0;
     q.tau_ns = 0.f; q.slot_items = 0.f;
     int warps = g_warps ? g_warps : 6;

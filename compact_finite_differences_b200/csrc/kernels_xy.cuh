@@ -19,7 +19,7 @@ struct XYParams {
     unsigned long long *counter;
     const int *order;   // draw position -> (item << 3) | segment, item = plane * (nxp + nyp) + index in plane;
                         // segment 0 = the whole line, s >= 1 = output chunks [(s-1) kseg, s kseg); nullptr = identity
-    int kseg;           // chunks per line segment (sub-plane wavefronts, see xy_order)
+    int kseg, ksegy;    // chunks per segment of the x lines / of the y lines (sub-plane wavefronts, see xy_order; 0 = whole)
     // Start-up stagger (off when tau_ns == 0): a warp whose FIRST item sits in slot s of the draw order starts it
     // s * tau_ns late, so that the wavefront exists from the first generation of items on instead of all resident
     // warps starting together (worth 3 % on lines of >= 32 tiles, nothing on shorter ones).
@@ -272,8 +272,9 @@ stream_kernel_xy(const __grid_constant__ CUtensorMap tmx_in, const __grid_consta
         const int K = contig ? px.K : py.K;
         if (!SEG || seg == 0) { kb = 0; ke = K - 1; ko = 0; kp = K; }
         else {
-            const int s0 = (seg - 1) * q.kseg;
-            const int s1 = (s0 + q.kseg < K) ? s0 + q.kseg : K;
+            const int ks = contig ? q.kseg : q.ksegy;
+            const int s0 = (seg - 1) * ks;
+            const int s1 = (s0 + ks < K) ? s0 + ks : K;
             ko = s0;
             kp = s1;
             kb = s0 > 0 ? s0 - 1 : 0;

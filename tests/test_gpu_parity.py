@@ -211,12 +211,13 @@ def test_fused_xy_launch_shapes(C, warps, slots):
         C.lib().cfd_set_launch(0, 0, 0)
 
 
-@pytest.mark.parametrize("sub", [1, 2, 3, 16])
-@pytest.mark.parametrize("shape", [(5, 160, 192), (3, 96, 258), (2, 64, 1056), (2, 1056, 64)])
+@pytest.mark.parametrize("sub", [1, 2, 3, 16, 2 | (4 << 8), 3 | (1 << 8), 16 | (32 << 8), 40 | (2 << 8)])
+@pytest.mark.parametrize("shape", [(5, 160, 192), (3, 96, 258), (2, 64, 1056), (2, 1056, 64), (3, 1024, 1024)])
 def test_fused_xy_sub_plane_wavefronts(C, sub, shape):
     """CFD_XY_SUB: lines cut into segments of `sub` chunks (warm-up chunk in front, look-ahead chunk behind), squares
     of sub x sub tiles as wavefronts of their own.  Every segment length, ragged last chunks, a line whose last
-    segment is a single chunk (33 chunks, sub 16), and the whole-line case (sub >= chunks)."""
+    segment is a single chunk (33 chunks, sub 16), and the whole-line case (sub >= chunks).  sub = x | y << 8 cuts the
+    x lines and the y lines differently (rectangles; 16 | 32 << 8 is the library default for lines of >= 32 tiles)."""
     rng = np.random.default_rng(hash((sub, shape)) % 2 ** 32)
     f = rng.random(shape)
     want = O.derivative(f, 0, 0.1), O.derivative(f, 1, 0.2)

@@ -251,18 +251,20 @@ def test_xy_draw_order_is_a_wavefront(nz, nxp, nyp, active):
 
 
 @pytest.mark.parametrize("nz,nxp,nyp,sub", [(3, 32, 32, 16), (2, 32, 8, 16), (2, 5, 40, 4), (1, 64, 64, 4), (4, 7, 7, 2),
-                                            (2, 16, 16, 16), (2, 33, 17, 16)])
+                                            (2, 16, 16, 16), (2, 33, 17, 16), (3, 32, 32, 16 | (32 << 8)),
+                                            (2, 32, 32, 32 | (16 << 8)), (2, 32, 32, 8 | (16 << 8))])
 def test_xy_draw_order_sub_planes(nz, nxp, nyp, sub):
     """Sub-plane wavefronts: lines longer than `sub` tiles are cut into segments; every line has each of its
     segments exactly once, the segments tile the line, and an x segment is drawn next to the y segments that share
     its square of tiles (same plane, x bundle inside the y segment's chunk range and vice versa)."""
     order, seg = _xy_order(nz, nxp, nyp, 5.0, sub)
     ipp = nxp + nyp
-    kmax = max(nxp, nyp)
-    ks = sub if sub * 7 >= kmax else (kmax + 6) // 7
-    cut = nxp > ks or nyp > ks
-    ngx = -(-nyp // ks) if (cut and nyp > ks) else 1          # segments of an x line (nyp tiles long)
-    ngy = -(-nxp // ks) if (cut and nxp > ks) else 1
+    subx, suby = sub & 255, (sub >> 8) or (sub & 255)           # segment length of the x lines / of the y lines
+    ksx = subx if subx * 7 >= nyp else (nyp + 6) // 7            # an x line is nyp tiles long; at most 7 segments
+    ksy = suby if suby * 7 >= nxp else (nxp + 6) // 7
+    ngx = -(-nyp // ksx) if nyp > ksx else 1                     # segments of an x line
+    ngy = -(-nxp // ksy) if nxp > ksy else 1
+    cut = ngx > 1 or ngy > 1
     assert seg.max() <= 7
     seen = {}
     for e, s in zip(order.tolist(), seg.tolist()):
@@ -275,7 +277,7 @@ def test_xy_draw_order_sub_planes(nz, nxp, nyp, sub):
     if not cut:
         return
     # neighbours in the draw belong to the same square: an (x, y) pair drawn back to back shares tiles
-    sy, sx = (ks if ngy > 1 else nxp), (ks if ngx > 1 else nyp)
+    sy, sx = (ksy if ngy > 1 else nxp), (ksx if ngx > 1 else nyp)
     pairs = 0
     for i in range(len(order) - 1):
         e0, e1 = order[i], order[i + 1]
@@ -296,7 +298,7 @@ def test_xy_draw_order_sub_planes(nz, nxp, nyp, sub):
         pos[(e, sg)] = i
     for (e, sg), i in pos.items():
         if sg >= 1 and (e, sg + 1) in pos:
-            assert pos[(e, sg + 1)] - i >= ks, (e, sg)
+            assert pos[(e, sg + 1)] - i >= (ksx if (e % ipp) < nxp else ksy), (e, sg)
 
 
 # ---------------------------------------------------------------------------------------------------
