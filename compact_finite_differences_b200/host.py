@@ -19,11 +19,12 @@ from .compact import CompactFiniteDifferenceSolver
 
 
 class HostGradient:
-    def __init__(self, shape, spacings, slabs=8, device=None, ddz=None):
+    def __init__(self, shape, spacings, slabs=8, device=None, ddz=None, ramp=True):
         """
         :param shape: (nz, ny, nx)
         :param spacings: (dx, dy, dz)
-        :param slabs: number of z-slabs the transfers are pipelined in (nz is split as evenly as possible)
+        :param slabs: nz / slabs = planes per z-slab of the transfer pipeline
+        :param ramp: start with thin slabs (see below); False = uniform slabs
         :param ddz: optional d/dz operator `ddz(f, out)` for the resident block, e.g. a ZPartitionedDerivative when
                     this block is one rank's slab of a z-partitioned field (d/dx, d/dy never leave the slab)
         """
@@ -32,7 +33,17 @@ class HostGradient:
         self.dx, self.dy, self.dz = (float(h) for h in spacings)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         slabs = max(1, min(int(slabs), nz))
-        cuts = [round(i * nz / slabs) for i in range(slabs + 1)]
+        # The device->host copies are the bound of the call (three results for one field) and cannot start before
+        # the first slab has landed and been differentiated: the first slabs are thin (nz/64 planes, doubling up to
+        # nz/slabs), so that lag is an eighth of a uniform slab's.
+        full = max(1, nz // slabs)
+        cuts, step = [0], (max(4, nz // 64) if ramp else full)
+        while cuts[-1] < nz:
+            step = min(step, full)
+            cuts.append(min(nz, cuts[-1] + step))
+            step *= 2
+        if len(cuts) > 2 and cuts[-1] - cuts[-2] < 4:         # no sliver at the end (a slab needs >= 4 planes)
+            del cuts[-2]
         self.slabs = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
         self._solvers = {}
         for a, b in self.slabs:
