@@ -11,7 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import compact_finite_differences_b200 as C
 
-M = ctypes.CDLL(os.path.join(ROOT, "scripts", "_ab", "libdrammix.so"))
+SO = os.path.join(ROOT, "scripts", "_ab", "libdrammix.so")
+if not os.path.exists(SO):                                  # build here (nvcc cross-compiles), the .so travels with gpurun
+    import subprocess
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared",
+                           "-Xcompiler", "-fPIC", "-o", SO, os.path.join(ROOT, "scripts", "dram_mix.cu")])
+M = ctypes.CDLL(SO)
 vp = ctypes.c_void_p
 M.mix_copy.argtypes = [vp, vp, ctypes.c_long, ctypes.c_int, ctypes.c_int, vp]
 M.mix_r1w2.argtypes = [vp, vp, vp, ctypes.c_long, ctypes.c_int, ctypes.c_int, vp]
