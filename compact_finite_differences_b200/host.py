@@ -19,6 +19,23 @@ from .compact import CompactFiniteDifferenceSolver
 
 
 class HostGradient:
+    @staticmethod
+    def slab_cuts(nz, slabs=8, ramp=True):
+        """[(first plane, end plane)] of the transfer pipeline.  The device->host copies are the bound of the call
+        (three results for one field) and cannot start before the first slab has landed and been differentiated, so
+        with `ramp` the first slabs are thin (nz/64 planes, doubling up to nz/slabs): that lag is an eighth of a
+        uniform slab's."""
+        slabs = max(1, min(int(slabs), nz))
+        full = max(1, nz // slabs)
+        cuts, step = [0], (max(4, nz // 64) if ramp else full)
+        while cuts[-1] < nz:
+            step = min(step, full)
+            cuts.append(min(nz, cuts[-1] + step))
+            step *= 2
+        if len(cuts) > 2 and cuts[-1] - cuts[-2] < min(4, full):     # no sliver at the end
+            del cuts[-2]
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
     def __init__(self, shape, spacings, slabs=8, device=None, ddz=None, ramp=True):
         """
         :param shape: (nz, ny, nx)
@@ -32,19 +49,7 @@ class HostGradient:
         nz, ny, nx = self.shape
         self.dx, self.dy, self.dz = (float(h) for h in spacings)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        slabs = max(1, min(int(slabs), nz))
-        # The device->host copies are the bound of the call (three results for one field) and cannot start before
-        # the first slab has landed and been differentiated: the first slabs are thin (nz/64 planes, doubling up to
-        # nz/slabs), so that lag is an eighth of a uniform slab's.
-        full = max(1, nz // slabs)
-        cuts, step = [0], (max(4, nz // 64) if ramp else full)
-        while cuts[-1] < nz:
-            step = min(step, full)
-            cuts.append(min(nz, cuts[-1] + step))
-            step *= 2
-        if len(cuts) > 2 and cuts[-1] - cuts[-2] < 4:         # no sliver at the end (a slab needs >= 4 planes)
-            del cuts[-2]
-        self.slabs = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        self.slabs = self.slab_cuts(nz, slabs, ramp)
         self._solvers = {}
         for a, b in self.slabs:
             if (b - a) not in self._solvers:

@@ -386,3 +386,25 @@ def test_scheme_definitions_match_the_published_schemes(scheme):
     assert out[35] == 1                                         # 41 rows = two chunks: every sweep is exact
     check(lib().cfd_debug_scheme(O.SCHEMES[scheme], 400, h, out.ctypes.data_as(dp)))
     assert out[35] == (2 if scheme == "compact6" else 1) and out[36] ** (32 * out[35]) <= 1.2e-16
+
+
+@pytest.mark.parametrize("nz", [1, 3, 4, 5, 7, 40, 48, 64, 128, 500, 512, 1000, 1024])
+@pytest.mark.parametrize("slabs", [1, 5, 8])
+@pytest.mark.parametrize("ramp", [False, True])
+def test_host_gradient_slab_cuts(nz, slabs, ramp):
+    """The transfer pipeline of HostGradient (host API of the OpenCL flavour, code/ocl/compact.py:26-61): its z-slabs
+    tile [0, nz) without gaps or overlaps, no slab is thicker than nz / slabs, and with `ramp` the first slab -- the lag
+    before the device->host copies can start -- is at most an eighth of a uniform slab (down to 4 planes)."""
+    from compact_finite_differences_b200.host import HostGradient
+    cuts = HostGradient.slab_cuts(nz, slabs, ramp)
+    assert cuts[0][0] == 0 and cuts[-1][1] == nz
+    assert all(a1 == b0 for (_, b0), (a1, _) in zip(cuts[:-1], cuts[1:]))
+    assert all(b > a for a, b in cuts)
+    full = max(1, nz // min(slabs, nz))
+    assert max(b - a for a, b in cuts) <= full + min(4, full)         # the last slab may absorb a sliver
+    if ramp and nz >= 64 * 4 and slabs == 8:
+        assert cuts[0][1] == nz // 64
+        sizes = [b - a for a, b in cuts]
+        assert all(s2 <= 2 * s1 or s2 <= full for s1, s2 in zip(sizes[:-1], sizes[1:]))
+    if not ramp:
+        assert len(cuts) <= -(-nz // full)
