@@ -757,6 +757,11 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
     }
     const long nitems = (long)gx.nz * (gx.ny / CH + (gx.nx + CH - 1) / CH);
     warps = g_warps ? g_warps : (plan_warps ? plan_warps : def_warps);
+    // Launches of few items per warp take a seventh warp per SM: the launch runs in about items / warps generations of
+    // items and ends with a partly filled one, so finer generations pay (256^3: 0.0813 -> 0.0760 ms, [64,512,512]:
+    // 0.0951 -> 0.0866; never slower than 6 warps up to 384^3), while long launches are better off with 6 warps and
+    // fewer concurrent DRAM streams (512^3: 0.533 vs 0.545 ms).  profiles/r2y_sweep_xy_warps.txt.
+    if (!g_warps && !plan_warps && nslot == 4 && sub == 0 && nitems <= 72L * sms) warps = 7;
     if (warps > max_warps) warps = max_warps;
     const long per_sm = (nitems + sms - 1) / sms;
     if (!g_warps && per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
