@@ -413,15 +413,19 @@ def bind_to_gpu_numa_node(local):
     return None, None
 
 
-def copy_ceiling(f, out_host, f_host, reps=2):
-    """Pinned-copy ceiling of the e2e step on this rank: H2D of the field and D2H of three results, both directions
-    at once, no kernel.  Returns seconds per step."""
+def copy_ceiling(f, out_host, f_host, fence, reduce_max, reps=2):
+    """Pinned-copy ceiling of the e2e step: H2D of the field and D2H of three results, both directions at once, no
+    kernel, ALL ranks copying at the same time -- every repetition starts behind a barrier (`fence`) and counts as the
+    slowest rank's time (`reduce_max`); the best repetition is returned, in seconds per step.  (Round 2 found the
+    barrier missing: ranks drifted apart between repetitions, the slow ranks' best repetition ran while the fast ones
+    were already idle, and the 8-GPU ceiling read 203 ms where the copies of all ranks together take 299 ms --
+    profiles/r2z_e2e_variants_n8.txt.)"""
     import torch
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     tmp = torch.empty_like(f)
     best = None
     for _ in range(reps + 1):
-        torch.cuda.synchronize()
+        fence()
         t0 = time.perf_counter()
         with torch.cuda.stream(s_in):
             tmp.copy_(f_host, non_blocking=True)
@@ -429,7 +433,7 @@ def copy_ceiling(f, out_host, f_host, reps=2):
             for o in out_host:
                 o.copy_(f, non_blocking=True)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = reduce_max(time.perf_counter() - t0)
         best = dt if best is None else min(best, dt)
     return best
 
@@ -601,11 +605,14 @@ def run_ours(args):
     e2e_ok = all(float((out_host[a] - df[a].cpu()).abs().max()) == 0.0 for a in range(3))
     # pinned-copy ceiling of the same step: all ranks copy at once (they share the host's memory system), no kernels
     fence()
-    ceil_s = copy_ceiling(f, out_host, f_host)
-    if world > 1:
-        t = torch.tensor([e2e_s, ceil_s], dtype=torch.float64, device=dev)
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, ceil_s = t.tolist()
+        return float(t.item())
+    ceil_s = copy_ceiling(f, out_host, f_host, fence, reduce_max)
+    e2e_s = reduce_max(e2e_s)
     e2e_value = (N ** 3) * 3 * e2e_steps / e2e_s
     ceil_value = (N ** 3) * 3 / ceil_s
     if prev_aff:
@@ -674,7 +681,7 @@ def run_ours(args):
                     "step_ms": [round(1e3 * t, 2) for t in e2e_times],
                     "pinned_copy_ceiling": ceil_value, "frac_of_copy_ceiling": e2e_value / ceil_value,
                     "numa_node_of_rank0_buffers": numa_node,
-                    "ceiling": "H2D of f + D2H of three results, both directions at once on every rank, no kernels"},
+                    "ceiling": "H2D of f + D2H of three results, both directions at once, all ranks at the same time (barrier before every repetition, slowest rank counts), no kernels"},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
