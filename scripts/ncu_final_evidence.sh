@@ -1,3 +1,4 @@
+# gpurun job behind profiles/r2x_bench_launches.csv, r2x_ncu_full_raw_*: each ncu pass runs only after the same command exited 0 without ncu
 set -x
 python bench.py --steps 5 --warmup 3 --no-cpu --no-extra > gpurun_out/x_bench_plain.json 2>/dev/null && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/x_bench_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-extra > gpurun_out/x_ncu1.log 2>&1

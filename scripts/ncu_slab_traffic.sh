@@ -1,3 +1,4 @@
+# gpurun job behind profiles/r2x_ncu_dram_xy_*: DRAM bytes + duration of the fused x/y launch on the slab shapes (final draw order, and 16-tile squares)
 for nz in 128 256 512; do
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:stream_kernel_xy -s 3 -c 5 --csv --log-file gpurun_out/y_dram_xy_${nz}.csv python scripts/time_xy_one.py $nz 1024 1024 2 > /dev/null 2>&1
 done
