@@ -94,7 +94,8 @@ int cfd_apply_xy(cfd_plan *plan_x, cfd_plan *plan_y, const double *f, double *df
  * On return everything is ordered on `stream` as if the three launches had been issued there. */
 int cfd_apply_xyz(cfd_plan *plan_x, cfd_plan *plan_y, cfd_plan *plan_z, const double *f, double *dfdx, double *dfdy,
                   double *dfdz, void *stream);
-/* Warps per SM of that launch for an axis-0 plan (0 = default 6).  5 leaves room on the SMs for kernels that run
+/* Warps per SM of that launch for an axis-0 plan.  0 = the library's choice: 6, or 7 for short launches (at most 72
+ * work items per SM and lines of fewer than 32 tiles, e.g. 256^3).  5 leaves room on the SMs for kernels that run
  * beside it on another stream, e.g. the exchange chain of a partitioned d/dz started before it. */
 int cfd_plan_set_xy_warps(cfd_plan *plan_x, int warps_per_sm);
 
