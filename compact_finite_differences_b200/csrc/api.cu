@@ -770,6 +770,17 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
     if (active > 0.0 && active < 1.0) active = 1.0;
 }
 
+// Host-only inspection entry for the CPU tests: the launch shape cfd_apply_xy would pick on a device of `sms` SMs.
+extern "C" int cfd_debug_xy_shape(int nz, int ny, int nx, int sms, int *warps, double *active, int *sub)
+{
+    if (!warps || !active || !sub || sms < 1) return fail(CFD_EINVAL, "cfd_debug_xy_shape: bad argument");
+    Geometry g;
+    int rc = make_geometry(g, nz, ny, nx, 0);
+    if (rc) return rc;
+    xy_shape(g, sms, 4, 0, *warps, *active, *sub);
+    return CFD_OK;
+}
+
 // (Re)build the draw-order table of an axis-0 plan.  Called from cfd_create with the default launch shape, so that
 // cfd_apply_xy neither allocates nor synchronises; it only runs again if the launch knobs were changed afterwards.
 static int xy_prepare(cfd_plan *px, double active, int sub)

@@ -211,6 +211,10 @@ int cfd_debug_neighbour(int n, int part_rank, int part_size, int *virtual_ranks,
  * Returns the number of entries (<0 on error); out may be NULL to query it.  And the two weights d(lo face)/d f[-1],
  * d(hi face)/d f[n] that cfd_reduced_unknowns_deferred applies (blocks of n rows). */
 long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *out, long capacity);
+/* Host-only: the launch shape cfd_apply_xy picks for an [nz, ny, nx] field on a device of `sms` SMs -- warps per SM
+ * (6, or 7 for short launches), planes in flight of the draw order, and the line cut (0 = whole lines, else x-segment
+ * length | y-segment length << 8 in tiles). */
+int cfd_debug_xy_shape(int nz, int ny, int nx, int sms, int *warps, double *active, int *sub);
 int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_hi);
 /* Host-only: chunks of look-ahead (1, 2; 0 = two-pass) the one-pass solve needs for n rows of coeffs[7], and the
  * definition of a scheme -- out[37]: b1,c1,ai,bi,ci,an,bn | two special rows per end | a2,b2,c2 (row 1), am,bm,cm

@@ -408,3 +408,25 @@ def test_host_gradient_slab_cuts(nz, slabs, ramp):
         assert all(s2 <= 2 * s1 or s2 <= full for s1, s2 in zip(sizes[:-1], sizes[1:]))
     if not ramp:
         assert len(cuts) <= -(-nz // full)
+
+
+@pytest.mark.parametrize("shape, warps, cut", [
+    ((512, 512, 512), 6, False),          # the headline launch: 6 warps per SM (7: 0.545 vs 0.534 ms)
+    ((256, 256, 256), 7, False),          # BASELINE configs[1]: short launch, a seventh warp (0.0808 -> 0.0756 ms)
+    ((128, 128, 128), 7, False),
+    ((64, 512, 512), 7, False),           # the e2e pipeline's slabs
+    ((128, 1024, 1024), 6, True),         # the 8-GPU slab: 32-tile lines are cut, 6 warps
+    ((512, 1024, 1024), 6, True),
+    ((2, 64, 64), 1, False),              # fewer items than warps
+])
+def test_xy_launch_shape_rule(shape, warps, cut):
+    """The launch shape of the fused d/dx + d/dy kernel is a host-side rule (api.cu xy_shape) measured in
+    profiles/r2y_sweep_xy_warps.txt: pinned here for a 148-SM device so that a change of the rule shows up on CPU."""
+    from compact_finite_differences_b200._lib import check, lib
+    w, sub, act = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+    check(lib().cfd_debug_xy_shape(*shape, 148, ctypes.byref(w), ctypes.byref(act), ctypes.byref(sub)))
+    assert w.value == warps
+    assert (sub.value != 0) == cut
+    if cut:
+        assert sub.value == (16 | (32 << 8))
+    assert act.value >= 1.0
