@@ -99,6 +99,16 @@ def stream_lines(F, coeffs, h=None, lo_closure=True, hi_closure=True, halo_lo=No
 
     def bwd(e, x, mode, k_out):
         tab = T["head"] if mode == 1 else T["tail"]
+        if mode == 0 and k_out is None:
+            # warm-up sweep (kernels.cuh bwd_chunk<0, false>): only the end value is used, evaluated as four Horner
+            # chains in g^4 -- x_out = sum_j (-g)^j e_j + (-g)^32 x_in
+            ng = -T["g_mid"]
+            g4 = (ng * ng) * (ng * ng)
+            c = [g4 * x + e[:, CH - 4], e[:, CH - 3].copy(), e[:, CH - 2].copy(), e[:, CH - 1].copy()]
+            for j in range(CH - 8, -1, -4):
+                for m in range(4):
+                    c[m] = g4 * c[m] + e[:, j + m]
+            return ng * (ng * (ng * c[3] + c[2]) + c[1]) + c[0]
         for j in range(CH - 1, -1, -1):
             g = T["g_mid"] if mode == 0 else tab["g"][j]
             x = -g * x + e[:, j]
