@@ -656,6 +656,29 @@ def run_ours(args):
                     3 * BYTES_PER_POINT * pts_local * args.steps / (ms * 1e-3) / 1e9}
     if pieces:
         roofline["pieces"] = pieces
+    # Streaming yardsticks, live, on this rank's arrays: a plain grid-stride kernel with the launches' read : write
+    # mixes (cfd_debug_stream: copy = a single derivative's mix; one read + two writes = the fused x/y launch's).
+    # DRAM streams the 1 : 2 mix several percent below the 1 : 1 copy figure `peak` holds; `frac_of_yardstick` says
+    # how far each launch is from a kernel that does nothing but move its bytes.  Purely additive: never fails the line.
+    try:
+        L = C.lib()
+        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def stream_ms(third):
+            def call():
+                rc = L.cfd_debug_stream(f.data_ptr(), df[0].data_ptr(), df[1].data_ptr() if third else None,
+                                        f.numel(), sp)
+                if rc != 0:
+                    raise RuntimeError(f"cfd_debug_stream: {rc}")
+            return _time_calls(call, reps=10, warm=2)
+        y_copy = 16 * pts_local / (stream_ms(False) * 1e-3) / 1e9
+        y_r1w2 = 24 * pts_local / (stream_ms(True) * 1e-3) / 1e9
+        roofline["yardstick"] = {"what": "plain streaming kernels timed live on the same arrays (cfd_debug_stream)",
+                                 "copy_1r1w_GBps": y_copy, "one_read_two_writes_GBps": y_r1w2}
+        roofline["launches"]["xy"]["frac_of_yardstick"] = gbps[0] / (y_copy if args.separate else y_r1w2)
+        roofline["launches"]["z"]["frac_of_yardstick"] = gbps[1] / y_copy
+    except Exception as e:         # noqa: BLE001  (df[0], df[1] now hold the yardstick's copies; nothing reads them after this)
+        roofline["yardstick"] = {"error": repr(e)}
 
     extra = None
     if world == 1 and not args.no_extra:

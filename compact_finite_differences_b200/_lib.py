@@ -64,6 +64,7 @@ SIGNATURES = {
     "cfd_debug_tables": (_i, [_i, _dp, _d, _dp]),
     "cfd_debug_xy_order": (_l, [_i, _i, _i, _d, _i, ctypes.POINTER(_i), _l]),
     "cfd_debug_xy_shape": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), _dp, ctypes.POINTER(_i)]),
+    "cfd_debug_stream": (_i, [_vp, _vp, _vp, _l, _vp]),
     "cfd_debug_halo_weights": (_i, [_i, _d, _dp, _dp]),
     "cfd_debug_lookahead": (_i, [_i, _dp]),
     "cfd_debug_scheme": (_i, [_i, _i, _d, _dp]),

@@ -770,6 +770,38 @@ static void xy_shape(const Geometry &gx, int sms, int nslot, int plan_warps, int
     if (active > 0.0 && active < 1.0) active = 1.0;
 }
 
+// Measurement yardstick (bench.py `roofline.yardstick`, scripts/dram_mix.py): a plain grid-stride streaming kernel with
+// the read : write mix of the library's launches -- c == nullptr: copy (8 B read + 8 B written per element, the mix of a
+// single derivative); otherwise one read and two writes (the mix of the fused d/dx + d/dy launch).  DRAM streams the
+// 1 : 2 mix about 7 % below the 1 : 1 copy figure (profiles/r2u_dram_mix_yardstick.txt), which is what a roofline
+// fraction against the copy bandwidth cannot show.  No part of any derivative path.
+__global__ void __launch_bounds__(256) stream_yardstick_kernel(const double2 *__restrict__ a, double2 *__restrict__ b,
+                                                               double2 *__restrict__ c, long n2)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    if (c) {
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += stride) {
+            const double2 v = a[i];
+            b[i] = v;
+            c[i] = make_double2(v.y, v.x);
+        }
+    } else {
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2; i += stride) b[i] = a[i];
+    }
+}
+
+extern "C" int cfd_debug_stream(const double *a, double *b, double *c, long n, void *stream)
+{
+    if (!a || !b || n < 2 || (n & 1) || ((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)c & 15))
+        return fail(CFD_EINVAL, "cfd_debug_stream: needs 16-byte aligned arrays of an even number of doubles");
+    static DeviceInfo dinfo;
+    if (!dinfo.ok) { int rc = device_info(dinfo); if (rc) return rc; }
+    stream_yardstick_kernel<<<16 * dinfo.sms, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const double2 *>(a), reinterpret_cast<double2 *>(b), reinterpret_cast<double2 *>(c), n / 2);
+    CUDA_TRY(cudaGetLastError());
+    return CFD_OK;
+}
+
 // Host-only inspection entry for the CPU tests: the launch shape cfd_apply_xy would pick on a device of `sms` SMs.
 extern "C" int cfd_debug_xy_shape(int nz, int ny, int nx, int sms, int *warps, double *active, int *sub)
 {

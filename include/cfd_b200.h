@@ -215,6 +215,11 @@ long cfd_debug_xy_order(int nz, int nxp, int nyp, double active, int sub, int *o
  * (6, or 7 for short launches), planes in flight of the draw order, and the line cut (0 = whole lines, else x-segment
  * length | y-segment length << 8 in tiles). */
 int cfd_debug_xy_shape(int nz, int ny, int nx, int sms, int *warps, double *active, int *sub);
+/* Measurement yardstick, no part of any derivative path: a plain grid-stride streaming kernel over n doubles (n even,
+ * 16-byte aligned device arrays) with the read : write mix of the library's launches -- c == NULL: b = a (a single
+ * derivative's 8 B read + 8 B written per point); otherwise b and c written from a (the fused d/dx + d/dy launch's 8 +
+ * 16 B).  bench.py times it next to the derivative launches (`roofline.yardstick`). */
+int cfd_debug_stream(const double *a, double *b, double *c, long n, void *stream);
 int cfd_debug_halo_weights(int n, double h, double *w_lo, double *w_hi);
 /* Host-only: chunks of look-ahead (1, 2; 0 = two-pass) the one-pass solve needs for n rows of coeffs[7], and the
  * definition of a scheme -- out[37]: b1,c1,ai,bi,ci,an,bn | two special rows per end | a2,b2,c2 (row 1), am,bm,cm
