@@ -207,6 +207,8 @@ def run_reference(args):
         return
     n = 512 if args.gpus == 1 else 1024
     per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    if args.ref_seconds:
+        per_step = float(args.ref_seconds)
     rates = []
     kind = cores = sample = None
     for i in range(args.warmup + args.steps):
@@ -727,6 +729,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: CPU seconds per step (default: 60 s spread over the steps, 2 .. 20 s each)")
     ap.add_argument("--comm", default="nvlink", choices=["nvlink", "pairwise", "allgather"],
                     help="exchange of the partitioned d/dz: NVLink peer-memory stores from our kernels, NCCL send/recv per "
                          "z-neighbour, or NCCL all-gather")

@@ -430,3 +430,24 @@ def test_xy_launch_shape_rule(shape, warps, cut):
     if cut:
         assert sub.value == (16 | (32 << 8))
     assert act.value >= 1.0
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the driver's reference arm: the reference's own CPU path from oracle/_ref, or the C
+    port when the reference did not compile) prints exactly one JSON line with the contract's keys and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-seconds", "0.5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["metric"].startswith("grid points/sec per derivative") and d["unit"] == "points/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e6 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and "512" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("512^3")
