@@ -451,3 +451,23 @@ def test_bench_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"] and "512" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["config"]["workload"].startswith("512^3")
+
+
+@pytest.mark.parametrize("n", [33, 64, 130, 515])
+def test_kernel_schedule_is_exact_on_cubics(n):
+    """The kernel's schedule (chunked forward sweep, Horner warm-up, look-ahead back-substitution: tests/emulate.py follows
+    kernels.cuh step by step) keeps the scheme's exactness: cubic polynomials are differentiated to round-off and a
+    mirrored line gives the mirrored derivative with the opposite sign -- truncating the look-ahead at 32 rows costs
+    nothing measurable."""
+    h = 0.21
+    x = np.arange(n) * h - 0.3 * n * h
+    rng = np.random.default_rng(n)
+    c = rng.random((5, 4))
+    F = c[:, :1] + c[:, 1:2] * x + c[:, 2:3] * x ** 2 + c[:, 3:4] * x ** 3
+    dF = c[:, 1:2] + 2 * c[:, 2:3] * x + 3 * c[:, 3:4] * x ** 2
+    got = stream_lines(F, PADE, h)
+    assert np.abs(got - dF).max() <= 2e-13 * np.abs(F).max() / h
+    R = rng.random((5, n))
+    a = stream_lines(R, PADE, h)
+    b = stream_lines(R[:, ::-1].copy(), PADE, h)[:, ::-1]
+    assert np.abs(a + b).max() <= 1e-12 * np.abs(a).max()

@@ -164,3 +164,34 @@ def test_order_of_convergence_oracle(axis):
     assert 14.0 < mean_r[-1] < 17.5, mean_r
     assert 6.5 < max_r[-1] < 9.0, max_r
     assert all(r > 8.0 for r in mean_r)
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+@pytest.mark.parametrize("n", [4, 7, 33, 130])
+def test_oracle_structural_properties(axis, n):
+    """Size-independent properties of the scheme the reference implements (code/cuda/kernels.cu:34-44 RHS,
+    near_toeplitz.py:36-50 matrix): the derivative of a constant is zero, polynomials up to degree 3 are differentiated
+    exactly (4th-order interior rows, 3rd-order closure rows), the operator is linear, and mirroring the line mirrors the
+    derivative with the opposite sign (the closures at the two ends are mirror images of each other)."""
+    rng = np.random.default_rng(n + axis)
+    shape = [3, 4, 6]
+    shape[2 - axis] = n
+    h = 0.37
+    x = np.arange(n) * h - 0.4 * n * h
+    idx = [None, None, None]
+    idx[2 - axis] = slice(None)
+    xs = x[tuple(idx)] * np.ones(shape)
+    assert np.abs(O.derivative(np.full(shape, 3.25), axis, h)).max() <= 1e-13
+    c = rng.random(4)
+    poly = c[0] + c[1] * xs + c[2] * xs ** 2 + c[3] * xs ** 3
+    dpoly = c[1] + 2 * c[2] * xs + 3 * c[3] * xs ** 2
+    scale = np.abs(poly).max() / h
+    assert np.abs(O.derivative(poly, axis, h) - dpoly).max() <= 2e-13 * scale
+    f, g = rng.random(shape), rng.random(shape)
+    lin = O.derivative(2.5 * f - 1.5 * g, axis, h) - (2.5 * O.derivative(f, axis, h) - 1.5 * O.derivative(g, axis, h))
+    assert np.abs(lin).max() <= 1e-12 * np.abs(O.derivative(f, axis, h)).max()
+    mirrored = np.flip(O.derivative(np.flip(f, 2 - axis).copy(), axis, h), 2 - axis)
+    assert np.abs(mirrored + O.derivative(f, axis, h)).max() <= 1e-12 * np.abs(O.derivative(f, axis, h)).max()
+    # a quartic is NOT exact at the closures: the test above is sharp
+    if n >= 7:
+        assert np.abs(O.derivative(xs ** 4, axis, h) - 4 * xs ** 3).max() > 1e-6 * np.abs(4 * xs ** 3).max()
